@@ -1,0 +1,93 @@
+/* gpfq_b200.h -- C ABI of libgpfq_b200.so: the B200 (sm_100a) implementation of the GPFQ
+ * per-layer quantization hot path of YixuanSeanZhou/Quantized_Neural_Nets.
+ *
+ * The reference has no FFI: its boundary is the Python call from quantize_neural_net.py:150/:180
+ * into StepAlgorithm._quantize_layer (step_algorithm.py:151-249).  These entry points are what a
+ * binding for that path needs; quantized_neural_nets_b200/_lib.py is the
+ * ctypes binding and INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless its name ends in _host;
+ *   - the library keeps no state between calls except the thread-local last-error string;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ *     the host, so results are valid in stream order;
+ *   - return value 0 = success, non-zero = error (text via gpfq_last_error()).
+ *   - "feature-major" means a (d x ld) fp32 matrix whose row t is calibration column t of the
+ *     reference's (m x d) layer-input matrix, ld >= m, ld % 4 == 0, base 16-byte aligned.
+ */
+#ifndef GPFQ_B200_H
+#define GPFQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPFQ_ABI_VERSION 1
+
+/* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0') */
+enum { GPFQ_MODE_MSQ = 0, GPFQ_MODE_SOFT = 1, GPFQ_MODE_HARD = 2 };
+
+/* solver variants: 0 = blocked direct (exact reference update order, fp32 SIMT),
+ *                  1 = Gram form on tcgen05 tensor cores (split-TF32) */
+enum { GPFQ_SOLVER_DIRECT = 0, GPFQ_SOLVER_GRAM = 1 };
+
+int gpfq_abi_version(void);
+const char* gpfq_last_error(void);
+
+/* Elementwise alphabet map out[i] = quantizer(x[i]); replaces the three quantizer functions
+ * of step_algorithm.py:38-104 for unit parity.  delta is read from device memory. */
+int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta, int32_t K,
+                      int32_t mode, float lam, void* stream);
+
+/* (rows x cols, ld_in) row-major  ->  (cols x ld_out) row-major, columns rows..ld_out-1 zeroed.
+ * Turns the reference's (m x d) layer input (quantize_neural_net.py:291,347) into feature-major. */
+int gpfq_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,
+                       int64_t ld_out, void* stream);
+
+/* Fused unfold(stride = kernel) + row gather + transpose; replaces SaveInputConv2d.__call__
+ * (quantize_neural_net.py:325-350).  in: (B,C,H,W) contiguous.  idx[n_idx]: rows of the
+ * (B*L, C*kh*kw) patch matrix to keep, drawn on the host exactly as the reference does
+ * (np.random.choice with replacement, :340-345).  Channels [c_begin, c_end) select one group.
+ * out: feature-major ((c_end-c_begin)*kh*kw  x  ld_out), row order (c, ki, kj) as nn.Unfold. */
+int gpfq_im2col_gather_f32(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh,
+                           int32_t kw, int32_t dil_h, int32_t dil_w, int32_t pad_h, int32_t pad_w,
+                           int32_t c_begin, int32_t c_end, const int64_t* idx, int64_t n_idx,
+                           float* out, int64_t ld_out, void* stream);
+
+/* Workspace (bytes) gpfq_solve_f32 needs for `n_rows` neurons of a (d, m) problem. */
+size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m);
+
+/* The greedy path-following solve: replaces StepAlgorithm._quantization
+ * (step_algorithm.py:107-148) plus the residual norms of _quantize_layer (:216-219) for
+ * neurons [n0, n1) of W.
+ *   W (N x d, ldw), X / Xq feature-major (d x ldx), *delta on device, K = 2^(bits-1).
+ *   Q (N x d, ldq): rows n0..n1-1 written (fp32 alphabet values, as the reference stores them).
+ *   levels: optional int8 (N x d, ld = d) signed level indices, rows n0..n1-1 (may be NULL).
+ *   row_err2: optional double[n1-n0], ||u_n||^2 of the final residual (may be NULL).
+ *   U_out: optional fp32 ((n1-n0) x ldu) row-major final residual matrix (may be NULL).
+ */
+int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq,
+                   int64_t ldx, int32_t N, int32_t d, int32_t m, int32_t n0, int32_t n1,
+                   const float* delta, int32_t K, int32_t mode, float lam, float* Q, int64_t ldq,
+                   int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Optional per-kernel timing for bench.py's roofline object.  Between gpfq_profile_begin() and
+ * gpfq_profile_end() every sweep launch of the direct solver is bracketed by CUDA events on its
+ * own stream.  gpfq_profile_end() waits for them and fills out[8] = { sweep launches, sweep ms,
+ * sweep algorithmic HBM bytes, sweep fp32 instructions (5 per neuron*sample*feature), other
+ * solver-kernel launches, 0, 0, 0 }.  Not for use inside a timed region. */
+int gpfq_profile_begin(void);
+int gpfq_profile_end(double* out_host);
+
+/* Number of kernels the library has launched so far on behalf of this process (bench.py's
+ * gpu_launches counter). */
+int64_t gpfq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPFQ_B200_H */

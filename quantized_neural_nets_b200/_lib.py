@@ -1,0 +1,90 @@
+"""ctypes binding of libgpfq_b200.so (C ABI declared in include/gpfq_b200.h).
+
+The CUDA library is the product; there is no CPU or PyTorch fallback.  If the shared object
+has not been built (``python -c "import __graft_entry__ as g; g.build()"``) importing this
+module raises ImportError, and every compute call raises RuntimeError when no CUDA device is
+present."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpfq_b200.so")
+
+MODE_MSQ, MODE_SOFT, MODE_HARD = 0, 1, 2
+SOLVER_DIRECT, SOLVER_GRAM = 0, 1
+
+c_ptr = ctypes.c_void_p  # device pointers travel as integers
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_f32 = ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/gpfq_b200.h one to one
+SIGNATURES = {
+    "gpfq_abi_version": (c_i32, []),
+    "gpfq_last_error": (ctypes.c_char_p, []),
+    "gpfq_launch_count": (c_i64, []),
+    "gpfq_profile_begin": (c_i32, []),
+    "gpfq_profile_end": (c_i32, [ctypes.POINTER(ctypes.c_double)]),
+    "gpfq_quantize_f32": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, c_ptr]),
+    "gpfq_transpose_f32": (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
+    "gpfq_im2col_gather_f32": (c_i32, [c_ptr] + [c_i32] * 12 + [c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
+    "gpfq_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
+    "gpfq_solve_f32": (c_i32, [c_i32, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
+                               c_ptr, c_i32, c_i32, c_f32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                               ctypes.c_size_t, c_ptr]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA library first "
+            "(python -c \"import __graft_entry__ as g; g.build()\").  There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libgpfq_b200: " + lib.gpfq_last_error().decode("utf-8", "replace"))
+
+
+def require_cuda(*tensors):
+    if not torch.cuda.is_available():
+        raise RuntimeError("libgpfq_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    for t in tensors:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise TypeError(f"expected a CUDA float32 tensor, got {t.device} {t.dtype}")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def launch_count():
+    return int(lib.gpfq_launch_count())
+
+
+def profile_begin():
+    check(lib.gpfq_profile_begin())
+
+
+def profile_end():
+    """-> dict(sweep_launches, sweep_ms, sweep_bytes, sweep_fp32_instr, other_launches)"""
+    out = (ctypes.c_double * 8)()
+    check(lib.gpfq_profile_end(out))
+    return dict(sweep_launches=int(out[0]), sweep_ms=out[1], sweep_bytes=out[2], sweep_fp32_instr=out[3],
+                other_launches=int(out[4]))

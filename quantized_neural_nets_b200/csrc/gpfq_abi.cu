@@ -1,0 +1,231 @@
+// libgpfq_b200: ABI plumbing + the small data-movement kernels
+// (alphabet map, transpose to feature-major, fused conv im2col + patch gather).
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "gpfq_common.cuh"
+
+namespace gpfq {
+
+static thread_local std::string g_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+struct ProfileRec {
+    cudaEvent_t a, b;
+    double bytes, instr;
+};
+static bool g_profile = false;
+static std::vector<ProfileRec> g_recs;
+static double g_other = 0;
+static cudaEvent_t g_pending = nullptr;
+
+bool profile_on() { return g_profile; }
+void profile_mark_begin(cudaStream_t stream) {
+    if (!g_profile) return;
+    cudaEventCreate(&g_pending);
+    cudaEventRecord(g_pending, stream);
+}
+void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr) {
+    if (!g_profile || !g_pending) return;
+    ProfileRec r{g_pending, nullptr, alg_bytes, fp32_instr};
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.b, stream);
+    g_recs.push_back(r);
+    g_pending = nullptr;
+}
+void profile_count_other(int n) {
+    if (g_profile) g_other += n;
+}
+
+// cuTensorMapEncodeTiled is a driver-API symbol; resolve it through the runtime so that the
+// library has no link-time dependency on libcuda.so (it must load on a box without a driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (EncodeTiledFn)p;
+    return fn;
+}
+
+int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    GPFQ_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this CUDA driver");
+    GPFQ_REQUIRE(((uintptr_t)base & 15) == 0 && (ld % 4) == 0, "tensor map: base must be 16-byte aligned and ld %% 4 == 0");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GPFQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void quantize_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n,
+                                const float* __restrict__ delta_p, float Kf, int mode, float lam) {
+    const float delta = *delta_p;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int lv;
+        out[i] = alphabet_map(x[i], delta, Kf, mode, lam, &lv);
+    }
+}
+
+// (rows x cols) -> (cols x ld_out); pad columns rows..ld_out-1 are zero-filled.
+__global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
+                                 float* __restrict__ out, int64_t ld_out) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        int64_t r = r0 + ty + k, c = c0 + tx;
+        tile[ty + k][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        int64_t c = c0 + ty + k, r = r0 + tx;
+        if (c < cols && r < ld_out) out[c * ld_out + r] = tile[tx][ty + k];
+    }
+}
+
+// One thread per kept patch row r (coalesced stores along the feature-major row), grid.y walks
+// the C*kh*kw features.  Patch geometry is nn.Unfold with stride == kernel_size
+// (quantize_neural_net.py:320): patch l of image b starts at (l / Lw * kh - pad_h, l % Lw * kw - pad_w).
+__global__ void im2col_gather_kernel(const float* __restrict__ in, int C, int H, int W, int kh, int kw, int dil_h,
+                                     int dil_w, int pad_h, int pad_w, int c_begin, int n_feat, int Lw, int L,
+                                     const int64_t* __restrict__ idx, int64_t n_idx, float* __restrict__ out,
+                                     int64_t ld_out, int feats_per_block) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ld_out) return;
+    const int f0 = blockIdx.y * feats_per_block;
+    const int f1 = min(f0 + feats_per_block, n_feat);
+    if (r >= n_idx) {
+        for (int f = f0; f < f1; ++f) out[(int64_t)f * ld_out + r] = 0.f;
+        return;
+    }
+    const int64_t p = idx[r];
+    const int b = (int)(p / L);
+    const int l = (int)(p % L);
+    const int y0 = (l / Lw) * kh - pad_h;
+    const int x0 = (l % Lw) * kw - pad_w;
+    const float* img = in + (int64_t)b * C * H * W;
+    const int kk = kh * kw;
+    for (int f = f0; f < f1; ++f) {
+        const int c = c_begin + f / kk;
+        const int ki = (f % kk) / kw, kj = f % kw;
+        const int y = y0 + ki * dil_h, x = x0 + kj * dil_w;
+        float v = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + ((int64_t)c * H + y) * W + x);
+        out[(int64_t)f * ld_out + r] = v;
+    }
+}
+
+}  // namespace gpfq
+
+using namespace gpfq;
+
+extern "C" {
+
+int gpfq_abi_version(void) { return GPFQ_ABI_VERSION; }
+const char* gpfq_last_error(void) { return g_error.c_str(); }
+int64_t gpfq_launch_count(void) { return g_launches.load(); }
+
+int gpfq_profile_begin(void) {
+    g_recs.clear();
+    g_other = 0;
+    g_profile = true;
+    return 0;
+}
+
+int gpfq_profile_end(double* out_host) {
+    g_profile = false;
+    double ms_total = 0, bytes = 0, instr = 0;
+    for (auto& r : g_recs) {
+        GPFQ_CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0;
+        GPFQ_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_total += ms;
+        bytes += r.bytes;
+        instr += r.instr;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    if (out_host) {
+        out_host[0] = (double)g_recs.size();
+        out_host[1] = ms_total;
+        out_host[2] = bytes;
+        out_host[3] = instr;
+        out_host[4] = g_other;
+        out_host[5] = out_host[6] = out_host[7] = 0;
+    }
+    g_recs.clear();
+    return 0;
+}
+
+int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
+                      void* stream) {
+    GPFQ_REQUIRE(mode >= 0 && mode <= 2, "gpfq_quantize_f32: bad mode %d", mode);
+    GPFQ_REQUIRE(n >= 0 && K >= 1, "gpfq_quantize_f32: bad size/K");
+    if (n == 0) return 0;
+    int blocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
+    quantize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n, delta, (float)K, mode, lam);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int gpfq_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                       void* stream) {
+    GPFQ_REQUIRE(rows >= 0 && cols >= 0 && ld_in >= cols && ld_out >= rows, "gpfq_transpose_f32: bad shape");
+    if (rows == 0 || cols == 0) return 0;
+    dim3 grid((unsigned)ceil_div(ld_out, 32), (unsigned)ceil_div(cols, 32));
+    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, rows, cols, ld_in, out, ld_out);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int gpfq_im2col_gather_f32(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                           int32_t dil_h, int32_t dil_w, int32_t pad_h, int32_t pad_w, int32_t c_begin, int32_t c_end,
+                           const int64_t* idx, int64_t n_idx, float* out, int64_t ld_out, void* stream) {
+    GPFQ_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && dil_h > 0 && dil_w > 0,
+                 "gpfq_im2col_gather_f32: bad geometry");
+    GPFQ_REQUIRE(0 <= c_begin && c_begin < c_end && c_end <= C, "gpfq_im2col_gather_f32: bad channel range");
+    GPFQ_REQUIRE(n_idx >= 0 && ld_out >= n_idx, "gpfq_im2col_gather_f32: ld_out < n_idx");
+    const int Lh = (H + 2 * pad_h - dil_h * (kh - 1) - 1) / kh + 1;
+    const int Lw = (W + 2 * pad_w - dil_w * (kw - 1) - 1) / kw + 1;
+    GPFQ_REQUIRE(Lh > 0 && Lw > 0, "gpfq_im2col_gather_f32: kernel larger than padded input");
+    if (ld_out == 0) return 0;
+    const int n_feat = (c_end - c_begin) * kh * kw;
+    const int fpb = 16;
+    dim3 grid((unsigned)ceil_div(ld_out, 256), (unsigned)ceil_div(n_feat, fpb));
+    im2col_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, H, W, kh, kw, dil_h, dil_w, pad_h, pad_w,
+                                                                 c_begin, n_feat, Lw, Lh * Lw, idx, n_idx, out, ld_out,
+                                                                 fpb);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

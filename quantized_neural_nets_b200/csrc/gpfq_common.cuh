@@ -1,0 +1,140 @@
+// Shared host/device helpers for libgpfq_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/gpfq_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgpfq_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace gpfq {
+
+// ---------------------------------------------------------------- host side: errors / counters
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define GPFQ_CUDA_TRY(expr)                                                                 \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            gpfq::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 2;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+#define GPFQ_REQUIRE(cond, ...)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            gpfq::set_error(__VA_ARGS__);  \
+            return 1;                      \
+        }                                  \
+    } while (0)
+
+#define GPFQ_CHECK_LAUNCH()                 \
+    do {                                    \
+        gpfq::count_launch();               \
+        GPFQ_CUDA_TRY(cudaGetLastError());  \
+    } while (0)
+
+// bench-only per-launch timing of the dominant kernel (see gpfq_profile_begin/end)
+bool profile_on();
+void profile_mark_begin(cudaStream_t stream);
+void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr);
+void profile_count_other(int n);
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---------------------------------------------------------------- device side: alphabet maps
+// All arithmetic is fp32 with explicit round-to-nearest intrinsics so that nvcc can neither
+// contract a*b+c into an FMA nor replace the true divisions: the reference's ATen ops round
+// after every elementwise operation (step_algorithm.py:56,78-81,103-104).
+
+__device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+
+// min(|floor(x/delta + 0.5)|, K)   (step_algorithm.py:56)
+__device__ __forceinline__ float level_count(float x, float delta, float Kf) {
+    float z = floorf(__fadd_rn(__fdiv_rn(x, delta), 0.5f));
+    return fminf(fabsf(z), Kf);
+}
+
+// sign(x) * max(|x| - lam, 0)       (step_algorithm.py:79,103)
+__device__ __forceinline__ float shrinkf(float x, float lam) {
+    return __fmul_rn(sgnf(x), fmaxf(__fsub_rn(fabsf(x), lam), 0.f));
+}
+
+// Returns the alphabet value; *level receives the signed level index
+// (msq/soft: value == level*delta; hard: value == sign*(lam + (|level|-1)*delta), level 0 == pruned).
+__device__ __forceinline__ float alphabet_map(float x, float delta, float Kf, int mode, float lam, int* level) {
+    if (mode == GPFQ_MODE_MSQ) {
+        float k = level_count(x, delta, Kf);
+        float s = sgnf(x);
+        *level = (int)(s * k);
+        return __fmul_rn(__fmul_rn(s, delta), k);
+    } else if (mode == GPFQ_MODE_SOFT) {
+        float y = shrinkf(x, lam);
+        float k = level_count(y, delta, Kf);
+        float s = sgnf(y);
+        *level = (int)(s * k);
+        return __fmul_rn(__fmul_rn(s, delta), k);
+    } else {
+        // F.threshold(|x|, lam, 0) * sign(x)
+        float kept = __fmul_rn((fabsf(x) > lam) ? fabsf(x) : 0.f, sgnf(x));
+        float y = shrinkf(kept, lam);
+        float k = level_count(y, delta, Kf);
+        float s = sgnf(kept);
+        float on = (fabsf(kept) > lam) ? 1.f : 0.f;
+        *level = (int)(s * on * (k + 1.f));
+        return __fmul_rn(__fmul_rn(s, __fadd_rn(lam, __fmul_rn(delta, k))), on);
+    }
+}
+
+// ---------------------------------------------------------------- device side: mbarrier + TMA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 2-D tiled TMA load: box lands densely ([rows][cols]) at `dst`; c0 = column (inner), c1 = row.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// Host: encode a 2-D fp32 tensor map over a (rows x cols) row-major matrix with leading dimension ld.
+int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                       int box_cols);
+
+}  // namespace gpfq

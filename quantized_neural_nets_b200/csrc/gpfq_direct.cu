@@ -1,0 +1,548 @@
+// Blocked direct greedy path-following solver (GPFQ_SOLVER_DIRECT).
+//
+// Reference algorithm (step_algorithm.py:140-148), per feature t:
+//     U += w_t (x) x_t ;  a = U xq_t / ||xq_t||^2 ;  q_t = Q(a) ;  U -= q_t (x) xq_t
+//
+// B200 formulation.  Features are processed in blocks of kB = 32.  For block [t0, t0+kB):
+//   (1) sweep kernel  : P[n][s] = <U_{t0-1}[n,:], xq_{t0+s}>  for all s in the block -- direct fp32
+//                       dot products against the CURRENT residual, accumulated in short fp32
+//                       chains and combined in fp64 in a fixed order (deterministic);
+//   (2) recur kernel  : the kB sequential decisions of one neuron are made by one warp from P and
+//                       the in-block Gram entries G = Xq_blk^T X_blk, H = Xq_blk^T Xq_blk (fp64, exact
+//                       products):   a_t = fl32(p_t + w_t G_tt) / ||xq_t||^2 ;  q_t = Q(a_t) ;
+//                       p_s += w_t G_st - q_t H_st  (s > t);
+//   (3) next sweep    : applies the kB rank-1 updates to U in the reference's order with the
+//                       reference's roundings (mul, add, mul, sub -- never contracted to FMA), so U is
+//                       bit-identical to the reference's U whenever the decisions agree, then computes
+//                       P for the following block in the same pass (U is read and written ONCE per
+//                       block instead of five times per feature).
+// The sweep is an fp32-issue-bound streaming kernel: 5 fp32 instructions per (neuron, sample,
+// feature) and 8/kB bytes of U traffic; X / Xq block tiles are staged by TMA, double-buffered.
+//
+// U lives in a solver-private tiled layout  U[j/4][Npad][4]  so that a warp whose lanes own 32
+// consecutive neurons reads/writes 512 contiguous bytes per column quad.
+#include <algorithm>
+
+#include "gpfq_common.cuh"
+
+namespace gpfq {
+
+constexpr int kB = 32;            // greedy steps per block
+constexpr int kThreads = 256;     // sweep CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kJS = 128;          // calibration columns per smem stage
+constexpr int kColsPerWarp = kJS / kWarps;       // 16
+constexpr int kChunksPerStage = kColsPerWarp / 4;  // 4 column quads per warp per stage
+constexpr int kStageFloats = 3 * kB * kJS;       // x_prev | xq_prev | xq_next
+constexpr int kRedStride = kB + 1;
+constexpr int kMaxTJ = 4096;      // keeps every fp32 accumulation chain <= 512 terms
+
+struct DirectPlan {
+    int R, TN, n_tiles, TJ, j_tiles, nblk, gram_slices, gram_slice_len;
+    int64_t Npad, mpad;
+    size_t off_U, off_G, off_H, off_norm, off_gpart, off_part, off_epart, total;
+};
+
+static DirectPlan make_plan(int n_rows, int d, int m) {
+    DirectPlan p{};
+    p.mpad = round_up(std::max(m, 1), kJS);
+    p.Npad = round_up(std::max(n_rows, 1), 128);
+    p.nblk = (int)ceil_div(d, kB);
+    const int max_jt = (int)(p.mpad / kJS);
+    p.R = 1;
+    for (int R : {4, 2, 1}) {
+        int nt = (int)ceil_div(n_rows, 32 * R);
+        if ((int64_t)nt * max_jt >= 140 || R == 1) {
+            p.R = R;
+            break;
+        }
+    }
+    p.TN = 32 * p.R;
+    p.n_tiles = (int)ceil_div(n_rows, p.TN);
+    int want = std::max(1, (2 * 148 + p.n_tiles - 1) / p.n_tiles);
+    int jt = std::min(max_jt, want);
+    jt = std::max<int>(jt, (int)ceil_div(p.mpad, kMaxTJ));
+    p.TJ = (int)round_up(ceil_div(p.mpad, jt), kJS);
+    p.j_tiles = (int)ceil_div(p.mpad, p.TJ);
+    // block-Gram kernel: split the m-long dot products into slices so the grid fills the GPU
+    int gs = std::max(1, std::min<int>((int)ceil_div(m, 256), (int)ceil_div(2 * 148, p.nblk)));
+    p.gram_slice_len = (int)round_up(ceil_div(std::max(m, 1), gs), 32);
+    p.gram_slices = (int)ceil_div(std::max(m, 1), p.gram_slice_len);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    };
+    p.off_U = take((size_t)p.mpad * p.Npad * sizeof(float));
+    p.off_G = take((size_t)p.nblk * kB * kB * sizeof(double));
+    p.off_H = take((size_t)p.nblk * kB * kB * sizeof(double));
+    p.off_norm = take((size_t)p.nblk * kB * sizeof(float));
+    p.off_gpart = take((size_t)p.nblk * p.gram_slices * 2 * kB * kB * sizeof(double));
+    p.off_part = take((size_t)p.j_tiles * p.Npad * kB * sizeof(double));
+    p.off_epart = take((size_t)p.j_tiles * p.Npad * sizeof(double));
+    p.total = off;
+    return p;
+}
+
+size_t direct_workspace_bytes(int n_rows, int d, int m) { return make_plan(n_rows, d, m).total; }
+
+// ------------------------------------------------------------------------------------------
+// Block Gram entries, fp64.  For block b and s,t in [0,kB):
+//   G[b][t][s] = <xq_{t0+s}, x_{t0+t}>     H[b][t][s] = <xq_{t0+s}, xq_{t0+t}>
+// grid (nblk, slices); each thread owns a 2x2 (t,s) sub-tile of both matrices.
+__global__ void __launch_bounds__(256) block_gram_kernel(const float* __restrict__ X, const float* __restrict__ Xq,
+                                                         int64_t ldx, int d, int m, int slice_len, int slices,
+                                                         double* __restrict__ gpart) {
+    __shared__ double xs[kB][33];
+    __shared__ double xqs[kB][33];
+    const int blk = blockIdx.x, sl = blockIdx.y;
+    const int t0 = blk * kB;
+    const int jb = sl * slice_len, je = min(jb + slice_len, m);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double g00 = 0, g01 = 0, g10 = 0, g11 = 0, h00 = 0, h01 = 0, h10 = 0, h11 = 0;
+    for (int j0 = jb; j0 < je; j0 += 32) {
+        const int col = threadIdx.x & 31;
+#pragma unroll
+        for (int r = threadIdx.x >> 5; r < kB; r += 8) {
+            const bool ok = (t0 + r < d) && (j0 + col < je);
+            const int64_t a = (int64_t)(t0 + r) * ldx + j0 + col;
+            xs[r][col] = ok ? (double)X[a] : 0.0;
+            xqs[r][col] = ok ? (double)Xq[a] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const double a0 = xqs[2 * tx][j], a1 = xqs[2 * tx + 1][j];     // xq_s
+            const double b0 = xs[2 * ty][j], b1 = xs[2 * ty + 1][j];       // x_t
+            const double c0 = xqs[2 * ty][j], c1 = xqs[2 * ty + 1][j];     // xq_t
+            g00 = fma(a0, b0, g00); g01 = fma(a1, b0, g01); g10 = fma(a0, b1, g10); g11 = fma(a1, b1, g11);
+            h00 = fma(a0, c0, h00); h01 = fma(a1, c0, h01); h10 = fma(a0, c1, h10); h11 = fma(a1, c1, h11);
+        }
+        __syncthreads();
+    }
+    double* gp = gpart + ((int64_t)(blk * slices + sl) * 2) * kB * kB;
+    double* hp = gp + kB * kB;
+    const int t = 2 * ty, s = 2 * tx;
+    gp[t * kB + s] = g00; gp[t * kB + s + 1] = g01; gp[(t + 1) * kB + s] = g10; gp[(t + 1) * kB + s + 1] = g11;
+    hp[t * kB + s] = h00; hp[t * kB + s + 1] = h01; hp[(t + 1) * kB + s] = h10; hp[(t + 1) * kB + s + 1] = h11;
+}
+
+// Fixed-order sum over slices; norm32[t] = (sqrt(fl32(sum xq_t^2)))^2 as linalg.norm(.)**2 gives
+// (step_algorithm.py:142).
+__global__ void block_gram_finish_kernel(const double* __restrict__ gpart, int slices, int nblk,
+                                         double* __restrict__ G, double* __restrict__ H, float* __restrict__ norm32) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nblk * kB * kB) return;
+    const int blk = e / (kB * kB), r = e % (kB * kB);
+    double g = 0, h = 0;
+    for (int sl = 0; sl < slices; ++sl) {
+        const double* gp = gpart + ((int64_t)(blk * slices + sl) * 2) * kB * kB;
+        g += gp[r];
+        h += gp[kB * kB + r];
+    }
+    G[e] = g;
+    H[e] = h;
+    const int t = r / kB, s = r % kB;
+    if (t == s) {
+        const float root = sqrtf((float)h);
+        norm32[blk * kB + t] = __fmul_rn(root, root);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// One warp per neuron, lane s owns p_s of the current block.
+struct RecurArgs {
+    const float* W;      // row 0 of the shard
+    int64_t ldw;
+    float* Q;            // row 0 of the shard
+    int64_t ldq;
+    int8_t* levels;      // row 0 of the shard or NULL
+    int64_t ldl;
+    const double* part;  // [j_tiles][Npad][kB]
+    const double* G;     // this block: [kB][kB]
+    const double* H;
+    const float* norm32; // this block: [kB]
+    const float* delta;
+    int64_t Npad;
+    int n_rows, d, t0, bvalid, j_tiles, first, mode;
+    float Kf, lam;
+};
+
+__global__ void __launch_bounds__(128) recur_kernel(RecurArgs a) {
+    __shared__ double Gs[kB][kB + 1];
+    __shared__ double Hs[kB][kB + 1];
+    __shared__ float ns[kB];
+    for (int e = threadIdx.x; e < kB * kB; e += blockDim.x) {
+        Gs[e / kB][e % kB] = a.G[e];
+        Hs[e / kB][e % kB] = a.H[e];
+    }
+    if (threadIdx.x < kB) ns[threadIdx.x] = a.norm32[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= a.n_rows) return;
+    double p = 0.0;
+    if (!a.first) {
+        const double* src = a.part + (int64_t)n * kB + lane;
+        const int64_t stride = a.Npad * kB;
+        int jt = 0;
+        for (; jt + 4 <= a.j_tiles; jt += 4) {
+            const double v0 = src[(int64_t)jt * stride], v1 = src[(int64_t)(jt + 1) * stride];
+            const double v2 = src[(int64_t)(jt + 2) * stride], v3 = src[(int64_t)(jt + 3) * stride];
+            p += v0; p += v1; p += v2; p += v3;      // fixed order
+        }
+        for (; jt < a.j_tiles; ++jt) p += src[(int64_t)jt * stride];
+    }
+    const int t_mine = a.t0 + lane;
+    const float w = (t_mine < a.d) ? a.W[(int64_t)n * a.ldw + t_mine] : 0.f;
+    const float delta = *a.delta;
+    float q_mine = 0.f;
+    int lv_mine = 0;
+    for (int t = 0; t < a.bvalid; ++t) {
+        const double pt = __shfl_sync(0xffffffffu, p, t);
+        const float wt = __shfl_sync(0xffffffffu, w, t);
+        const double dot = fma((double)wt, Gs[t][t], pt);   // <u_{t-1} + w_t x_t, xq_t>
+        const float nrm = ns[t];
+        const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;   // step_algorithm.py:143-146
+        int lv;
+        const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv);
+        if (lane == t) {
+            q_mine = q;
+            lv_mine = lv;
+        }
+        if (lane > t) {
+            p = fma((double)wt, Gs[t][lane], p);
+            p = fma(-(double)q, Hs[t][lane], p);
+        }
+    }
+    if (t_mine < a.d) {
+        a.Q[(int64_t)n * a.ldq + t_mine] = q_mine;
+        if (a.levels) a.levels[(int64_t)n * a.ldl + t_mine] = (int8_t)lv_mine;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct SweepArgs {
+    const float* W;   // row 0 of the shard
+    int64_t ldw;
+    const float* Q;   // row 0 of the shard
+    int64_t ldq;
+    float* U;         // tiled [mpad/4][Npad][4]
+    double* part;     // [j_tiles][Npad][kB]
+    double* epart;    // [j_tiles][Npad]
+    int64_t Npad, mpad;
+    int n_rows, d, t0, bvalid, TJ;
+    int first;        // block 0: U starts at zero, nothing to load
+    int has_next;     // compute P for block t0 + kB
+    int store_u;      // write U back
+    int want_err;     // accumulate ||u_n||^2 (last block)
+};
+
+template <int R>
+__global__ void __launch_bounds__(kThreads, 1)
+sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXq, const SweepArgs a) {
+    constexpr int TN = 32 * R;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // 2 "stage full" barriers
+    float* base = reinterpret_cast<float*>(smem_raw + 128);
+    float* wsm = base + 2 * kStageFloats;                             // [kB/4][TN] float4
+    float* qsm = wsm + kB * TN;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntile = blockIdx.y, jt = blockIdx.x;
+    const int64_t jbeg = (int64_t)jt * a.TJ;
+    const int64_t jend = min(jbeg + (int64_t)a.TJ, a.mpad);
+    const int nst = (int)((jend - jbeg) / kJS);
+    const int row0 = ntile * TN;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const uint32_t stage_bytes = (uint32_t)((2 + (a.has_next ? 1 : 0)) * kB * kJS * sizeof(float));
+    auto issue = [&](int st) {
+        float* buf = base + (st & 1) * kStageFloats;
+        uint64_t* bar = &bars[st & 1];
+        const int col = (int)(jbeg + (int64_t)st * kJS);
+        mbar_expect_tx(bar, stage_bytes);
+        tma_load_2d(buf, &tmX, col, a.t0, bar);
+        tma_load_2d(buf + kB * kJS, &tmXq, col, a.t0, bar);
+        if (a.has_next) tma_load_2d(buf + 2 * kB * kJS, &tmXq, col, a.t0 + kB, bar);
+    };
+    if (tid == 0 && nst > 0) issue(0);
+
+    // w / q of this block: smem float4 slot (g, nl) = steps 4g..4g+3 of local neuron nl
+    for (int e = tid; e < TN * (kB / 4); e += kThreads) {
+        const int nl = e >> 3, g = e & 7;
+        const int row = row0 + nl;
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), qv = wv;
+        if (row < a.n_rows) {
+            const float* wp = a.W + (int64_t)row * a.ldw;
+            const float* qp = a.Q + (int64_t)row * a.ldq;
+            const int t = a.t0 + 4 * g;
+            if (t + 0 < a.d) { wv.x = wp[t + 0]; qv.x = qp[t + 0]; }
+            if (t + 1 < a.d) { wv.y = wp[t + 1]; qv.y = qp[t + 1]; }
+            if (t + 2 < a.d) { wv.z = wp[t + 2]; qv.z = qp[t + 2]; }
+            if (t + 3 < a.d) { wv.w = wp[t + 3]; qv.w = qp[t + 3]; }
+        }
+        reinterpret_cast<float4*>(wsm)[g * TN + nl] = wv;
+        reinterpret_cast<float4*>(qsm)[g * TN + nl] = qv;
+    }
+    __syncthreads();
+
+    float P[R][kB];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int s = 0; s < kB; ++s) P[i][s] = 0.f;
+    double esum[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) esum[i] = 0.0;
+
+    float4* U4 = reinterpret_cast<float4*>(a.U);
+    const int nq = nst * kChunksPerStage;
+    const int nb4 = (a.bvalid + 3) >> 2;
+    auto u_index = [&](int q) -> int64_t {
+        const int st = q / kChunksPerStage, c = q % kChunksPerStage;
+        const int64_t j = jbeg + (int64_t)st * kJS + warp * kColsPerWarp + c * 4;
+        return (j >> 2) * a.Npad + row0 + lane;
+    };
+
+    float4 ucur[R], unext[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) ucur[i] = unext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!a.first && nq > 0) {
+        const int64_t idx = u_index(0);
+#pragma unroll
+        for (int i = 0; i < R; ++i) ucur[i] = U4[idx + 32 * i];
+    }
+
+    for (int q = 0; q < nq; ++q) {
+        const int st = q / kChunksPerStage, c = q % kChunksPerStage;
+        if (c == 0) {
+            if (tid == 0 && st + 1 < nst) issue(st + 1);
+            mbar_wait(&bars[st & 1], (uint32_t)((st >> 1) & 1));
+        }
+        if (!a.first && q + 1 < nq) {
+            const int64_t idx = u_index(q + 1);
+#pragma unroll
+            for (int i = 0; i < R; ++i) unext[i] = U4[idx + 32 * i];
+        }
+        const float* buf = base + (st & 1) * kStageFloats;
+        const int jl = warp * kColsPerWarp + c * 4;
+        const float* sx = buf + jl;
+        const float* sxq = buf + kB * kJS + jl;
+        const float* sxn = buf + 2 * kB * kJS + jl;
+
+        // (3) apply the kB rank-1 pairs of this block, reference order and roundings
+#pragma unroll 2
+        for (int g = 0; g < nb4; ++g) {
+            float4 wv[R], qv[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                wv[i] = reinterpret_cast<const float4*>(wsm)[g * TN + lane + 32 * i];
+                qv[i] = reinterpret_cast<const float4*>(qsm)[g * TN + lane + 32 * i];
+            }
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) {
+                const float4 xs = *reinterpret_cast<const float4*>(sx + (4 * g + ss) * kJS);
+                const float4 xq = *reinterpret_cast<const float4*>(sxq + (4 * g + ss) * kJS);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const float w = ss == 0 ? wv[i].x : ss == 1 ? wv[i].y : ss == 2 ? wv[i].z : wv[i].w;
+                    const float qq = ss == 0 ? qv[i].x : ss == 1 ? qv[i].y : ss == 2 ? qv[i].z : qv[i].w;
+                    ucur[i].x = __fsub_rn(__fadd_rn(ucur[i].x, __fmul_rn(w, xs.x)), __fmul_rn(qq, xq.x));
+                    ucur[i].y = __fsub_rn(__fadd_rn(ucur[i].y, __fmul_rn(w, xs.y)), __fmul_rn(qq, xq.y));
+                    ucur[i].z = __fsub_rn(__fadd_rn(ucur[i].z, __fmul_rn(w, xs.z)), __fmul_rn(qq, xq.z));
+                    ucur[i].w = __fsub_rn(__fadd_rn(ucur[i].w, __fmul_rn(w, xs.w)), __fmul_rn(qq, xq.w));
+                }
+            }
+        }
+        if (a.store_u) {
+            const int64_t idx = u_index(q);
+#pragma unroll
+            for (int i = 0; i < R; ++i) U4[idx + 32 * i] = ucur[i];
+        }
+        // (1) dot products of the updated residual against the next block's xq columns
+        if (a.has_next) {
+#pragma unroll
+            for (int s = 0; s < kB; ++s) {
+                const float4 xn = *reinterpret_cast<const float4*>(sxn + s * kJS);
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    float acc = P[i][s];
+                    acc = fmaf(ucur[i].x, xn.x, acc);
+                    acc = fmaf(ucur[i].y, xn.y, acc);
+                    acc = fmaf(ucur[i].z, xn.z, acc);
+                    acc = fmaf(ucur[i].w, xn.w, acc);
+                    P[i][s] = acc;
+                }
+            }
+        }
+        if (a.want_err) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                float e = ucur[i].x * ucur[i].x;
+                e = fmaf(ucur[i].y, ucur[i].y, e);
+                e = fmaf(ucur[i].z, ucur[i].z, e);
+                e = fmaf(ucur[i].w, ucur[i].w, e);
+                esum[i] += (double)e;
+            }
+        }
+        if (c == kChunksPerStage - 1) __syncthreads();   // stage buffer may be refilled
+#pragma unroll
+        for (int i = 0; i < R; ++i) ucur[i] = unext[i];
+    }
+    __syncthreads();
+
+    // cross-warp combine (the 8 warps own disjoint column ranges), fixed order, fp64
+    if (a.has_next) {
+        float* red = base;   // [kWarps][TN][kRedStride], aliases the stage buffers
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int s = 0; s < kB; ++s) red[(warp * TN + lane + 32 * i) * kRedStride + s] = P[i][s];
+        __syncthreads();
+        for (int e = tid; e < TN * kB; e += kThreads) {
+            const int n = e / kB, s = e % kB;
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) acc += (double)red[(w * TN + n) * kRedStride + s];
+            a.part[((int64_t)jt * a.Npad + row0 + n) * kB + s] = acc;
+        }
+    }
+    if (a.want_err) {
+        __syncthreads();
+        double* red2 = reinterpret_cast<double*>(base);   // [kWarps][TN]
+#pragma unroll
+        for (int i = 0; i < R; ++i) red2[warp * TN + lane + 32 * i] = esum[i];
+        __syncthreads();
+        for (int n = tid; n < TN; n += kThreads) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) acc += red2[w * TN + n];
+            a.epart[(int64_t)jt * a.Npad + row0 + n] = acc;
+        }
+    }
+}
+
+template <int R>
+static size_t sweep_smem_bytes() {
+    constexpr int TN = 32 * R;
+    size_t main_bytes = (size_t)(2 * kStageFloats + 2 * kB * TN) * sizeof(float);
+    size_t red_bytes = (size_t)kWarps * TN * kRedStride * sizeof(float);
+    return 128 + std::max(main_bytes, red_bytes);
+}
+
+__global__ void err_finish_kernel(const double* __restrict__ epart, int j_tiles, int64_t Npad, int n_rows,
+                                  double* __restrict__ row_err2) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_rows) return;
+    double acc = 0.0;
+    for (int jt = 0; jt < j_tiles; ++jt) acc += epart[(int64_t)jt * Npad + n];
+    row_err2[n] = acc;
+}
+
+__global__ void untile_kernel(const float* __restrict__ U, int64_t Npad, int n_rows, int m, float* __restrict__ out,
+                              int64_t ldu) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (j >= m || n >= n_rows) return;
+    out[(int64_t)n * ldu + j] = U[((j >> 2) * Npad + n) * 4 + (j & 3)];
+}
+
+template <int R>
+static int launch_sweep(const DirectPlan& p, const CUtensorMap& tmX, const CUtensorMap& tmXq, const SweepArgs& a,
+                        cudaStream_t stream) {
+    static bool configured = false;
+    const size_t smem = sweep_smem_bytes<R>();
+    if (!configured) {
+        GPFQ_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)p.j_tiles, (unsigned)p.n_tiles);
+    profile_mark_begin(stream);
+    sweep_kernel<R><<<grid, kThreads, smem, stream>>>(tmX, tmXq, a);
+    if (profile_on()) {
+        // algorithmic HBM bytes of one sweep: U read (unless first) + U write (if stored), the three
+        // kB-row X / Xq tiles once, the W / Q block tiles, and the fp64 partials written for the recurrence
+        const double nm = (double)a.n_rows * (double)(a.mpad);
+        double bytes = (a.first ? 0.0 : 4.0 * nm) + (a.store_u ? 4.0 * nm : 0.0) +
+                       4.0 * kB * (double)a.mpad * (2 + (a.has_next ? 1 : 0)) + 8.0 * a.n_rows * kB +
+                       (a.has_next ? 8.0 * p.j_tiles * (double)a.n_rows * kB : 0.0);
+        double instr = nm * (4.0 * a.bvalid + (a.has_next ? 1.0 * kB : 0.0));
+        profile_mark_end(stream, bytes, instr);
+    }
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m, int n_rows,
+                 const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
+                 double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+    const DirectPlan p = make_plan(n_rows, d, m);
+    GPFQ_REQUIRE(workspace_bytes >= p.total, "gpfq_solve_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
+    GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "gpfq_solve_f32: workspace must be 256-byte aligned");
+    unsigned char* ws = (unsigned char*)workspace;
+    float* U = (float*)(ws + p.off_U);
+    double* G = (double*)(ws + p.off_G);
+    double* H = (double*)(ws + p.off_H);
+    float* norm32 = (float*)(ws + p.off_norm);
+    double* gpart = (double*)(ws + p.off_gpart);
+    double* part = (double*)(ws + p.off_part);
+    double* epart = (double*)(ws + p.off_epart);
+
+    CUtensorMap tmX, tmXq;
+    if (int rc = make_tensor_map_2d(&tmX, X, d, m, ldx, kB, kJS)) return rc;
+    if (int rc = make_tensor_map_2d(&tmXq, Xq, d, m, ldx, kB, kJS)) return rc;
+
+    block_gram_kernel<<<dim3(p.nblk, p.gram_slices), 256, 0, stream>>>(X, Xq, ldx, d, m, p.gram_slice_len,
+                                                                       p.gram_slices, gpart);
+    GPFQ_CHECK_LAUNCH();
+    block_gram_finish_kernel<<<(unsigned)ceil_div((int64_t)p.nblk * kB * kB, 256), 256, 0, stream>>>(
+        gpart, p.gram_slices, p.nblk, G, H, norm32);
+    GPFQ_CHECK_LAUNCH();
+
+    for (int blk = 0; blk < p.nblk; ++blk) {
+        const int t0 = blk * kB;
+        const int bvalid = std::min(kB, d - t0);
+        RecurArgs r{};
+        r.W = W; r.ldw = ldw; r.Q = Q; r.ldq = ldq; r.levels = levels; r.ldl = d;
+        r.part = part; r.G = G + (size_t)blk * kB * kB; r.H = H + (size_t)blk * kB * kB;
+        r.norm32 = norm32 + (size_t)blk * kB; r.delta = delta; r.Npad = p.Npad;
+        r.n_rows = n_rows; r.d = d; r.t0 = t0; r.bvalid = bvalid; r.j_tiles = p.j_tiles;
+        r.first = (blk == 0); r.mode = mode; r.Kf = (float)K; r.lam = lam;
+        recur_kernel<<<(unsigned)ceil_div(n_rows, 4), 128, 0, stream>>>(r);
+        GPFQ_CHECK_LAUNCH();
+        profile_count_other(1);
+
+        SweepArgs s{};
+        s.W = W; s.ldw = ldw; s.Q = Q; s.ldq = ldq; s.U = U; s.part = part; s.epart = epart;
+        s.Npad = p.Npad; s.mpad = p.mpad; s.n_rows = n_rows; s.d = d; s.t0 = t0; s.bvalid = bvalid; s.TJ = p.TJ;
+        s.first = (blk == 0);
+        s.has_next = (blk + 1 < p.nblk);
+        s.want_err = (!s.has_next && row_err2 != nullptr);
+        s.store_u = s.has_next || (U_out != nullptr);
+        if (!s.has_next && !s.want_err && !s.store_u) break;   // nothing observable left to do
+        int rc = p.R == 4 ? launch_sweep<4>(p, tmX, tmXq, s, stream)
+               : p.R == 2 ? launch_sweep<2>(p, tmX, tmXq, s, stream)
+                          : launch_sweep<1>(p, tmX, tmXq, s, stream);
+        if (rc) return rc;
+    }
+    if (row_err2) {
+        err_finish_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, stream>>>(epart, p.j_tiles, p.Npad, n_rows, row_err2);
+        GPFQ_CHECK_LAUNCH();
+    }
+    if (U_out) {
+        untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)n_rows), 256, 0, stream>>>(U, p.Npad, n_rows, m, U_out, ldu);
+        GPFQ_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+}  // namespace gpfq

@@ -1,0 +1,46 @@
+// gpfq_solve_f32 / gpfq_workspace_bytes: argument validation and solver dispatch.
+#include "gpfq_common.cuh"
+
+namespace gpfq {
+size_t direct_workspace_bytes(int n_rows, int d, int m);
+int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m, int n_rows,
+                 const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
+                 double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream);
+}  // namespace gpfq
+
+using namespace gpfq;
+
+extern "C" {
+
+size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m) {
+    if (n_rows <= 0 || d <= 0 || m <= 0) return 256;
+    if (solver == GPFQ_SOLVER_DIRECT) return direct_workspace_bytes(n_rows, d, m);
+    return 0;
+}
+
+int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int32_t N,
+                   int32_t d, int32_t m, int32_t n0, int32_t n1, const float* delta, int32_t K, int32_t mode, float lam,
+                   float* Q, int64_t ldq, int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    GPFQ_REQUIRE(N >= 0 && d >= 0 && m >= 0, "gpfq_solve_f32: negative dimension");
+    GPFQ_REQUIRE(0 <= n0 && n0 <= n1 && n1 <= N, "gpfq_solve_f32: bad neuron range [%d, %d) of %d", n0, n1, N);
+    GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_HARD, "gpfq_solve_f32: bad mode %d", mode);
+    GPFQ_REQUIRE(K >= 1 && K <= 127, "gpfq_solve_f32: boundary index K=%d outside [1,127]", K);
+    GPFQ_REQUIRE(ldw >= d && ldq >= d, "gpfq_solve_f32: ldw/ldq smaller than d");
+    GPFQ_REQUIRE(ldx >= m && (ldx % 4) == 0, "gpfq_solve_f32: ldx must be >= m and a multiple of 4");
+    GPFQ_REQUIRE(U_out == nullptr || ldu >= m, "gpfq_solve_f32: ldu smaller than m");
+    const int n_rows = n1 - n0;
+    if (n_rows == 0 || d == 0) return 0;
+    GPFQ_REQUIRE(m > 0, "gpfq_solve_f32: no calibration rows");
+    GPFQ_REQUIRE(W && X && Xq && delta && Q && workspace, "gpfq_solve_f32: null pointer");
+    const float* Ws = W + (int64_t)n0 * ldw;
+    float* Qs = Q + (int64_t)n0 * ldq;
+    int8_t* Ls = levels ? levels + (int64_t)n0 * d : nullptr;
+    if (solver == GPFQ_SOLVER_DIRECT)
+        return direct_solve(Ws, ldw, X, Xq, ldx, d, m, n_rows, delta, K, mode, lam, Qs, ldq, Ls, row_err2, U_out, ldu,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
+    GPFQ_REQUIRE(false, "gpfq_solve_f32: unknown solver %d", solver);
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+"""Host-side mirror of the reference's orchestrator (src/quantize_neural_net.py):
+``QuantizeNeuralNet`` with the same 16-argument constructor and ``quantize_network()``, and the
+two forward-hook classes ``SaveInputMLP`` / ``SaveInputConv2d`` with the same constructor
+arguments and ``.inputs`` protocol.
+
+Differences from the reference are confined to where the work runs:
+  * layer inputs are produced directly in the solver's feature-major layout by the fused
+    im2col + patch-gather CUDA kernel (the tensors handed out are (m x d) transposed views);
+  * the per-layer solve is libgpfq_b200 (StepAlgorithm mirror in step_algorithm.py);
+  * with torch.distributed initialised (one process per GPU), every rank runs the calibration
+    forward on the same batches, solves a contiguous slice of each layer's output neurons and
+    the slices are exchanged with ONE all-gather per layer.
+"""
+import copy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr, require_cuda
+from .sharding import neuron_slice, gather_layer
+from .step_algorithm import quantize_layer_impl, reduce_errors
+from .utils import InterruptException, extract_layers
+
+LINEAR_MODULE_TYPE = nn.Linear
+CONV2D_MODULE_TYPE = nn.Conv2d
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class SaveInputMLP:
+    """Stores the input of a Linear layer (reference quantize_neural_net.py:277-292)."""
+
+    def __init__(self):
+        self.inputs = []
+
+    def __call__(self, module, module_in, module_out):
+        if len(module_in) != 1:
+            raise TypeError('The number of input layer is not equal to one!')
+        self.inputs.append(module_in[0])
+        raise InterruptException
+
+
+class SaveInputConv2d:
+    """Stores the sub-sampled patch matrix of a Conv2d layer's input (reference
+    quantize_neural_net.py:295-350).
+
+    Semantics kept from the reference: patches are nn.Unfold patches with stride == kernel_size
+    (the layer's own ``stride`` is accepted and ignored, :320); per image ``int(p*L + 1)`` patch
+    rows (L when p == 1) are drawn WITH replacement from numpy's global RNG on the first call and
+    reused on the second call (:340-347).  The gather itself is one CUDA kernel that writes the
+    feature-major matrix; ``inputs[k]`` is its (m x C*kh*kw) transposed view."""
+
+    def __init__(self, kernel_size, dilation, padding, stride, groups, retain_rate):
+        self.p = retain_rate
+        self.kernel_size = _pair(kernel_size)
+        self.dilation = _pair(dilation)
+        self.padding = _pair(padding)
+        self.stride = stride          # unused, as in the reference
+        self.groups = groups
+        self.inputs = []
+        self.call_count = 0
+        self.rand_indices = None
+        self._idx_dev = None
+
+    def _draw(self, batch_size, num_blocks):
+        keep = int(self.p * num_blocks + 1 if self.p != 1 else self.p * num_blocks)
+        return np.concatenate([np.random.choice(np.arange(num_blocks * i, num_blocks * (i + 1)), size=keep)
+                               for i in range(batch_size)])
+
+    def __call__(self, module, module_in, module_out):
+        if len(module_in) != 1:
+            raise TypeError('The number of input layer is not equal to one!')
+        x = module_in[0]
+        require_cuda(x)
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        (kh, kw), (dh, dw), (ph, pw) = self.kernel_size, self.dilation, self.padding
+        Lh = (H + 2 * ph - dh * (kh - 1) - 1) // kh + 1
+        Lw = (W + 2 * pw - dw * (kw - 1) - 1) // kw + 1
+        if self.call_count == 0:
+            self.rand_indices = self._draw(B, Lh * Lw)
+            self._idx_dev = torch.from_numpy(np.ascontiguousarray(self.rand_indices, dtype=np.int64)).to(x.device)
+        self.call_count += 1
+        m = int(self._idx_dev.numel())
+        ld = (m + 3) // 4 * 4
+        feats = C * kh * kw
+        out = torch.empty((feats, ld), dtype=torch.float32, device=x.device)
+        check(lib.gpfq_im2col_gather_f32(ptr(x), B, C, H, W, kh, kw, dh, dw, ph, pw, 0, C,
+                                         ptr(self._idx_dev), m, ptr(out), ld, stream_ptr()))
+        self.inputs.append(out[:, :m].t())
+        raise InterruptException
+
+
+class QuantizeNeuralNet:
+    """Drop-in for the reference's QuantizeNeuralNet (quantize_neural_net.py:19-274)."""
+
+    def __init__(self,
+                 network_to_quantize, network_name, batch_size, data_loader,
+                 mlp_bits, cnn_bits,
+                 ignore_layers,
+                 mlp_alphabet_scalar, cnn_alphabet_scalar,
+                 mlp_percentile, cnn_percentile,
+                 reg, lamb, retain_rate, stochastic_quantization, device,
+                 *, process_group=None, solver=None, verbose=False):
+        self.network_name = network_name
+        self.analog_network = network_to_quantize          # not copied, as in the reference (:82)
+        self.batch_size = batch_size
+        self.data_loader_iter = iter(data_loader)
+
+        self.mlp_boundary_idx = 2 ** (mlp_bits - 1)         # alphabet delta*{-K..K}  (:87-88)
+        self.cnn_boundary_idx = 2 ** (cnn_bits - 1)
+        self.mlp_alphabet_scalar = mlp_alphabet_scalar
+        self.mlp_alphabet_step_size = mlp_alphabet_scalar / self.mlp_boundary_idx
+        self.cnn_alphabet_step_size = cnn_alphabet_scalar / self.cnn_boundary_idx
+        self.mlp_bits = mlp_bits
+        self.cnn_bits = cnn_bits
+        self.mlp_percentile = mlp_percentile
+        self.cnn_percentile = cnn_percentile
+        self.ignore_layers = ignore_layers
+        self.retain_rate = retain_rate
+        self.reg = reg
+        self.lamb = lamb
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError("quantized_neural_nets_b200 runs on CUDA devices only; there is no CPU fallback")
+        self.stochastic_quantization = stochastic_quantization
+
+        self.quantized_network = copy.deepcopy(self.analog_network)
+        self.analog_network_layers = []
+        extract_layers(self.analog_network, self.analog_network_layers)
+        self.quantized_network_layers = []
+        extract_layers(self.quantized_network, self.quantized_network_layers)
+
+        # B200 additions (keyword-only, defaults reproduce the single-GPU reference behaviour)
+        self.process_group = process_group
+        self.solver = solver
+        self.verbose = verbose
+        self.layer_log = []      # (layer_idx, quantize_error tensor, relative_quantize_error tensor)
+
+    # ------------------------------------------------------------------
+    def quantize_network(self):
+        """Quantize every non-ignored layer in definition order and return the quantized copy
+        (reference quantize_neural_net.py:117-214)."""
+        layers_to_quantize = [i for i in range(len(self.quantized_network_layers)) if i not in self.ignore_layers]
+        if self.verbose:
+            print(f'Layer indices to quantize {layers_to_quantize}')
+            print(f'Total number of layers to quantize {len(layers_to_quantize)}')
+        for layer_idx in layers_to_quantize:
+            analog_layer_input, quantized_layer_input = self._populate_linear_layer_input(layer_idx)
+            layer = self.analog_network_layers[layer_idx]
+            if type(layer) == LINEAR_MODULE_TYPE:
+                groups = 1
+                W = layer.weight.data
+                W_shape = W.shape
+                step, K, pct = self.mlp_alphabet_step_size, self.mlp_boundary_idx, self.mlp_percentile
+            elif type(layer) == CONV2D_MODULE_TYPE:
+                groups = layer.groups
+                W_shape = layer.weight.data.shape
+                W = layer.weight.data.view(W_shape[0], -1)
+                step, K, pct = self.cnn_alphabet_step_size, self.cnn_boundary_idx, self.cnn_percentile
+            else:
+                raise TypeError(f'The layer type {type(layer)} is not currently supported')
+
+            m = analog_layer_input.shape[0]
+            N = W.shape[0]
+            n0, n1 = neuron_slice(N, groups, self.process_group)
+            Q, err2, ref2 = quantize_layer_impl(W, analog_layer_input, quantized_layer_input, m, step, K, pct,
+                                                self.reg, self.lamb, groups, self.stochastic_quantization,
+                                                self.device, neuron_range=(n0, n1), solver=self.solver,
+                                                return_partials=True)
+            Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group)
+            quantize_error, relative_quantize_error, _, _ = reduce_errors(err2, ref2, groups)
+            self.quantized_network_layers[layer_idx].weight.data = Q.reshape(W_shape).float()
+            self.layer_log.append((layer_idx, quantize_error, relative_quantize_error))
+            if self.verbose:
+                print(f'The quantization error of layer {layer_idx} is {quantize_error.cpu().numpy()}.')
+                print(f'The relative quantization error of layer {layer_idx} is '
+                      f'{relative_quantize_error.cpu().numpy()}.\n')
+            del analog_layer_input, quantized_layer_input
+        return self.quantized_network
+
+    # ------------------------------------------------------------------
+    def _populate_linear_layer_input(self, layer_idx):
+        """Inputs of layer ``layer_idx`` in the analog and in the (partially) quantized network for
+        one FRESH batch of the loader (reference quantize_neural_net.py:217-274)."""
+        raw_input_data, _ = next(self.data_loader_iter)
+        analog_layer = self.analog_network_layers[layer_idx]
+        if type(analog_layer) == LINEAR_MODULE_TYPE:
+            save_input = SaveInputMLP()
+        elif type(analog_layer) == CONV2D_MODULE_TYPE:
+            save_input = SaveInputConv2d(kernel_size=analog_layer.kernel_size, dilation=analog_layer.dilation,
+                                         padding=analog_layer.padding, stride=analog_layer.stride,
+                                         groups=analog_layer.groups, retain_rate=self.retain_rate)
+        else:
+            raise TypeError(f'The layer type {type(analog_layer)} is not currently supported')
+
+        images = raw_input_data.to(self.device, non_blocking=True)
+        with torch.no_grad():
+            for network, layers in ((self.analog_network, self.analog_network_layers),
+                                    (self.quantized_network, self.quantized_network_layers)):
+                handle = layers[layer_idx].register_forward_hook(save_input)
+                try:
+                    network(images)
+                except InterruptException:
+                    pass
+                finally:
+                    handle.remove()
+        return save_input.inputs[0], save_input.inputs[1]

@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's ``StepAlgorithm`` (src/step_algorithm.py) on top of
+libgpfq_b200.so.  Same names, argument order, in-place behaviour and return types as the
+reference, so ``from step_algorithm import StepAlgorithm`` can be swapped for
+``from quantized_neural_nets_b200.step_algorithm import StepAlgorithm``.
+
+Everything numerically relevant runs in hand-written sm_100a CUDA (csrc/); this file only
+shapes arguments.  PyTorch is used for device memory, the layer radius (``torch.quantile``,
+once per layer, step_algorithm.py:191) and the plain ``W @ X^T`` library GEMM behind the
+relative-error denominators (step_algorithm.py:217,219)."""
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr, require_cuda
+
+# solver used by _quantization/_quantize_layer: _lib.SOLVER_DIRECT or _lib.SOLVER_GRAM
+DEFAULT_SOLVER = _lib.SOLVER_DIRECT
+
+
+def _delta_tensor(step_size, device):
+    """The reference passes the step size as a 0-dim tensor (step * radius, :192); the unit-test
+    entry points may also be handed a Python float."""
+    if isinstance(step_size, torch.Tensor):
+        return step_size.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+    return torch.tensor([float(step_size)], dtype=torch.float32, device=device)
+
+
+def _elementwise(mode, step_size, x, boundary_idx, lamb):
+    require_cuda(x)
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    delta = _delta_tensor(step_size, x.device)
+    check(lib.gpfq_quantize_f32(ptr(xc), ptr(out), xc.numel(), ptr(delta), int(boundary_idx), mode, float(lamb),
+                                stream_ptr()))
+    return out
+
+
+def feature_major(X):
+    """(m x d) layer input -> (feature-major tensor whose row t is column t of X, leading dim ld).
+    Zero-copy when ``X`` already is a transposed view of a 16-byte aligned (d x ld) buffer with
+    ld % 4 == 0 (what SaveInputConv2d / SaveInputMLP of this package hand out); otherwise one
+    transpose kernel."""
+    require_cuda(X)
+    m, d = X.shape
+    ld = X.stride(1)
+    if X.stride(0) == 1 and ld >= m and ld % 4 == 0 and X.data_ptr() % 16 == 0:
+        return X.t(), ld
+    ld = (m + 3) // 4 * 4
+    out = torch.empty((d, ld), dtype=torch.float32, device=X.device)
+    Xc = X if X.stride(1) == 1 else X.contiguous()
+    check(lib.gpfq_transpose_f32(ptr(Xc), m, d, Xc.stride(0), ptr(out), ld, stream_ptr()))
+    return out, ld
+
+
+def solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, want_err=True, want_residual=False,
+               levels=None, solver=None):
+    """Run the greedy path for neurons [n0, n1) of W (N x d) against feature-major inputs.
+    Writes rows n0..n1-1 of Q.  Returns (row_err2 float64[n1-n0] | None, U (n1-n0, m) | None)."""
+    solver = DEFAULT_SOLVER if solver is None else solver
+    N, d = W.shape
+    rows = n1 - n0
+    dev = W.device
+    row_err2 = torch.empty(rows, dtype=torch.float64, device=dev) if want_err else None
+    U = torch.empty((rows, m), dtype=torch.float32, device=dev) if want_residual else None
+    if rows == 0 or d == 0:
+        if row_err2 is not None:
+            row_err2.zero_()
+        return row_err2, U
+    nbytes = lib.gpfq_workspace_bytes(solver, rows, d, m)
+    if nbytes == 0:
+        raise RuntimeError(f"libgpfq_b200: solver {solver} is not available")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.gpfq_solve_f32(solver, ptr(W), W.stride(0), ptr(Xfm), ptr(Xqfm), ldx, N, d, m, n0, n1, ptr(delta),
+                             int(K), mode, float(lamb), ptr(Q), Q.stride(0), ptr(levels), ptr(row_err2), ptr(U),
+                             m, ptr(ws), nbytes, stream_ptr()))
+    return row_err2, U
+
+
+class StepAlgorithm:
+    # ------------------------------------------------------------------ alphabet maps
+    def _msq(step_size, x, boundary_idx, lamb):
+        """Nearest-alphabet map (reference step_algorithm.py:38-56), CUDA elementwise kernel."""
+        return _elementwise(_lib.MODE_MSQ, step_size, x, boundary_idx, lamb)
+
+    def _soft_thresholding_msq(step_size, x, boundary_idx, lamb):
+        """reg='L1' map (reference step_algorithm.py:84-104)."""
+        return _elementwise(_lib.MODE_SOFT, step_size, x, boundary_idx, lamb)
+
+    def _hard_thresholding_msq(step_size, x, boundary_idx, lamb):
+        """reg='L0' map (reference step_algorithm.py:59-81)."""
+        return _elementwise(_lib.MODE_HARD, step_size, x, boundary_idx, lamb)
+
+    def _stochastic_msq(step_size, x, boundary_idx, lamb):
+        """SGPFQ map (reference step_algorithm.py:7-35).  Its Bernoulli draws come from torch's
+        global generator and cannot be reproduced by a custom kernel; listed as a 'next' row in
+        SURVEY.md section 8f and not part of this library yet."""
+        raise NotImplementedError("stochastic quantization (SGPFQ) is not implemented by libgpfq_b200 yet")
+
+    _MODE_OF = {}
+
+    # ------------------------------------------------------------------ greedy path
+    def _quantization(W, Q, U, analog_layer_input, quantized_layer_input, quantizer,
+                      step_size, boundary_idx, lamb):
+        """In place on Q (N x d) and U (N x m), as the reference (step_algorithm.py:107-148)."""
+        mode = StepAlgorithm._MODE_OF.get(quantizer)
+        if mode is None:
+            raise NotImplementedError(f"quantizer {quantizer} has no CUDA implementation")
+        require_cuda(W, Q, U, analog_layer_input, quantized_layer_input)
+        N, d = W.shape
+        m = analog_layer_input.shape[0]
+        if U.shape != (N, m) or Q.shape != (N, d):
+            raise ValueError("Q / U shapes do not match W and the layer inputs")
+        Wc = W if W.stride(1) == 1 else W.contiguous()
+        Xfm, ldx = feature_major(analog_layer_input)
+        Xqfm, ldq = feature_major(quantized_layer_input)
+        if ldq != ldx:
+            Xqfm, ldq = _repack(Xqfm, m, ldx)
+        delta = _delta_tensor(step_size, W.device)
+        Qc = Q if (Q.stride(1) == 1) else torch.empty((N, d), dtype=torch.float32, device=W.device)
+        _, Ures = solve_rows(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Qc, 0, N,
+                             want_err=False, want_residual=True)
+        if Qc is not Q:
+            Q.copy_(Qc)
+        U.copy_(Ures)
+
+    # ------------------------------------------------------------------ one layer
+    def _quantize_layer(W, analog_layer_input, quantized_layer_input, m,
+                        step_size, boundary_idx, percentile,
+                        reg, lamb, groups, stochastic_quantization, device):
+        """Drop-in for the reference's per-layer entry (step_algorithm.py:151-249): returns
+        (Q, quantize_error, relative_quantize_error, quantize_adder, relative_adder) with errors
+        as 0-dim tensors on the device."""
+        return quantize_layer_impl(W, analog_layer_input, quantized_layer_input, m, step_size, boundary_idx,
+                                   percentile, reg, lamb, groups, stochastic_quantization, device,
+                                   want_adder=True)
+
+
+StepAlgorithm._MODE_OF = {
+    StepAlgorithm._msq: _lib.MODE_MSQ,
+    StepAlgorithm._soft_thresholding_msq: _lib.MODE_SOFT,
+    StepAlgorithm._hard_thresholding_msq: _lib.MODE_HARD,
+}
+
+
+def _repack(Xfm, m, ld):
+    out = torch.zeros((Xfm.shape[0], ld), dtype=torch.float32, device=Xfm.device)
+    out[:, :m] = Xfm[:, :m]
+    return out, ld
+
+
+def layer_delta(W, step_size, boundary_idx, percentile, reg, lamb):
+    """delta = step * mean_i quantile_pct(|W_i|), minus lamb/K for L0 (step_algorithm.py:191-192).
+    percentile == 1 is the row maximum; both stay on the device (no host sync)."""
+    absW = torch.abs(W)
+    rad = (absW.amax(dim=1) if percentile == 1 else torch.quantile(absW, percentile, dim=1)).mean()
+    delta = step_size * rad - lamb / boundary_idx if reg == 'L0' else step_size * rad
+    return delta
+
+
+def mode_of(reg, stochastic_quantization):
+    if reg == 'L1':
+        return _lib.MODE_SOFT
+    if reg == 'L0':
+        return _lib.MODE_HARD
+    if stochastic_quantization:
+        raise NotImplementedError("stochastic quantization (SGPFQ) is not implemented by libgpfq_b200 yet")
+    return _lib.MODE_MSQ
+
+
+def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, lamb, groups,
+                        stochastic_quantization, device, want_adder=False, neuron_range=None, levels=None,
+                        solver=None, return_partials=False):
+    """Shared body of ``StepAlgorithm._quantize_layer`` and of the sharded orchestrator.
+
+    neuron_range=(n0, n1) restricts the solve to a contiguous slice of output neurons (rows
+    outside it are left zero in Q); with return_partials=True the per-neuron squared norms
+    (||u_n||^2, ||X w_n||^2 as float64, full length N, zero outside the slice) are returned instead
+    of the reduced errors so that the caller can all-gather them."""
+    if torch.device(device).type != 'cuda':
+        raise RuntimeError("libgpfq_b200 runs on CUDA devices only; there is no CPU fallback")
+    require_cuda(W, X, Xq)
+    mode = mode_of(reg, stochastic_quantization)
+    N, d = W.shape
+    dev = W.device
+    n0, n1 = (0, N) if neuron_range is None else neuron_range
+    Wc = W if W.stride(1) == 1 else W.contiguous()
+    delta = layer_delta(Wc, step_size, boundary_idx, percentile, reg, lamb).to(torch.float32).reshape(1)
+    Q = torch.zeros((N, d), dtype=torch.float32, device=dev)
+    Xfm, ldx = feature_major(X)
+    Xqfm, ldq = feature_major(Xq)
+    if ldq != ldx:
+        Xqfm, ldq = _repack(Xqfm, m, ldx)
+    err2 = torch.zeros(N, dtype=torch.float64, device=dev)
+    ref2 = torch.zeros(N, dtype=torch.float64, device=dev)
+    adder = None
+    n_per_group = N // groups
+    for g in range(groups):
+        g0, g1 = max(n0, g * n_per_group), min(n1, (g + 1) * n_per_group)
+        if g0 >= g1:
+            continue
+        Xg = Xfm[g * d:(g + 1) * d]
+        Xqg = Xqfm[g * d:(g + 1) * d]
+        e2, Ures = solve_rows(Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, Q, g0, g1,
+                              want_err=True, want_residual=(want_adder and groups == 1), levels=levels,
+                              solver=solver)
+        err2[g0:g1] = e2
+        # ||X w_n||^2 : plain library GEMM (cuBLAS fp32) -- step_algorithm.py:217,219
+        Y = torch.matmul(Wc[g0:g1], Xg[:, :m])
+        ref2[g0:g1] = (Y.double() ** 2).sum(dim=1)
+        if Ures is not None:
+            adder = Ures.t()
+    if return_partials:
+        return Q, err2, ref2
+    return (Q,) + reduce_errors(err2, ref2, groups, adder)
+
+
+def reduce_errors(err2, ref2, groups, adder=None):
+    """(quantize_error, relative_quantize_error, quantize_adder, relative_adder) from per-neuron
+    squared norms, with the reference's conventions (step_algorithm.py:215-219, 239-245)."""
+    if groups == 1:
+        err = err2.sum().sqrt().float()
+        rel = (err2.sum().sqrt() / ref2.sum().sqrt()).float()
+        rel_adder = (err2.sqrt().float() / (ref2.sqrt().float() + 1e-5))
+        return err, rel, adder, rel_adder
+    e = err2.view(groups, -1).sum(dim=1).sqrt()
+    r = ref2.view(groups, -1).sum(dim=1).sqrt()
+    return (e.sum() / groups).float(), ((e / r).sum() / groups).float(), None, None

@@ -1,0 +1,125 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/gpfq_b200.h
+declares (no compute without a GPU), the host logic of the orchestrator mirror, and the
+world_size-2 sharding exchange over gloo."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import quantized_neural_nets_b200._lib as L
+    header = open(os.path.join(ROOT, "include", "gpfq_b200.h")).read()
+    declared = set(re.findall(r"\b(gpfq_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    dll = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(dll, name), f"{name} declared in gpfq_b200.h but not exported"
+    assert declared == set(L.SIGNATURES), "ctypes binding and header disagree"
+    assert L.lib.gpfq_abi_version() == 1
+
+
+def test_workspace_and_argument_validation_without_gpu():
+    import quantized_neural_nets_b200._lib as L
+    assert L.lib.gpfq_workspace_bytes(L.SOLVER_DIRECT, 512, 256, 200960) >= 512 * 200960 * 4
+    # invalid arguments are rejected before anything touches the device
+    rc = L.lib.gpfq_solve_f32(0, None, 4, None, None, 8, 4, 4, 8, 3, 2, None, 8, 0, 0.0, None, 4, None, None, None, 8,
+                              None, 0, None)
+    assert rc != 0 and b"neuron range" in L.lib.gpfq_last_error()
+    rc = L.lib.gpfq_quantize_f32(None, None, 4, None, 8, 7, 0.0, None)
+    assert rc != 0 and b"mode" in L.lib.gpfq_last_error()
+
+
+def test_no_cpu_fallback():
+    import quantized_neural_nets_b200 as qb
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-GPU behaviour")
+    with pytest.raises(RuntimeError):
+        qb.StepAlgorithm._msq(0.1, torch.zeros(4), 8, 0.0)
+    with pytest.raises(RuntimeError):
+        qb.QuantizeNeuralNet(nn.Sequential(nn.Linear(4, 4)), "x", 2, [], 4, 4, [], 1.16, 1.16, 1, 1, None, 0.1, 0.25,
+                             False, torch.device("cpu"))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "quantized_neural_nets_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", ""), f"{f} mentions the oracle"
+
+
+def test_extract_layers_matches_oracle_walk():
+    import torchvision
+    from oracle import gpfq_oracle as orc
+    from quantized_neural_nets_b200.utils import extract_layers
+    for name, count in (("resnet18", 21), ("alexnet", 8), ("resnet50", 54), ("vgg16", 16), ("mobilenet_v2", None)):
+        m = getattr(torchvision.models, name)(weights=None)
+        a, b = [], []
+        extract_layers(m, a)
+        orc.extract_layers(m, b)
+        assert len(a) == len(b) and all(x is y for x, y in zip(a, b)), name
+        if count is not None:
+            assert len(a) == count, (name, len(a))
+
+
+def test_neuron_slices_partition():
+    from quantized_neural_nets_b200.sharding import neuron_slice
+    for N in (1, 7, 64, 1000, 4096):
+        for world in (1, 2, 3, 4, 8):
+            cover = []
+            for r in range(world):
+                n0, n1 = neuron_slice(N, 1, world=world, rank=r)
+                assert 0 <= n0 <= n1 <= N
+                cover += list(range(n0, n1))
+            assert cover == list(range(N))
+
+
+def test_pack_unpack_round_trip():
+    from quantized_neural_nets_b200 import sharding as sh
+    g = torch.Generator().manual_seed(3)
+    N, d, world = 10, 7, 4
+    Q = torch.randn(N, d, generator=g)
+    e2 = torch.rand(N, generator=g, dtype=torch.float64)
+    r2 = torch.rand(N, generator=g, dtype=torch.float64)
+    per = sh.rows_per_rank(N, world)
+    bufs = [sh.pack_slice(Q, e2, r2, *sh.neuron_slice(N, 1, world=world, rank=r), per) for r in range(world)]
+    Q2, e2b, r2b = sh.unpack_all(torch.cat(bufs), N, d)
+    assert torch.equal(Q, Q2) and torch.equal(e2, e2b) and torch.equal(r2, r2b)
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from quantized_neural_nets_b200 import sharding as sh
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    N, d = 11, 6
+    Qtrue = torch.randn(N, d, generator=g)
+    etrue = torch.rand(N, generator=g, dtype=torch.float64)
+    rtrue = torch.rand(N, generator=g, dtype=torch.float64)
+    n0, n1 = sh.neuron_slice(N, 1)
+    Q = torch.zeros(N, d); e = torch.zeros(N, dtype=torch.float64); r = torch.zeros(N, dtype=torch.float64)
+    Q[n0:n1], e[n0:n1], r[n0:n1] = Qtrue[n0:n1], etrue[n0:n1], rtrue[n0:n1]
+    Qf, ef, rf = sh.gather_layer(Q, e, r, n0, n1)
+    ok = torch.equal(Qf, Qtrue) and torch.equal(ef, etrue) and torch.equal(rf, rtrue)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_all_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+        assert dict(out) == {0: True, 1: True}
