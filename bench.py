@@ -122,33 +122,40 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-CPU_CLASSES = [  # (N, d, m, greedy steps sampled) -- one ResNet-50 layer shape per calibration-row class
-    (256, 64, 200960, 2), (512, 128, 50432, 4), (64, 576, 23296, 8), (1024, 256, 12800, 8),
-    (128, 1152, 6656, 16), (2048, 512, 3328, 16), (256, 2304, 1792, 48), (512, 4608, 768, 64), (1000, 2048, 256, 128),
+CPU_CLASSES = [  # (N, d, m) -- one ResNet-50 layer shape per calibration-row class
+    (256, 64, 200960), (512, 128, 50432), (64, 576, 23296), (1024, 256, 12800), (128, 1152, 6656),
+    (2048, 512, 3328), (256, 2304, 1792), (512, 4608, 768), (1000, 2048, 256),
 ]
 
 
-def cpu_reference_sample(shapes, scale=1.0):
+def cpu_reference_sample(shapes, seconds_per_class=1.5):
     """Times the oracle's greedy loop (a torch-CPU restatement issuing the reference's own ATen ops,
-    step_algorithm.py:140-148) for the first k features of one layer per calibration-row class and
-    extrapolates to the whole network: the loop's cost per feature is constant within a layer.
+    step_algorithm.py:140-148) for the first k features of one layer per calibration-row class
+    (k sized so that each class takes about ``seconds_per_class``) and extrapolates to the whole
+    network: the loop's cost per feature is constant within a layer.
     Returns (extrapolated units/s, seconds spent, extrapolated seconds for the network)."""
     from oracle import gpfq_oracle as orc
     g = torch.Generator().manual_seed(3)
     rates = {}
     spent = 0.0
-    for (N, d, m, k) in CPU_CLASSES:
-        k = max(1, int(k * scale))
+    for (N, d, m) in CPU_CLASSES:
         W = torch.randn(N, d, generator=g) * 0.05
         X = torch.relu(torch.randn(m, d, generator=g))
-        Q = torch.zeros_like(W)
-        U = torch.zeros(N, m)
         delta = orc.layer_step_size(W, 1.16 / 8, 8, 1, None, 0.1)
-        orc.greedy_path(W, Q, U, X, X, orc.msq, delta, 8, 0.0, steps=1)       # touch pages / warm caches
-        t0 = time.perf_counter()
-        orc.greedy_path(W, Q, U, X, X, orc.msq, delta, 8, 0.0, steps=k)
-        dt = time.perf_counter() - t0
-        spent += dt
+
+        def run(k):
+            Q = torch.zeros_like(W)
+            U = torch.zeros(N, m)
+            t0 = time.perf_counter()
+            orc.greedy_path(W, Q, U, X, X, orc.msq, delta, 8, 0.0, steps=k)
+            return time.perf_counter() - t0
+
+        run(1)                                  # touch pages / warm caches
+        k0 = 2
+        dt0 = run(k0)
+        k = int(min(d, max(k0, seconds_per_class / (dt0 / k0))))
+        dt = run(k)
+        spent += dt0 + dt
         rates[m] = N * m * k / dt
     ms = sorted(rates)
     total_units = 0.0
@@ -169,7 +176,7 @@ def run_reference_arm(args):
     shapes = layer_shapes(model, args.batch, args.retain)
     cores = torch.get_num_threads()
     for _ in range(args.warmup):
-        cpu_reference_sample(shapes, scale=0.25)
+        cpu_reference_sample(shapes, seconds_per_class=0.3)
     vals, times = [], []
     for _ in range(args.steps):
         v, spent, _ = cpu_reference_sample(shapes)
@@ -229,10 +236,10 @@ def run_cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(pool, read_back):
+    def one_step(pool, read_back, profile=False):
         np.random.seed(0)
         qnn = qb.QuantizeNeuralNet(model, args.model, args.batch, BatchPool(pool), args.bits, args.bits, [],
-                                   1.16, 1.16, 1, 1, None, 0.1, args.retain, False, dev)
+                                   1.16, 1.16, 1, 1, None, 0.1, args.retain, False, dev, profile=profile)
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -273,6 +280,8 @@ def run_cuda_arm(args):
     _lib.profile_begin()
     step_ms, _, _ = one_step(dev_pool, False)
     prof = _lib.profile_end()
+    _, qprof, _ = one_step(dev_pool, False, profile=True)
+    phases, per_layer = qprof.phase_times_ms()
 
     out = None
     if rank == 0:
@@ -312,6 +321,8 @@ def run_cuda_arm(args):
                          "frac": (prof["sweep_fp32_instr"] / sweep_s) / fp32_peak if sweep_s > 0 else 0.0},
             },
             "rel_err_mean": sum(rel) / len(rel),
+            "phase_ms_per_step": {k: round(v, 2) for k, v in phases.items()},
+            "solve_ms_per_layer": [round(per_layer[i].get("solve", 0.0), 3) for i in sorted(per_layer)],
         }
         if world == 1 and not args.no_cpu_baseline:
             v, spent, extrap = cpu_reference_sample(shapes)

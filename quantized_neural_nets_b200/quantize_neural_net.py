@@ -105,7 +105,7 @@ class QuantizeNeuralNet:
                  mlp_alphabet_scalar, cnn_alphabet_scalar,
                  mlp_percentile, cnn_percentile,
                  reg, lamb, retain_rate, stochastic_quantization, device,
-                 *, process_group=None, solver=None, verbose=False):
+                 *, process_group=None, solver=None, verbose=False, profile=False):
         self.network_name = network_name
         self.analog_network = network_to_quantize          # not copied, as in the reference (:82)
         self.batch_size = batch_size
@@ -140,6 +140,38 @@ class QuantizeNeuralNet:
         self.solver = solver
         self.verbose = verbose
         self.layer_log = []      # (layer_idx, quantize_error tensor, relative_quantize_error tensor)
+        self.profile = profile   # record CUDA-event timings of the phases of every layer
+        self._marks = []         # (layer_idx, phase, start_event, end_event)
+
+    # ------------------------------------------------------------------
+    class _Phase:
+        """CUDA-event bracket around one phase of one layer (only when profile=True)."""
+
+        def __init__(self, owner, layer_idx, name):
+            self.owner, self.layer_idx, self.name = owner, layer_idx, name
+
+        def __enter__(self):
+            if self.owner.profile:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.owner.profile:
+                self.b.record()
+                self.owner._marks.append((self.layer_idx, self.name, self.a, self.b))
+            return False
+
+    def phase_times_ms(self):
+        """{phase: total ms} and per-layer list, after a profile=True run."""
+        torch.cuda.synchronize()
+        totals, per_layer = {}, {}
+        for idx, name, a, b in self._marks:
+            ms = a.elapsed_time(b)
+            totals[name] = totals.get(name, 0.0) + ms
+            per_layer.setdefault(idx, {})[name] = per_layer.setdefault(idx, {}).get(name, 0.0) + ms
+        return totals, per_layer
 
     # ------------------------------------------------------------------
     def quantize_network(self):
@@ -168,11 +200,13 @@ class QuantizeNeuralNet:
             m = analog_layer_input.shape[0]
             N = W.shape[0]
             n0, n1 = neuron_slice(N, groups, self.process_group)
-            Q, err2, ref2 = quantize_layer_impl(W, analog_layer_input, quantized_layer_input, m, step, K, pct,
-                                                self.reg, self.lamb, groups, self.stochastic_quantization,
-                                                self.device, neuron_range=(n0, n1), solver=self.solver,
-                                                return_partials=True)
-            Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group)
+            with self._Phase(self, layer_idx, 'solve'):
+                Q, err2, ref2 = quantize_layer_impl(W, analog_layer_input, quantized_layer_input, m, step, K, pct,
+                                                    self.reg, self.lamb, groups, self.stochastic_quantization,
+                                                    self.device, neuron_range=(n0, n1), solver=self.solver,
+                                                    return_partials=True)
+            with self._Phase(self, layer_idx, 'gather'):
+                Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group)
             quantize_error, relative_quantize_error, _, _ = reduce_errors(err2, ref2, groups)
             self.quantized_network_layers[layer_idx].weight.data = Q.reshape(W_shape).float()
             self.layer_log.append((layer_idx, quantize_error, relative_quantize_error))
@@ -198,15 +232,17 @@ class QuantizeNeuralNet:
         else:
             raise TypeError(f'The layer type {type(analog_layer)} is not currently supported')
 
-        images = raw_input_data.to(self.device, non_blocking=True)
+        with self._Phase(self, layer_idx, 'h2d'):
+            images = raw_input_data.to(self.device, non_blocking=True)
         with torch.no_grad():
-            for network, layers in ((self.analog_network, self.analog_network_layers),
-                                    (self.quantized_network, self.quantized_network_layers)):
+            for name, network, layers in (('forward_analog', self.analog_network, self.analog_network_layers),
+                                          ('forward_quantized', self.quantized_network, self.quantized_network_layers)):
                 handle = layers[layer_idx].register_forward_hook(save_input)
-                try:
-                    network(images)
-                except InterruptException:
-                    pass
-                finally:
-                    handle.remove()
+                with self._Phase(self, layer_idx, name):
+                    try:
+                        network(images)
+                    except InterruptException:
+                        pass
+                    finally:
+                        handle.remove()
         return save_input.inputs[0], save_input.inputs[1]
