@@ -201,7 +201,9 @@ def workload_config(args):
                         "(BASELINE.json configs[3]); one step = quantize_network() over all layers",
             "global_batch": args.batch, "image": "3x224x224 Gaussian", "weights": "random init (torch.manual_seed(0))",
             "l2": "per-step inputs (8.3 GB of images, up to 400 MB of layer inputs) exceed the 126 MB L2",
-            "parallelism": f"neuron-sharded x{args.gpus}, replicated calibration forward, 1 all-gather per layer"}
+            "parallelism": f"neuron-sharded x{args.gpus}, {args.forward} calibration forward, "
+                           + ("1 all-gather (Q) per layer" if args.forward == "replicated"
+                              else "2 all-gathers (layer inputs, Q) per layer")}
 
 
 # ----------------------------------------------------------------------------- CUDA arm
@@ -239,7 +241,8 @@ def run_cuda_arm(args):
     def one_step(pool, read_back, profile=False):
         np.random.seed(0)
         qnn = qb.QuantizeNeuralNet(model, args.model, args.batch, BatchPool(pool), args.bits, args.bits, [],
-                                   1.16, 1.16, 1, 1, None, 0.1, args.retain, False, dev, profile=profile)
+                                   1.16, 1.16, 1, 1, None, 0.1, args.retain, False, dev, profile=profile,
+                                   shard_forward=(args.forward == "sharded"))
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -348,12 +351,25 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--retain", type=float, default=0.25)
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic image batches cycled by the loader")
+    ap.add_argument("--forward", default="replicated", choices=["replicated", "sharded"],
+                    help="multi-GPU only: replicate the calibration forward on every rank (BASELINE.json's design) or "
+                         "split each batch over the ranks and all-gather the layer inputs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_cuda_arm(args)
+    # stdout carries exactly ONE JSON line: route everything else that native libraries may print
+    # there (e.g. NCCL's version banner) to stderr, and write the JSON to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = sys.stdout
+    sys.stdout = os.fdopen(real_stdout, "w")
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_cuda_arm(args)
+    finally:
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -19,8 +19,8 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr, require_cuda
-from .sharding import neuron_slice, gather_layer
-from .step_algorithm import quantize_layer_impl, reduce_errors
+from .sharding import neuron_slice, gather_layer, gather_inputs, world_and_rank
+from .step_algorithm import quantize_layer_impl, reduce_errors, row_radius, delta_from_radii
 from .utils import InterruptException, extract_layers
 
 LINEAR_MODULE_TYPE = nn.Linear
@@ -54,8 +54,14 @@ class SaveInputConv2d:
     reused on the second call (:340-347).  The gather itself is one CUDA kernel that writes the
     feature-major matrix; ``inputs[k]`` is its (m x C*kh*kw) transposed view."""
 
-    def __init__(self, kernel_size, dilation, padding, stride, groups, retain_rate):
+    def __init__(self, kernel_size, dilation, padding, stride, groups, retain_rate, image_range=None,
+                 full_batch=None):
         self.p = retain_rate
+        # B200 addition: when the calibration forward is sharded over ranks, this rank's forward sees
+        # images [i0, i1) of a ``full_batch``-image batch; indices are still drawn for ALL images so
+        # that numpy's RNG stream is consumed exactly as in the reference.
+        self.image_range = image_range
+        self.full_batch = full_batch
         self.kernel_size = _pair(kernel_size)
         self.dilation = _pair(dilation)
         self.padding = _pair(padding)
@@ -82,8 +88,16 @@ class SaveInputConv2d:
         Lh = (H + 2 * ph - dh * (kh - 1) - 1) // kh + 1
         Lw = (W + 2 * pw - dw * (kw - 1) - 1) // kw + 1
         if self.call_count == 0:
-            self.rand_indices = self._draw(B, Lh * Lw)
-            self._idx_dev = torch.from_numpy(np.ascontiguousarray(self.rand_indices, dtype=np.int64)).to(x.device)
+            L = Lh * Lw
+            if self.image_range is None:
+                self.rand_indices = self._draw(B, L)
+                local = self.rand_indices
+            else:
+                i0, i1 = self.image_range
+                self.rand_indices = self._draw(self.full_batch, L)
+                keep = len(self.rand_indices) // self.full_batch
+                local = self.rand_indices[i0 * keep:i1 * keep] - i0 * L
+            self._idx_dev = torch.from_numpy(np.ascontiguousarray(local, dtype=np.int64)).to(x.device)
         self.call_count += 1
         m = int(self._idx_dev.numel())
         ld = (m + 3) // 4 * 4
@@ -105,7 +119,7 @@ class QuantizeNeuralNet:
                  mlp_alphabet_scalar, cnn_alphabet_scalar,
                  mlp_percentile, cnn_percentile,
                  reg, lamb, retain_rate, stochastic_quantization, device,
-                 *, process_group=None, solver=None, verbose=False, profile=False):
+                 *, process_group=None, solver=None, verbose=False, profile=False, shard_forward=False):
         self.network_name = network_name
         self.analog_network = network_to_quantize          # not copied, as in the reference (:82)
         self.batch_size = batch_size
@@ -136,7 +150,8 @@ class QuantizeNeuralNet:
         extract_layers(self.quantized_network, self.quantized_network_layers)
 
         # B200 additions (keyword-only, defaults reproduce the single-GPU reference behaviour)
-        self.process_group = process_group
+        self.process_group = process_group   # None = default group when torch.distributed is initialised; False = never shard
+        self.shard_forward = shard_forward   # split each calibration batch over the ranks and all-gather X / X~ columns
         self.solver = solver
         self.verbose = verbose
         self.layer_log = []      # (layer_idx, quantize_error tensor, relative_quantize_error tensor)
@@ -181,6 +196,7 @@ class QuantizeNeuralNet:
         if self.verbose:
             print(f'Layer indices to quantize {layers_to_quantize}')
             print(f'Total number of layers to quantize {len(layers_to_quantize)}')
+        deltas = self._layer_deltas(layers_to_quantize)
         for layer_idx in layers_to_quantize:
             analog_layer_input, quantized_layer_input = self._populate_linear_layer_input(layer_idx)
             layer = self.analog_network_layers[layer_idx]
@@ -204,7 +220,7 @@ class QuantizeNeuralNet:
                 Q, err2, ref2 = quantize_layer_impl(W, analog_layer_input, quantized_layer_input, m, step, K, pct,
                                                     self.reg, self.lamb, groups, self.stochastic_quantization,
                                                     self.device, neuron_range=(n0, n1), solver=self.solver,
-                                                    return_partials=True)
+                                                    return_partials=True, delta=deltas[layer_idx])
             with self._Phase(self, layer_idx, 'gather'):
                 Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group)
             quantize_error, relative_quantize_error, _, _ = reduce_errors(err2, ref2, groups)
@@ -216,6 +232,35 @@ class QuantizeNeuralNet:
                       f'{relative_quantize_error.cpu().numpy()}.\n')
             del analog_layer_input, quantized_layer_input
         return self.quantized_network
+
+    # ------------------------------------------------------------------
+    def _layer_params(self, layer):
+        if type(layer) == LINEAR_MODULE_TYPE:
+            return self.mlp_alphabet_step_size, self.mlp_boundary_idx, self.mlp_percentile
+        return self.cnn_alphabet_step_size, self.cnn_boundary_idx, self.cnn_percentile
+
+    def _layer_deltas(self, layer_indices):
+        """Alphabet step of every layer to be quantized (reference step_algorithm.py:191-192).  They
+        depend on the analog weights only, so all per-neuron radii are computed on the device, brought
+        to the host in ONE copy, and averaged there (see step_algorithm.delta_from_radii); the per-layer
+        loop then never synchronises the host."""
+        radii, sizes = [], []
+        for i in layer_indices:
+            layer = self.analog_network_layers[i]
+            if type(layer) not in (LINEAR_MODULE_TYPE, CONV2D_MODULE_TYPE):
+                raise TypeError(f'The layer type {type(layer)} is not currently supported')
+            W = layer.weight.data.view(layer.weight.shape[0], -1)
+            radii.append(row_radius(W, self._layer_params(layer)[2]))
+            sizes.append(W.shape[0])
+        if not radii:
+            return {}
+        host = torch.cat(radii).cpu()
+        deltas, at = {}, 0
+        for i, n in zip(layer_indices, sizes):
+            step, K, _ = self._layer_params(self.analog_network_layers[i])
+            deltas[i] = delta_from_radii(host[at:at + n].clone(), step, K, self.reg, self.lamb).to(self.device)
+            at += n
+        return deltas
 
     # ------------------------------------------------------------------
     def _populate_linear_layer_input(self, layer_idx):
@@ -232,6 +277,16 @@ class QuantizeNeuralNet:
         else:
             raise TypeError(f'The layer type {type(analog_layer)} is not currently supported')
 
+        world, rank = world_and_rank(self.process_group)
+        sharded = self.shard_forward and world > 1
+        if sharded:
+            B = raw_input_data.shape[0]
+            if B % world != 0:
+                raise ValueError(f"shard_forward needs the batch ({B}) to be a multiple of the world size ({world})")
+            i0, i1 = rank * (B // world), (rank + 1) * (B // world)
+            raw_input_data = raw_input_data[i0:i1]
+            if isinstance(save_input, SaveInputConv2d):
+                save_input.image_range, save_input.full_batch = (i0, i1), B
         with self._Phase(self, layer_idx, 'h2d'):
             images = raw_input_data.to(self.device, non_blocking=True)
         with torch.no_grad():
@@ -245,4 +300,7 @@ class QuantizeNeuralNet:
                         pass
                     finally:
                         handle.remove()
+        if sharded:
+            with self._Phase(self, layer_idx, 'gather_inputs'):
+                return gather_inputs(save_input.inputs[0], save_input.inputs[1], self.process_group)
         return save_input.inputs[0], save_input.inputs[1]

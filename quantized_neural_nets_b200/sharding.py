@@ -8,9 +8,12 @@ import torch.distributed as dist
 
 
 def _world(group):
-    if not (dist.is_available() and dist.is_initialized()):
+    if group is False or not (dist.is_available() and dist.is_initialized()):
         return 1, 0
     return dist.get_world_size(group), dist.get_rank(group)
+
+
+world_and_rank = _world
 
 
 def rows_per_rank(N, world):
@@ -61,3 +64,24 @@ def gather_layer(Q, err2, ref2, n0, n1, groups=1, group=None):
     full = torch.empty((world * per, d + 4), dtype=torch.float32, device=Q.device)
     dist.all_gather_into_tensor(full, mine, group=group)
     return unpack_all(full, N, d)
+
+
+def gather_inputs(X_local, Xq_local, group=None):
+    """Sharded calibration forward: every rank holds the layer inputs of its own images, i.e. a
+    contiguous block of calibration rows (rows of the reference's (m x d) matrices, columns of the
+    feature-major buffers).  One all-gather of the packed pair gives every rank the full X and X~,
+    returned as (m x d) transposed views of feature-major (d x ld) buffers."""
+    world, _ = _world(group)
+    m_local, d = X_local.shape
+    pair = torch.empty((2, d, m_local), dtype=torch.float32, device=X_local.device)
+    pair[0].copy_(X_local.t())
+    pair[1].copy_(Xq_local.t())
+    full = torch.empty((world * 2, d, m_local), dtype=torch.float32, device=X_local.device)
+    dist.all_gather_into_tensor(full, pair, group=group)
+    full = full.view(world, 2, d, m_local)
+    m = world * m_local
+    ld = (m + 3) // 4 * 4
+    out = torch.zeros((2, d, ld), dtype=torch.float32, device=X_local.device) if ld != m else \
+        torch.empty((2, d, ld), dtype=torch.float32, device=X_local.device)
+    out[:, :, :m].view(2, d, world, m_local).copy_(full.permute(1, 2, 0, 3))
+    return out[0, :, :m].t(), out[1, :, :m].t()

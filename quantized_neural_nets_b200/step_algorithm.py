@@ -147,13 +147,26 @@ def _repack(Xfm, m, ld):
     return out, ld
 
 
-def layer_delta(W, step_size, boundary_idx, percentile, reg, lamb):
-    """delta = step * mean_i quantile_pct(|W_i|), minus lamb/K for L0 (step_algorithm.py:191-192).
-    percentile == 1 is the row maximum; both stay on the device (no host sync)."""
+def row_radius(W, percentile):
+    """quantile_pct(|W_i|) per neuron, on the device (percentile == 1 is the row maximum)."""
     absW = torch.abs(W)
-    rad = (absW.amax(dim=1) if percentile == 1 else torch.quantile(absW, percentile, dim=1)).mean()
-    delta = step_size * rad - lamb / boundary_idx if reg == 'L0' else step_size * rad
-    return delta
+    return absW.amax(dim=1) if percentile == 1 else torch.quantile(absW, percentile, dim=1)
+
+
+def delta_from_radii(radii_cpu, step_size, boundary_idx, reg, lamb):
+    """delta = step * mean_i(radius_i), minus lamb/K for L0 (step_algorithm.py:191-192).
+
+    The mean over the N per-neuron radii is taken by torch ON THE HOST: an fp32 mean is not
+    reduction-order independent, a device reduction can land one ulp away from the reference's CPU
+    value, and in ill-conditioned layers (m << d) a one-ulp change of the alphabet is amplified by the
+    greedy recurrence into visibly different paths.  N floats per layer; computed before the solve."""
+    rad = radii_cpu.mean()
+    return step_size * rad - lamb / boundary_idx if reg == 'L0' else step_size * rad
+
+
+def layer_delta(W, step_size, boundary_idx, percentile, reg, lamb):
+    """The layer's alphabet step as a 0-dim CPU tensor (synchronises the stream: N floats D2H)."""
+    return delta_from_radii(row_radius(W, percentile).cpu(), step_size, boundary_idx, reg, lamb)
 
 
 def mode_of(reg, stochastic_quantization):
@@ -168,13 +181,15 @@ def mode_of(reg, stochastic_quantization):
 
 def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, lamb, groups,
                         stochastic_quantization, device, want_adder=False, neuron_range=None, levels=None,
-                        solver=None, return_partials=False):
+                        solver=None, return_partials=False, delta=None):
     """Shared body of ``StepAlgorithm._quantize_layer`` and of the sharded orchestrator.
 
     neuron_range=(n0, n1) restricts the solve to a contiguous slice of output neurons (rows
     outside it are left zero in Q); with return_partials=True the per-neuron squared norms
     (||u_n||^2, ||X w_n||^2 as float64, full length N, zero outside the slice) are returned instead
-    of the reduced errors so that the caller can all-gather them."""
+    of the reduced errors so that the caller can all-gather them.  ``delta`` (0-dim tensor) skips the
+    alphabet computation when the caller has already done it (the orchestrator does it for all layers
+    up front, so the per-layer path never synchronises the host)."""
     if torch.device(device).type != 'cuda':
         raise RuntimeError("libgpfq_b200 runs on CUDA devices only; there is no CPU fallback")
     require_cuda(W, X, Xq)
@@ -183,7 +198,9 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
     dev = W.device
     n0, n1 = (0, N) if neuron_range is None else neuron_range
     Wc = W if W.stride(1) == 1 else W.contiguous()
-    delta = layer_delta(Wc, step_size, boundary_idx, percentile, reg, lamb).to(torch.float32).reshape(1)
+    if delta is None:
+        delta = layer_delta(Wc, step_size, boundary_idx, percentile, reg, lamb)
+    delta = _delta_tensor(delta, dev)
     Q = torch.zeros((N, d), dtype=torch.float32, device=dev)
     Xfm, ldx = feature_major(X)
     Xqfm, ldq = feature_major(Xq)

@@ -112,6 +112,12 @@ def _gloo_worker(rank, world, port, out):
     Q[n0:n1], e[n0:n1], r[n0:n1] = Qtrue[n0:n1], etrue[n0:n1], rtrue[n0:n1]
     Qf, ef, rf = sh.gather_layer(Q, e, r, n0, n1)
     ok = torch.equal(Qf, Qtrue) and torch.equal(ef, etrue) and torch.equal(rf, rtrue)
+    # sharded calibration forward: each rank contributes the calibration rows of its own images
+    m_local, dd = 5, 3
+    Xtrue = torch.randn(world * m_local, dd, generator=g)
+    Xqtrue = torch.randn(world * m_local, dd, generator=g)
+    Xf, Xqf = sh.gather_inputs(Xtrue[rank * m_local:(rank + 1) * m_local], Xqtrue[rank * m_local:(rank + 1) * m_local])
+    ok = ok and torch.equal(Xf, Xtrue) and torch.equal(Xqf, Xqtrue) and Xf.stride(0) == 1 and Xf.stride(1) % 4 == 0
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
