@@ -201,7 +201,8 @@ def workload_config(args):
                         "(BASELINE.json configs[3]); one step = quantize_network() over all layers",
             "global_batch": args.batch, "image": "3x224x224 Gaussian", "weights": "random init (torch.manual_seed(0))",
             "l2": "per-step inputs (8.3 GB of images, up to 400 MB of layer inputs) exceed the 126 MB L2",
-            "parallelism": f"neuron-sharded x{args.gpus}, {args.forward} calibration forward, "
+            "parallelism": "single GPU" if args.gpus == 1 else
+                           f"neuron-sharded x{args.gpus}, {args.forward} calibration forward, "
                            + ("1 all-gather (Q) per layer" if args.forward == "replicated"
                               else "2 all-gathers (layer inputs, Q) per layer")}
 
@@ -238,11 +239,12 @@ def run_cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(pool, read_back, profile=False):
+    def one_step(pool, read_back, profile=False, forward=None):
+        forward = forward or args.forward
         np.random.seed(0)
         qnn = qb.QuantizeNeuralNet(model, args.model, args.batch, BatchPool(pool), args.bits, args.bits, [],
                                    1.16, 1.16, 1, 1, None, 0.1, args.retain, False, dev, profile=profile,
-                                   shard_forward=(args.forward == "sharded"))
+                                   shard_forward=(forward == "sharded" and world > 1))
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -256,16 +258,16 @@ def run_cuda_arm(args):
         barrier()
         return start.elapsed_time(end), qnn, d2h
 
-    def timed(pool, read_back, sampler=None):
-        for _ in range(args.warmup):
-            one_step(pool, read_back)
+    def timed(pool, read_back, sampler=None, forward=None, warmup=None):
+        for _ in range(args.warmup if warmup is None else warmup):
+            one_step(pool, read_back, forward=forward)
         if sampler:
             sampler.start()
         before = _lib.launch_count()
         total = 0.0
         d2h = 0
         for _ in range(args.steps):
-            ms, qnn, d2h = one_step(pool, read_back)
+            ms, qnn, d2h = one_step(pool, read_back, forward=forward)
             total += ms
         launches = _lib.launch_count() - before
         clocks = sampler.stop() if sampler else None
@@ -276,6 +278,10 @@ def run_cuda_arm(args):
 
     total_ms, launches, clocks, qnn, _ = timed(dev_pool, False, ClockSampler(local) if rank == 0 else None)
     e2e_ms, _, _, qnn, d2h = timed(host_pool, True)
+    other_ms = None
+    if world > 1:   # the other multi-GPU forward mode, for the record (same K, one warm-up)
+        other = "replicated" if args.forward == "sharded" else "sharded"
+        other_ms, _, _, _, _ = timed(dev_pool, False, forward=other, warmup=1)
     n_layers = len(qnn.layer_log)
     rel = [float(r) for (_, _, r) in qnn.layer_log]
 
@@ -324,9 +330,13 @@ def run_cuda_arm(args):
                          "frac": (prof["sweep_fp32_instr"] / sweep_s) / fp32_peak if sweep_s > 0 else 0.0},
             },
             "rel_err_mean": sum(rel) / len(rel),
+            "forward_mode": args.forward if world > 1 else "single GPU",
             "phase_ms_per_step": {k: round(v, 2) for k, v in phases.items()},
             "solve_ms_per_layer": [round(per_layer[i].get("solve", 0.0), 3) for i in sorted(per_layer)],
         }
+        if other_ms is not None:
+            out["other_forward_mode"] = {"mode": other, "ms_per_step": other_ms / args.steps,
+                                         "value": units / (other_ms / args.steps * 1e-3)}
         if world == 1 and not args.no_cpu_baseline:
             v, spent, extrap = cpu_reference_sample(shapes)
             out["cpu_baseline"] = {
@@ -351,9 +361,10 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--retain", type=float, default=0.25)
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic image batches cycled by the loader")
-    ap.add_argument("--forward", default="replicated", choices=["replicated", "sharded"],
-                    help="multi-GPU only: replicate the calibration forward on every rank (BASELINE.json's design) or "
-                         "split each batch over the ranks and all-gather the layer inputs")
+    ap.add_argument("--forward", default="sharded", choices=["replicated", "sharded"],
+                    help="multi-GPU only: split each calibration batch over the ranks and all-gather the layer inputs "
+                         "(default; removes the replicated-forward Amdahl term), or replicate the calibration forward "
+                         "on every rank (BASELINE.json's sketch; Q bit-identical to the single-GPU run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: route everything else that native libraries may print

@@ -22,6 +22,7 @@
 // U lives in a solver-private tiled layout  U[j/4][Npad][4]  so that a warp whose lanes own 32
 // consecutive neurons reads/writes 512 contiguous bytes per column quad.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gpfq_common.cuh"
 
@@ -50,7 +51,9 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     p.nblk = (int)ceil_div(d, kB);
     const int max_jt = (int)(p.mpad / kJS);
     p.R = 1;
+    static const int force_r = getenv("GPFQ_FORCE_R") ? atoi(getenv("GPFQ_FORCE_R")) : 0;   // tuning aid
     for (int R : {4, 2, 1}) {
+        if (force_r && R != force_r && R != 1) continue;
         int nt = (int)ceil_div(n_rows, 32 * R);
         if ((int64_t)nt * max_jt >= 140 || R == 1) {
             p.R = R;
@@ -240,7 +243,7 @@ struct SweepArgs {
 };
 
 template <int R>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, R >= 4 ? 1 : 2)
 sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXq, const SweepArgs a) {
     constexpr int TN = 32 * R;
     extern __shared__ __align__(128) unsigned char smem_raw[];

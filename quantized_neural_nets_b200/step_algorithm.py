@@ -222,7 +222,7 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
         err2[g0:g1] = e2
         # ||X w_n||^2 : plain library GEMM (cuBLAS fp32) -- step_algorithm.py:217,219
         Y = torch.matmul(Wc[g0:g1], Xg[:, :m])
-        ref2[g0:g1] = (Y.double() ** 2).sum(dim=1)
+        ref2[g0:g1] = torch.linalg.vector_norm(Y, dim=1).double() ** 2
         if Ures is not None:
             adder = Ures.t()
     if return_partials:
