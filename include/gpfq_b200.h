@@ -25,14 +25,15 @@
 extern "C" {
 #endif
 
-#define GPFQ_ABI_VERSION 1
+#define GPFQ_ABI_VERSION 2
 
 /* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0') */
 enum { GPFQ_MODE_MSQ = 0, GPFQ_MODE_SOFT = 1, GPFQ_MODE_HARD = 2 };
 
-/* solver variants: 0 = blocked direct (exact reference update order, fp32 SIMT),
- *                  1 = Gram form on tcgen05 tensor cores (split-TF32) */
-enum { GPFQ_SOLVER_DIRECT = 0, GPFQ_SOLVER_GRAM = 1 };
+/* solver variants: 0 = blocked direct (exact reference update order, fp32 SIMT);
+ *                  1 = Gram form, Gram matrices formed on tcgen05 tensor cores (split-TF32, 3 MMAs per product);
+ *                  2 = Gram form, Gram matrices formed in fp64 SIMT (exact products) */
+enum { GPFQ_SOLVER_DIRECT = 0, GPFQ_SOLVER_GRAM = 1, GPFQ_SOLVER_GRAM_F64 = 2 };
 
 int gpfq_abi_version(void);
 const char* gpfq_last_error(void);
@@ -57,7 +58,8 @@ int gpfq_im2col_gather_f32(const float* in, int32_t B, int32_t C, int32_t H, int
                            int32_t c_begin, int32_t c_end, const int64_t* idx, int64_t n_idx,
                            float* out, int64_t ld_out, void* stream);
 
-/* Workspace (bytes) gpfq_solve_f32 needs for `n_rows` neurons of a (d, m) problem. */
+/* Workspace (bytes) gpfq_solve_f32 needs for `n_rows` neurons of a (d, m) problem; 0 = this solver
+ * does not support the shape (Gram solvers: d too large). */
 size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m);
 
 /* The greedy path-following solve: replaces StepAlgorithm._quantization
@@ -67,13 +69,16 @@ size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m
  *   Q (N x d, ldq): rows n0..n1-1 written (fp32 alphabet values, as the reference stores them).
  *   levels: optional int8 (N x d, ld = d) signed level indices, rows n0..n1-1 (may be NULL).
  *   row_err2: optional double[n1-n0], ||u_n||^2 of the final residual (may be NULL).
- *   U_out: optional fp32 ((n1-n0) x ldu) row-major final residual matrix (may be NULL).
+ *   row_ref2: optional double[n1-n0], ||X w_n||^2 (step_algorithm.py:217,219); Gram solvers only, must be
+ *             NULL for the direct solver (its caller forms X W^T with a library GEMM).
+ *   U_out: optional fp32 ((n1-n0) x ldu) row-major final residual matrix (may be NULL); direct solver
+ *          only -- the Gram solvers never materialise U.
  */
 int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq,
                    int64_t ldx, int32_t N, int32_t d, int32_t m, int32_t n0, int32_t n1,
                    const float* delta, int32_t K, int32_t mode, float lam, float* Q, int64_t ldq,
-                   int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   int8_t* levels, double* row_err2, double* row_ref2, float* U_out, int64_t ldu,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Optional per-kernel timing for bench.py's roofline object.  Between gpfq_profile_begin() and
  * gpfq_profile_end() every sweep launch of the direct solver is bracketed by CUDA events on its

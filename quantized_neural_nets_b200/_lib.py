@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpfq_b200.so")
 
 MODE_MSQ, MODE_SOFT, MODE_HARD = 0, 1, 2
-SOLVER_DIRECT, SOLVER_GRAM = 0, 1
+SOLVER_DIRECT, SOLVER_GRAM, SOLVER_GRAM_F64 = 0, 1, 2
 
 c_ptr = ctypes.c_void_p  # device pointers travel as integers
 c_i64 = ctypes.c_int64
@@ -32,7 +32,7 @@ SIGNATURES = {
     "gpfq_im2col_gather_f32": (c_i32, [c_ptr] + [c_i32] * 12 + [c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gpfq_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     "gpfq_solve_f32": (c_i32, [c_i32, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
-                               c_ptr, c_i32, c_i32, c_f32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                               c_ptr, c_i32, c_i32, c_f32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
                                ctypes.c_size_t, c_ptr]),
 }
 

@@ -7,6 +7,10 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
                  const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
                  double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream);
+size_t gram_workspace_bytes(int solver, int n_rows, int d, int m);
+int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m,
+               int n_rows, const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
+               double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace gpfq
 
 using namespace gpfq;
@@ -16,13 +20,14 @@ extern "C" {
 size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m) {
     if (n_rows <= 0 || d <= 0 || m <= 0) return 256;
     if (solver == GPFQ_SOLVER_DIRECT) return direct_workspace_bytes(n_rows, d, m);
+    if (solver == GPFQ_SOLVER_GRAM || solver == GPFQ_SOLVER_GRAM_F64) return gram_workspace_bytes(solver, n_rows, d, m);
     return 0;
 }
 
 int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int32_t N,
                    int32_t d, int32_t m, int32_t n0, int32_t n1, const float* delta, int32_t K, int32_t mode, float lam,
-                   float* Q, int64_t ldq, int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+                   float* Q, int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, float* U_out, int64_t ldu,
+                   void* workspace, size_t workspace_bytes, void* stream) {
     GPFQ_REQUIRE(N >= 0 && d >= 0 && m >= 0, "gpfq_solve_f32: negative dimension");
     GPFQ_REQUIRE(0 <= n0 && n0 <= n1 && n1 <= N, "gpfq_solve_f32: bad neuron range [%d, %d) of %d", n0, n1, N);
     GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_HARD, "gpfq_solve_f32: bad mode %d", mode);
@@ -37,6 +42,13 @@ int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, 
     const float* Ws = W + (int64_t)n0 * ldw;
     float* Qs = Q + (int64_t)n0 * ldq;
     int8_t* Ls = levels ? levels + (int64_t)n0 * d : nullptr;
+    if (solver == GPFQ_SOLVER_GRAM || solver == GPFQ_SOLVER_GRAM_F64) {
+        GPFQ_REQUIRE(U_out == nullptr, "gpfq_solve_f32: the Gram solvers do not materialise U (U_out must be NULL)");
+        return gram_solve(solver, Ws, ldw, X, Xq, ldx, d, m, n_rows, delta, K, mode, lam, Qs, ldq, Ls, row_err2,
+                          row_ref2, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
+    GPFQ_REQUIRE(row_ref2 == nullptr || solver != GPFQ_SOLVER_DIRECT,
+                 "gpfq_solve_f32: row_ref2 is produced by the Gram solvers only");
     if (solver == GPFQ_SOLVER_DIRECT)
         return direct_solve(Ws, ldw, X, Xq, ldx, d, m, n_rows, delta, K, mode, lam, Qs, ldq, Ls, row_err2, U_out, ldu,
                             workspace, workspace_bytes, (cudaStream_t)stream);

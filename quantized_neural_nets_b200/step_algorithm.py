@@ -52,27 +52,95 @@ def feature_major(X):
 
 
 def solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, want_err=True, want_residual=False,
-               levels=None, solver=None):
+               levels=None, solver=None, want_ref=False):
     """Run the greedy path for neurons [n0, n1) of W (N x d) against feature-major inputs.
-    Writes rows n0..n1-1 of Q.  Returns (row_err2 float64[n1-n0] | None, U (n1-n0, m) | None)."""
+    Writes rows n0..n1-1 of Q.  Returns (row_err2 | None, U (n1-n0, m) | None, row_ref2 | None);
+    row_ref2 (||X w_n||^2) is produced by the Gram solvers only."""
     solver = DEFAULT_SOLVER if solver is None else solver
     N, d = W.shape
     rows = n1 - n0
     dev = W.device
+    gram = solver in (_lib.SOLVER_GRAM, _lib.SOLVER_GRAM_F64)
     row_err2 = torch.empty(rows, dtype=torch.float64, device=dev) if want_err else None
-    U = torch.empty((rows, m), dtype=torch.float32, device=dev) if want_residual else None
+    row_ref2 = torch.empty(rows, dtype=torch.float64, device=dev) if (want_ref and gram) else None
+    U = torch.empty((rows, m), dtype=torch.float32, device=dev) if (want_residual and not gram) else None
     if rows == 0 or d == 0:
-        if row_err2 is not None:
-            row_err2.zero_()
-        return row_err2, U
+        for t in (row_err2, row_ref2):
+            if t is not None:
+                t.zero_()
+        return row_err2, U, row_ref2
     nbytes = lib.gpfq_workspace_bytes(solver, rows, d, m)
     if nbytes == 0:
-        raise RuntimeError(f"libgpfq_b200: solver {solver} is not available")
+        raise RuntimeError(f"libgpfq_b200: solver {solver} does not support a (d={d}, m={m}) layer")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib.gpfq_solve_f32(solver, ptr(W), W.stride(0), ptr(Xfm), ptr(Xqfm), ldx, N, d, m, n0, n1, ptr(delta),
-                             int(K), mode, float(lamb), ptr(Q), Q.stride(0), ptr(levels), ptr(row_err2), ptr(U),
-                             m, ptr(ws), nbytes, stream_ptr()))
-    return row_err2, U
+                             int(K), mode, float(lamb), ptr(Q), Q.stride(0), ptr(levels), ptr(row_err2),
+                             ptr(row_ref2), ptr(U), m, ptr(ws), nbytes, stream_ptr()))
+    if want_residual and gram:      # the Gram solvers never form U; rebuild it only when somebody asks for it
+        U = torch.matmul(W[n0:n1], Xfm[:, :m]) - torch.matmul(Q[n0:n1], Xqfm[:, :m])
+    return row_err2, U, row_ref2
+
+
+# ---------------------------------------------------------------------------------------------
+# per-layer solver choice "from measured time" (BASELINE.json north_star): the first time a
+# (rows, d, m, mode) shape is seen with solver='auto', every eligible solver is run once on the real
+# data and timed with CUDA events; a Gram candidate is kept only if it is faster AND reproduces at
+# least 99.9 % of the direct solver's levels on that layer.  The choice is cached for the process.
+AUTO = "auto"
+_AUTO_CHOICE = {}
+AUTO_LOG = []          # (key, {solver: ms}, agreement, chosen) for reports
+
+
+def gram_eligible(rows, d, m):
+    """Gram form pays off when the 3 Gram products (~ 3 d^2 m) are cheaper than the direct sweeps (~ 5 N d m)."""
+    return d <= 2048 and m >= 2 * d and rows * 2 >= d
+
+
+def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates):
+    N, d = W.shape
+    times, results = {}, {}
+    for sv in candidates:
+        Qs = torch.zeros((N, d), dtype=torch.float32, device=W.device)
+        for rep in range(2):                                   # first repetition warms caches / attributes
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Qs, n0, n1, want_err=True, solver=sv, want_ref=True)
+            b.record()
+        b.synchronize()
+        times[sv] = a.elapsed_time(b)
+        results[sv] = Qs[n0:n1]
+    base = results[_lib.SOLVER_DIRECT]
+    best, agree_best = _lib.SOLVER_DIRECT, 1.0
+    for sv in candidates:
+        if sv == _lib.SOLVER_DIRECT:
+            continue
+        agree = float((results[sv] == base).float().mean())
+        if agree >= 0.999 and times[sv] < times[best]:
+            best, agree_best = sv, agree
+    return best, times, agree_best
+
+
+def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1):
+    if solver != AUTO:
+        return DEFAULT_SOLVER if solver is None else solver
+    rows, d = n1 - n0, W.shape[1]
+    key = (rows, d, m, mode)
+    if key not in _AUTO_CHOICE:
+        candidates = [_lib.SOLVER_DIRECT]
+        if gram_eligible(rows, d, m):
+            for sv in AUTO_GRAM_CANDIDATES:
+                if lib.gpfq_workspace_bytes(sv, rows, d, m) > 0:
+                    candidates.append(sv)
+        if len(candidates) == 1:
+            _AUTO_CHOICE[key] = _lib.SOLVER_DIRECT
+        else:
+            best, times, agree = _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates)
+            _AUTO_CHOICE[key] = best
+            AUTO_LOG.append((key, times, agree, best))
+    return _AUTO_CHOICE[key]
+
+
+AUTO_GRAM_CANDIDATES = [_lib.SOLVER_GRAM_F64]
 
 
 class StepAlgorithm:
@@ -116,8 +184,8 @@ class StepAlgorithm:
             Xqfm, ldq = _repack(Xqfm, m, ldx)
         delta = _delta_tensor(step_size, W.device)
         Qc = Q if (Q.stride(1) == 1) else torch.empty((N, d), dtype=torch.float32, device=W.device)
-        _, Ures = solve_rows(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Qc, 0, N,
-                             want_err=False, want_residual=True)
+        _, Ures, _ = solve_rows(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Qc, 0, N,
+                                want_err=False, want_residual=True)
         if Qc is not Q:
             Q.copy_(Qc)
         U.copy_(Ures)
@@ -216,13 +284,17 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
             continue
         Xg = Xfm[g * d:(g + 1) * d]
         Xqg = Xqfm[g * d:(g + 1) * d]
-        e2, Ures = solve_rows(Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, Q, g0, g1,
-                              want_err=True, want_residual=(want_adder and groups == 1), levels=levels,
-                              solver=solver)
+        sv = resolve_solver(solver, Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, g0, g1)
+        e2, Ures, r2 = solve_rows(Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, Q, g0, g1,
+                                  want_err=True, want_residual=(want_adder and groups == 1), levels=levels,
+                                  solver=sv, want_ref=True)
         err2[g0:g1] = e2
-        # ||X w_n||^2 : plain library GEMM (cuBLAS fp32) -- step_algorithm.py:217,219
-        Y = torch.matmul(Wc[g0:g1], Xg[:, :m])
-        ref2[g0:g1] = torch.linalg.vector_norm(Y, dim=1).double() ** 2
+        if r2 is not None:
+            ref2[g0:g1] = r2
+        else:
+            # ||X w_n||^2 : plain library GEMM (cuBLAS fp32) -- step_algorithm.py:217,219
+            Y = torch.matmul(Wc[g0:g1], Xg[:, :m])
+            ref2[g0:g1] = torch.linalg.vector_norm(Y, dim=1).double() ** 2
         if Ures is not None:
             adder = Ures.t()
     if return_partials:

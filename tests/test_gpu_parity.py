@@ -180,3 +180,41 @@ def test_errors_are_loud(qb):
         z = torch.zeros(4, 4, device=DEV)
         qb.StepAlgorithm._quantize_layer(z, torch.zeros(8, 4, device=DEV), torch.zeros(8, 4, device=DEV), 8, 0.1, 8, 1,
                                          None, 0.1, 1, True, DEV)
+
+
+@pytest.mark.parametrize("reg,lam", [(None, 0.0), ("L1", 0.003), ("L0", 0.003)])
+def test_gram_f64_solver_vs_oracle(qb, reg, lam):
+    """Gram-form solver (fp64 Gram matrices) against the oracle on a layer with m >> d and N >= d, the regime
+    it is selected for; levels, both error norms and the denominators must match."""
+    from quantized_neural_nets_b200 import _lib
+    from quantized_neural_nets_b200.step_algorithm import quantize_layer_impl, reduce_errors
+    W, X, Xq = gc._problem(seed=79, N=150, d=70, m=2500, relu=True, xq_noise=0.02, zero_xq=(9,))
+    K, step = 8, 1.16 / 8
+    Qo, erro, relo, _, rel_addo = orc.quantize_layer(W, X, Xq, X.shape[0], step, K, 1, reg, lam, 1, False)
+    Q, e2, r2 = quantize_layer_impl(W.to(DEV), X.to(DEV), Xq.to(DEV), X.shape[0], step, K, 1, reg, lam, 1, False, DEV,
+                                    solver=_lib.SOLVER_GRAM_F64, return_partials=True)
+    err, rel, _, rel_add = reduce_errors(e2, r2, 1)
+    delta = orc.layer_step_size(W, step, K, 1, reg, lam)
+    lv, lvo = orc.level_index(Q.cpu(), delta, reg, lam), orc.level_index(Qo, delta, reg, lam)
+    assert (lv == lvo).float().mean().item() >= 0.999
+    assert abs(rel.item() - relo.item()) <= 1e-3 * relo.item()
+    assert abs(err.item() - erro.item()) <= 1e-3 * erro.item()
+    if torch.equal(lv, lvo):
+        np.testing.assert_allclose(rel_add.cpu().numpy(), rel_addo.numpy(), rtol=2e-3)
+
+
+def test_auto_solver_picks_from_measured_time(qb):
+    from quantized_neural_nets_b200 import _lib, step_algorithm as sa
+    W, X, Xq = gc._problem(seed=80, N=256, d=64, m=20000, relu=True, xq_noise=0.02)
+    W, X, Xq = W.to(DEV), X.to(DEV), Xq.to(DEV)
+    sa._AUTO_CHOICE.clear()
+    Qa, e2a, r2a = sa.quantize_layer_impl(W, X, Xq, X.shape[0], 1.16 / 8, 8, 1, None, 0.1, 1, False, DEV, solver=sa.AUTO,
+                                          return_partials=True)
+    assert len(sa._AUTO_CHOICE) == 1 and sa.AUTO_LOG, "the eligible shape must have been timed"
+    key, times, agree, chosen = sa.AUTO_LOG[-1]
+    assert set(times) >= {_lib.SOLVER_DIRECT, _lib.SOLVER_GRAM_F64} and chosen in times
+    Qd, e2d, r2d = sa.quantize_layer_impl(W, X, Xq, X.shape[0], 1.16 / 8, 8, 1, None, 0.1, 1, False, DEV,
+                                          solver=_lib.SOLVER_DIRECT, return_partials=True)
+    assert (Qa == Qd).float().mean().item() >= 0.999
+    assert abs(e2a.sum().item() - e2d.sum().item()) <= 2e-3 * e2d.sum().item()
+    assert abs(r2a.sum().item() - r2d.sum().item()) <= 1e-4 * r2d.sum().item()
