@@ -244,7 +244,8 @@ def run_cuda_arm(args):
         np.random.seed(0)
         qnn = qb.QuantizeNeuralNet(model, args.model, args.batch, BatchPool(pool), args.bits, args.bits, [],
                                    1.16, 1.16, 1, 1, None, 0.1, args.retain, False, dev, profile=profile,
-                                   shard_forward=(forward == "sharded" and world > 1))
+                                   shard_forward=(forward == "sharded" and world > 1),
+                                   solver=None if args.solver == "direct" else args.solver)
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -331,6 +332,8 @@ def run_cuda_arm(args):
             },
             "rel_err_mean": sum(rel) / len(rel),
             "forward_mode": args.forward if world > 1 else "single GPU",
+            "solver": args.solver,
+            "solver_choices": solver_choices(),
             "phase_ms_per_step": {k: round(v, 2) for k, v in phases.items()},
             "solve_ms_per_layer": [round(per_layer[i].get("solve", 0.0), 3) for i in sorted(per_layer)],
         }
@@ -350,6 +353,15 @@ def run_cuda_arm(args):
     return out
 
 
+def solver_choices():
+    """{"N x d x m": solver name} for the shapes the autotuner timed (rank 0's slices)."""
+    from quantized_neural_nets_b200 import step_algorithm as sa
+    names = {0: "direct", 1: "gram_tcgen05", 2: "gram_f64"}
+    return {f"{k[0]}x{k[1]}x{k[2]}": {"chosen": names[ch], "agree": round(ag, 6),
+                                      "ms": {names[s]: round(t, 3) for s, t in tm.items()}}
+            for (k, tm, ag, ch) in sa.AUTO_LOG}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -365,6 +377,9 @@ def main():
                     help="multi-GPU only: split each calibration batch over the ranks and all-gather the layer inputs "
                          "(default; removes the replicated-forward Amdahl term), or replicate the calibration forward "
                          "on every rank (BASELINE.json's sketch; Q bit-identical to the single-GPU run)")
+    ap.add_argument("--solver", default="auto", choices=["auto", "direct"],
+                    help="auto: per layer, direct vs Gram (tcgen05 / fp64) picked from measured time behind a 99.9 %% "
+                         "level-agreement gate during warm-up; direct: blocked direct solver everywhere")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: route everything else that native libraries may print

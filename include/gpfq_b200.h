@@ -62,6 +62,13 @@ int gpfq_im2col_gather_f32(const float* in, int32_t B, int32_t C, int32_t H, int
  * does not support the shape (Gram solvers: d too large). */
 size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m);
 
+/* Gram matrices of the layer inputs (the tensor-core piece of the Gram solvers, exposed for tests and
+ * profiling):  GT = X Xq^T,  H = Xq Xq^T,  A = X X^T, each (d x ldg) fp64 row-major with ldg = round_up(d, 64).
+ * solver = GPFQ_SOLVER_GRAM (tcgen05 split-TF32) or GPFQ_SOLVER_GRAM_F64 (fp64 SIMT).  Workspace:
+ * gpfq_workspace_bytes(solver, 1, d, m). */
+int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, int32_t d, int32_t m,
+                  double* GT, double* H, double* A, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The greedy path-following solve: replaces StepAlgorithm._quantization
  * (step_algorithm.py:107-148) plus the residual norms of _quantize_layer (:216-219) for
  * neurons [n0, n1) of W.

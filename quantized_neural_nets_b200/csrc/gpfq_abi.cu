@@ -83,6 +83,23 @@ int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_
     return 0;
 }
 
+int make_tensor_map_2d_sw128(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                             int box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    GPFQ_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this CUDA driver");
+    GPFQ_REQUIRE(((uintptr_t)base & 15) == 0 && (ld % 4) == 0 && box_cols * sizeof(float) == 128,
+                 "tensor map (SWIZZLE_128B): bad alignment or box");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GPFQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (SWIZZLE_128B) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void quantize_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n,
                                 const float* __restrict__ delta_p, float Kf, int mode, float lam) {

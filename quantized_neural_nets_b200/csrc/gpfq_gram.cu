@@ -332,6 +332,24 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
     }
 }
 
+// Gram matrices only (C ABI gpfq_gram_f32): GT, H, A as (d x ldg) fp64 with ldg = round_up(d, 64).
+int gram_matrices(int solver, const float* X, const float* Xq, int64_t ldx, int d, int m, double* GT, double* H,
+                  double* A, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const GramPlan p = gram_plan(solver, d, m);
+    GPFQ_REQUIRE(workspace_bytes >= p.total, "gpfq_gram_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
+    unsigned char* ws = (unsigned char*)workspace;
+    if (solver == GPFQ_SOLVER_GRAM_F64) {
+        double* part = (double*)(ws + p.off_part);
+        gram_f64_kernel<<<dim3(p.tiles, p.tiles, p.splits), 256, 0, stream>>>(X, Xq, ldx, d, m, p.dpad, p.slab, part);
+        GPFQ_CHECK_LAUNCH();
+        gram_f64_finish_kernel<<<(unsigned)ceil_div((int64_t)p.dpad * p.dpad, 256), 256, 0, stream>>>(part, p.splits,
+                                                                                                     p.dpad, GT, H, A);
+        GPFQ_CHECK_LAUNCH();
+        return 0;
+    }
+    return gram_tc_form(X, Xq, ldx, d, m, GT, H, A, p.dpad, ws + p.off_scratch, workspace_bytes - p.off_scratch, stream);
+}
+
 int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m,
                int n_rows, const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
                double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes, cudaStream_t stream) {

@@ -11,6 +11,8 @@ size_t gram_workspace_bytes(int solver, int n_rows, int d, int m);
 int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m,
                int n_rows, const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
                double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int gram_matrices(int solver, const float* X, const float* Xq, int64_t ldx, int d, int m, double* GT, double* H,
+                  double* A, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace gpfq
 
 using namespace gpfq;
@@ -22,6 +24,15 @@ size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m
     if (solver == GPFQ_SOLVER_DIRECT) return direct_workspace_bytes(n_rows, d, m);
     if (solver == GPFQ_SOLVER_GRAM || solver == GPFQ_SOLVER_GRAM_F64) return gram_workspace_bytes(solver, n_rows, d, m);
     return 0;
+}
+
+int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, int32_t d, int32_t m, double* GT,
+                  double* H, double* A, void* workspace, size_t workspace_bytes, void* stream) {
+    GPFQ_REQUIRE(solver == GPFQ_SOLVER_GRAM || solver == GPFQ_SOLVER_GRAM_F64, "gpfq_gram_f32: solver must be a Gram variant");
+    GPFQ_REQUIRE(d > 0 && m > 0 && ldx >= m && (ldx % 4) == 0, "gpfq_gram_f32: bad shape");
+    GPFQ_REQUIRE(X && Xq && GT && H && A && workspace, "gpfq_gram_f32: null pointer");
+    GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "gpfq_gram_f32: workspace must be 256-byte aligned");
+    return gram_matrices(solver, X, Xq, ldx, d, m, GT, H, A, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int32_t N,

@@ -140,7 +140,7 @@ def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1):
     return _AUTO_CHOICE[key]
 
 
-AUTO_GRAM_CANDIDATES = [_lib.SOLVER_GRAM_F64]
+AUTO_GRAM_CANDIDATES = [_lib.SOLVER_GRAM, _lib.SOLVER_GRAM_F64]
 
 
 class StepAlgorithm:

@@ -182,17 +182,18 @@ def test_errors_are_loud(qb):
                                          None, 0.1, 1, True, DEV)
 
 
+@pytest.mark.parametrize("solver", [2, 1], ids=["gram_f64", "gram_tcgen05"])
 @pytest.mark.parametrize("reg,lam", [(None, 0.0), ("L1", 0.003), ("L0", 0.003)])
-def test_gram_f64_solver_vs_oracle(qb, reg, lam):
-    """Gram-form solver (fp64 Gram matrices) against the oracle on a layer with m >> d and N >= d, the regime
-    it is selected for; levels, both error norms and the denominators must match."""
+def test_gram_solvers_vs_oracle(qb, reg, lam, solver):
+    """Gram-form solvers (fp64 SIMT and tcgen05 split-TF32 Gram matrices) against the oracle on a layer with
+    m >> d and N >= d, the regime they are selected for; levels, both error norms and the denominators must match."""
     from quantized_neural_nets_b200 import _lib
     from quantized_neural_nets_b200.step_algorithm import quantize_layer_impl, reduce_errors
     W, X, Xq = gc._problem(seed=79, N=150, d=70, m=2500, relu=True, xq_noise=0.02, zero_xq=(9,))
     K, step = 8, 1.16 / 8
     Qo, erro, relo, _, rel_addo = orc.quantize_layer(W, X, Xq, X.shape[0], step, K, 1, reg, lam, 1, False)
     Q, e2, r2 = quantize_layer_impl(W.to(DEV), X.to(DEV), Xq.to(DEV), X.shape[0], step, K, 1, reg, lam, 1, False, DEV,
-                                    solver=_lib.SOLVER_GRAM_F64, return_partials=True)
+                                    solver=solver, return_partials=True)
     err, rel, _, rel_add = reduce_errors(e2, r2, 1)
     delta = orc.layer_step_size(W, step, K, 1, reg, lam)
     lv, lvo = orc.level_index(Q.cpu(), delta, reg, lam), orc.level_index(Qo, delta, reg, lam)
@@ -212,9 +213,30 @@ def test_auto_solver_picks_from_measured_time(qb):
                                           return_partials=True)
     assert len(sa._AUTO_CHOICE) == 1 and sa.AUTO_LOG, "the eligible shape must have been timed"
     key, times, agree, chosen = sa.AUTO_LOG[-1]
-    assert set(times) >= {_lib.SOLVER_DIRECT, _lib.SOLVER_GRAM_F64} and chosen in times
+    assert set(times) >= {_lib.SOLVER_DIRECT, _lib.SOLVER_GRAM, _lib.SOLVER_GRAM_F64} and chosen in times
     Qd, e2d, r2d = sa.quantize_layer_impl(W, X, Xq, X.shape[0], 1.16 / 8, 8, 1, None, 0.1, 1, False, DEV,
                                           solver=_lib.SOLVER_DIRECT, return_partials=True)
     assert (Qa == Qd).float().mean().item() >= 0.999
     assert abs(e2a.sum().item() - e2d.sum().item()) <= 2e-3 * e2d.sum().item()
     assert abs(r2a.sum().item() - r2d.sum().item()) <= 1e-4 * r2d.sum().item()
+
+
+def test_gram_matrices_tcgen05_accuracy(qb):
+    """The tensor-core Gram kernel (TMA + tcgen05.mma kind::tf32 x3 + TMEM ping-pong) against float64."""
+    from quantized_neural_nets_b200._lib import lib, check, ptr, stream_ptr
+    d, m = 200, 5000      # not multiples of the 128 x 128 x 32 tile
+    g = torch.Generator(device=DEV).manual_seed(0)
+    ld = (m + 3) // 4 * 4
+    X = torch.relu(torch.randn(d, ld, device=DEV, generator=g)); X[:, m:] = 0
+    Xq = torch.relu(X + 0.02 * torch.randn(d, ld, device=DEV, generator=g)); Xq[:, m:] = 0
+    ldg = (d + 63) // 64 * 64
+    for solver, tol in ((1, 2e-6), (2, 1e-13)):
+        nbytes = lib.gpfq_workspace_bytes(solver, 1, d, m)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+        out = [torch.zeros((ldg, ldg), dtype=torch.float64, device=DEV) for _ in range(3)]
+        check(lib.gpfq_gram_f32(solver, ptr(X), ptr(Xq), ld, d, m, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(ws), nbytes,
+                                stream_ptr()))
+        Xd, Xqd = X[:, :m].double(), Xq[:, :m].double()
+        for got, want in zip(out, (Xd @ Xqd.T, Xqd @ Xqd.T, Xd @ Xd.T)):
+            rel = ((got[:d, :d] - want).norm() / want.norm()).item()
+            assert rel < tol, (solver, rel)

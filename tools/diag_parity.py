@@ -38,6 +38,14 @@ for i, layer in enumerate(qnn.analog_network_layers):
         dl = orc.layer_step_size(Wc, 1.16 / K, K, 1, None, 0.1)
         Q = torch.zeros_like(W); U = torch.zeros(W.shape[0], X.shape[0], device=DEV)
         qb.StepAlgorithm._quantization(W, Q, U, X, Xq, qb.StepAlgorithm._msq, dl.to(DEV), K, 0.1)
+    elif os.environ.get("SOLVER"):
+        from quantized_neural_nets_b200 import step_algorithm as sa
+        sv = int(os.environ["SOLVER"])
+        if not sa.gram_eligible(W.shape[0], W.shape[1], X.shape[0]):
+            sv = 0
+        Q, e2, r2 = sa.quantize_layer_impl(W, X, Xq, X.shape[0], 1.16 / K, K, 1, None, 0.1, 1, False, DEV, solver=sv,
+                                           return_partials=True)
+        print(f"   [solver {sv}]", end="")
     else:
         Q, err, rel, _, _ = qb.StepAlgorithm._quantize_layer(W, X, Xq, X.shape[0], 1.16 / K, K, 1, None, 0.1, 1, False, DEV)
     Qo, erro, relo, _, _ = orc.quantize_layer(Wc, Xc, Xqc, Xc.shape[0], 1.16 / K, K, 1, None, 0.1, 1, False)
