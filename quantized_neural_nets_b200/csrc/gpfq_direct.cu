@@ -49,24 +49,37 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     p.mpad = round_up(std::max(m, 1), kJS);
     p.Npad = round_up(std::max(n_rows, 1), 128);
     p.nblk = (int)ceil_div(d, kB);
-    const int max_jt = (int)(p.mpad / kJS);
-    p.R = 1;
+    const int stages = (int)(p.mpad / kJS);
+    const int min_jt = (int)ceil_div(p.mpad, kMaxTJ);
     static const int force_r = getenv("GPFQ_FORCE_R") ? atoi(getenv("GPFQ_FORCE_R")) : 0;   // tuning aid
+    // Pick (R, j_tiles) with a small cost model: CTAs run in waves of 148 x (CTAs per SM); a CTA costs a fixed
+    // start-up/teardown (barriers, first TMA and U loads, cross-warp combine) plus its stages; lanes of padded
+    // neurons are wasted work.  Measured issue efficiencies: R=4 0.63, R=2 0.50 (2 CTAs/SM), R=1 0.40.
+    double best = 1e300;
     for (int R : {4, 2, 1}) {
-        if (force_r && R != force_r && R != 1) continue;
-        int nt = (int)ceil_div(n_rows, 32 * R);
-        if ((int64_t)nt * max_jt >= 140 || R == 1) {
-            p.R = R;
-            break;
+        if (force_r && R != force_r) continue;
+        const int TN = 32 * R;
+        const int nt = (int)ceil_div(n_rows, TN);
+        const int per_sm = (R >= 4) ? 1 : 2;
+        const double eff = R == 4 ? 0.63 : R == 2 ? 0.50 : 0.40;
+        const double stage_cycles = (double)TN * kJS * 5.0 * kB / 128.0 / eff * per_sm;   // SM shared by per_sm CTAs
+        const double fixed_cycles = 16000.0;
+        for (int jt = min_jt; jt <= stages; ++jt) {
+            const int tj_stages = (int)ceil_div(stages, jt);
+            const int jt_eff = (int)ceil_div(stages, tj_stages);
+            const int64_t ctas = (int64_t)nt * jt_eff;
+            const double waves = (double)ceil_div(ctas, 148 * per_sm);
+            const double cost = waves * (fixed_cycles + tj_stages * stage_cycles);
+            if (cost < best * 0.999) {
+                best = cost;
+                p.R = R;
+                p.TJ = tj_stages * kJS;
+                p.j_tiles = jt_eff;
+            }
         }
     }
     p.TN = 32 * p.R;
     p.n_tiles = (int)ceil_div(n_rows, p.TN);
-    int want = std::max(1, (2 * 148 + p.n_tiles - 1) / p.n_tiles);
-    int jt = std::min(max_jt, want);
-    jt = std::max<int>(jt, (int)ceil_div(p.mpad, kMaxTJ));
-    p.TJ = (int)round_up(ceil_div(p.mpad, jt), kJS);
-    p.j_tiles = (int)ceil_div(p.mpad, p.TJ);
     // block-Gram kernel: split the m-long dot products into slices so the grid fills the GPU
     int gs = std::max(1, std::min<int>((int)ceil_div(m, 256), (int)ceil_div(2 * 148, p.nblk)));
     p.gram_slice_len = (int)round_up(ceil_div(std::max(m, 1), gs), 32);
@@ -93,42 +106,71 @@ size_t direct_workspace_bytes(int n_rows, int d, int m) { return make_plan(n_row
 // ------------------------------------------------------------------------------------------
 // Block Gram entries, fp64.  For block b and s,t in [0,kB):
 //   G[b][t][s] = <xq_{t0+s}, x_{t0+t}>     H[b][t][s] = <xq_{t0+s}, xq_{t0+t}>
-// grid (nblk, slices); each thread owns a 2x2 (t,s) sub-tile of both matrices.
+// grid (nblk, slices).  256 threads = 4 column groups x (8 x 8) threads, each thread a 4x4 (t,s) register tile
+// of both matrices over its group's 16 of the 64 staged columns; groups are combined through shared memory.
+constexpr int kBGC = 64;   // columns staged per iteration
 __global__ void __launch_bounds__(256) block_gram_kernel(const float* __restrict__ X, const float* __restrict__ Xq,
                                                          int64_t ldx, int d, int m, int slice_len, int slices,
                                                          double* __restrict__ gpart) {
-    __shared__ double xs[kB][33];
-    __shared__ double xqs[kB][33];
+    __shared__ double xs[kB][kBGC + 1];
+    __shared__ double xqs[kB][kBGC + 1];
     const int blk = blockIdx.x, sl = blockIdx.y;
     const int t0 = blk * kB;
     const int jb = sl * slice_len, je = min(jb + slice_len, m);
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double g00 = 0, g01 = 0, g10 = 0, g11 = 0, h00 = 0, h01 = 0, h10 = 0, h11 = 0;
-    for (int j0 = jb; j0 < je; j0 += 32) {
-        const int col = threadIdx.x & 31;
+    const int cg = threadIdx.x >> 6, ty = (threadIdx.x >> 3) & 7, tx = threadIdx.x & 7;
+    double g[4][4] = {}, h[4][4] = {};
+    for (int j0 = jb; j0 < je; j0 += kBGC) {
+        const int col = threadIdx.x & 63;
 #pragma unroll
-        for (int r = threadIdx.x >> 5; r < kB; r += 8) {
+        for (int r = threadIdx.x >> 6; r < kB; r += 4) {
             const bool ok = (t0 + r < d) && (j0 + col < je);
             const int64_t a = (int64_t)(t0 + r) * ldx + j0 + col;
             xs[r][col] = ok ? (double)X[a] : 0.0;
             xqs[r][col] = ok ? (double)Xq[a] : 0.0;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-            const double a0 = xqs[2 * tx][j], a1 = xqs[2 * tx + 1][j];     // xq_s
-            const double b0 = xs[2 * ty][j], b1 = xs[2 * ty + 1][j];       // x_t
-            const double c0 = xqs[2 * ty][j], c1 = xqs[2 * ty + 1][j];     // xq_t
-            g00 = fma(a0, b0, g00); g01 = fma(a1, b0, g01); g10 = fma(a0, b1, g10); g11 = fma(a1, b1, g11);
-            h00 = fma(a0, c0, h00); h01 = fma(a1, c0, h01); h10 = fma(a0, c1, h10); h11 = fma(a1, c1, h11);
+#pragma unroll 4
+        for (int jj = 0; jj < kBGC / 4; ++jj) {
+            const int j = cg * (kBGC / 4) + jj;
+            double qs_[4], xt[4], qt[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                qs_[e] = xqs[4 * tx + e][j];      // xq_s
+                xt[e] = xs[4 * ty + e][j];        // x_t
+                qt[e] = xqs[4 * ty + e][j];       // xq_t
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    g[r][c] = fma(qs_[c], xt[r], g[r][c]);
+                    h[r][c] = fma(qs_[c], qt[r], h[r][c]);
+                }
         }
         __syncthreads();
     }
+    // combine the 4 column groups in a fixed order through shared memory (reuses the staging buffers)
+    double* red = &xs[0][0];                           // needs 2 * 1024 doubles <= 2 * 32 * 65
     double* gp = gpart + ((int64_t)(blk * slices + sl) * 2) * kB * kB;
-    double* hp = gp + kB * kB;
-    const int t = 2 * ty, s = 2 * tx;
-    gp[t * kB + s] = g00; gp[t * kB + s + 1] = g01; gp[(t + 1) * kB + s] = g10; gp[(t + 1) * kB + s + 1] = g11;
-    hp[t * kB + s] = h00; hp[t * kB + s + 1] = h01; hp[(t + 1) * kB + s] = h10; hp[(t + 1) * kB + s + 1] = h11;
+    for (int grp = 0; grp < 4; ++grp) {
+        if (cg == grp) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int idx = (4 * ty + r) * kB + 4 * tx + c;
+                    if (grp == 0) {
+                        red[idx] = g[r][c];
+                        red[kB * kB + idx] = h[r][c];
+                    } else {
+                        red[idx] += g[r][c];
+                        red[kB * kB + idx] += h[r][c];
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < 2 * kB * kB; e += 256) gp[e] = red[e];
 }
 
 // Fixed-order sum over slices; norm32[t] = (sqrt(fl32(sum xq_t^2)))^2 as linalg.norm(.)**2 gives
@@ -172,31 +214,46 @@ struct RecurArgs {
     float Kf, lam;
 };
 
-__global__ void __launch_bounds__(128) recur_kernel(RecurArgs a) {
+// WPN warps cooperate on the partial sums of one neuron (fixed split and fixed combination order);
+// the neuron's first warp then runs the 32 sequential decisions.  CTA = 8 warps = 8 / WPN neurons.
+template <int WPN>
+__global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
     __shared__ double Gs[kB][kB + 1];
     __shared__ double Hs[kB][kB + 1];
     __shared__ float ns[kB];
+    __shared__ double psum[8][kB];
     for (int e = threadIdx.x; e < kB * kB; e += blockDim.x) {
         Gs[e / kB][e % kB] = a.G[e];
         Hs[e / kB][e % kB] = a.H[e];
     }
     if (threadIdx.x < kB) ns[threadIdx.x] = a.norm32[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (n >= a.n_rows) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * (8 / WPN) + warp / WPN;
+    const int piece = warp % WPN;
     double p = 0.0;
-    if (!a.first) {
+    if (!a.first && n < a.n_rows) {
         const double* src = a.part + (int64_t)n * kB + lane;
         const int64_t stride = a.Npad * kB;
-        int jt = 0;
-        for (; jt + 4 <= a.j_tiles; jt += 4) {
+        const int per = (a.j_tiles + WPN - 1) / WPN;
+        int jt = piece * per;
+        const int jt_end = min(jt + per, a.j_tiles);
+        for (; jt + 4 <= jt_end; jt += 4) {
             const double v0 = src[(int64_t)jt * stride], v1 = src[(int64_t)(jt + 1) * stride];
             const double v2 = src[(int64_t)(jt + 2) * stride], v3 = src[(int64_t)(jt + 3) * stride];
             p += v0; p += v1; p += v2; p += v3;      // fixed order
         }
-        for (; jt < a.j_tiles; ++jt) p += src[(int64_t)jt * stride];
+        for (; jt < jt_end; ++jt) p += src[(int64_t)jt * stride];
     }
+    if (WPN > 1) {
+        psum[warp][lane] = p;
+        __syncthreads();
+        if (piece != 0) return;
+        p = 0.0;
+#pragma unroll
+        for (int k = 0; k < WPN; ++k) p += psum[warp + k][lane];
+    }
+    if (n >= a.n_rows) return;
     const int t_mine = a.t0 + lane;
     const float w = (t_mine < a.d) ? a.W[(int64_t)n * a.ldw + t_mine] : 0.f;
     const float delta = *a.delta;
@@ -520,7 +577,9 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         r.norm32 = norm32 + (size_t)blk * kB; r.delta = delta; r.Npad = p.Npad;
         r.n_rows = n_rows; r.d = d; r.t0 = t0; r.bvalid = bvalid; r.j_tiles = p.j_tiles;
         r.first = (blk == 0); r.mode = mode; r.Kf = (float)K; r.lam = lam;
-        recur_kernel<<<(unsigned)ceil_div(n_rows, 4), 128, 0, stream>>>(r);
+        if (p.j_tiles >= 24) recur_kernel<8><<<(unsigned)n_rows, 256, 0, stream>>>(r);
+        else if (p.j_tiles >= 8) recur_kernel<2><<<(unsigned)ceil_div(n_rows, 4), 256, 0, stream>>>(r);
+        else recur_kernel<1><<<(unsigned)ceil_div(n_rows, 8), 256, 0, stream>>>(r);
         GPFQ_CHECK_LAUNCH();
         profile_count_other(1);
 
