@@ -40,8 +40,9 @@ constexpr int kMaxTJ = 4096;      // keeps every fp32 accumulation chain <= 512 
 
 struct DirectPlan {
     int R, TN, n_tiles, TJ, j_tiles, nblk, gram_slices, gram_slice_len;
+    int pR, p_n_tiles, pTJ, p_j_tiles, use_persistent;     // single-launch variant
     int64_t Npad, mpad;
-    size_t off_U, off_G, off_H, off_norm, off_gpart, off_part, off_epart, total;
+    size_t off_U, off_G, off_H, off_norm, off_gpart, off_part, off_epart, off_sync, total;
 };
 
 static DirectPlan make_plan(int n_rows, int d, int m) {
@@ -80,6 +81,36 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     }
     p.TN = 32 * p.R;
     p.n_tiles = (int)ceil_div(n_rows, p.TN);
+    // Single-launch (persistent) variant: one tile pass per CTA per block, recurrence inside the kernel.
+    double pbest = 1e300;
+    for (int R : {2, 1}) {
+        const int TN = 32 * R;
+        const int nt = (int)ceil_div(n_rows, TN);
+        const double eff = R == 2 ? 0.50 : 0.40;
+        const double stage_cycles = (double)TN * kJS * 5.0 * kB / 128.0 / eff;
+        const double recur_cycles = 9000.0 * (double)ceil_div(TN, kWarps * 4);
+        for (int jt = min_jt; jt <= stages; ++jt) {
+            const int tj_stages = (int)ceil_div(stages, jt);
+            const int jt_eff = (int)ceil_div(stages, tj_stages);
+            const int64_t tiles = (int64_t)nt * jt_eff;
+            const double cost = (double)ceil_div(tiles, 148) * (7000.0 + tj_stages * stage_cycles) + recur_cycles +
+                                40.0 * jt_eff;      // the last arrival sums jt_eff partials per neuron
+            if (cost < pbest * 0.999) {
+                pbest = cost;
+                p.pR = R;
+                p.pTJ = tj_stages * kJS;
+                p.p_j_tiles = jt_eff;
+            }
+        }
+    }
+    p.p_n_tiles = (int)ceil_div(n_rows, 32 * p.pR);
+    // per block the multi-launch path pays two launches (~6 us each incl. CPU cost) on top of its kernels
+    static const int force_p = getenv("GPFQ_PERSISTENT") ? atoi(getenv("GPFQ_PERSISTENT")) : -1;   // tuning aid
+    // Measured on B200 (r01): correct, but its serialised per-block chain (flag -> stage -> sweep -> ticket ->
+    // recurrence) costs 38 us per block against 31 us for the multi-launch path, whose recurrences spread over
+    // all SMs.  Kept for GPFQ_PERSISTENT=1 experiments; not selected by default.
+    p.use_persistent = (force_p >= 0) ? force_p : 0;
+    (void)pbest;
     // block-Gram kernel: split the m-long dot products into slices so the grid fills the GPU
     int gs = std::max(1, std::min<int>((int)ceil_div(m, 256), (int)ceil_div(2 * 148, p.nblk)));
     p.gram_slice_len = (int)round_up(ceil_div(std::max(m, 1), gs), 32);
@@ -95,8 +126,10 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     p.off_H = take((size_t)p.nblk * kB * kB * sizeof(double));
     p.off_norm = take((size_t)p.nblk * kB * sizeof(float));
     p.off_gpart = take((size_t)p.nblk * p.gram_slices * 2 * kB * kB * sizeof(double));
-    p.off_part = take((size_t)p.j_tiles * p.Npad * kB * sizeof(double));
-    p.off_epart = take((size_t)p.j_tiles * p.Npad * sizeof(double));
+    const int max_jt = std::max(p.j_tiles, p.p_j_tiles);
+    p.off_part = take((size_t)max_jt * p.Npad * kB * sizeof(double));
+    p.off_epart = take((size_t)max_jt * p.Npad * sizeof(double));
+    p.off_sync = take((size_t)2 * p.p_n_tiles * sizeof(unsigned int));
     p.total = off;
     return p;
 }
@@ -490,6 +523,358 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     }
 }
 
+
+// ==========================================================================================
+// Persistent single-launch variant of the same algorithm, for layers whose per-block sweep is short
+// (small m and/or few neurons): the per-block launches, their CPU cost and the inter-kernel gaps dominate
+// there.  One cooperative launch per layer; CTA c owns the tiles c, c+grid, ... for the WHOLE layer.
+// Synchronisation is per neuron tile, not grid-wide:
+//   tickets[ntile] : every CTA that finishes the dot products of block k+1 for one (ntile, jt) takes a ticket;
+//                    the LAST of the j_tiles arrivals runs the block's recurrence for that tile's neurons
+//                    (8 warps x 4 interleaved neurons per round) and publishes
+//   flags[ntile]   = k+2  ("q of block k+1 is in global memory"), which the tile's CTAs wait for.
+// Data written by other CTAs (Q tiles, partial dots) and this CTA's own U tile are read with ld.global.cg.
+struct PersistArgs {
+    const float* W;
+    int64_t ldw;
+    float* Q;
+    int64_t ldq;
+    int8_t* levels;
+    int64_t ldl;
+    float* U;
+    double* part;
+    double* epart;
+    const double* G;        // [nblk][kB][kB]
+    const double* H;
+    const float* norm32;    // [nblk][kB]
+    const float* delta;
+    unsigned int* sync;     // tickets[n_tiles] | flags[n_tiles], zeroed before the launch
+    int64_t Npad, mpad;
+    int n_rows, d, nblk, TJ, j_tiles, n_tiles, mode, want_err, store_last_u;
+    float Kf, lam;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int kRNB = 4;   // neurons interleaved per warp in the in-kernel recurrence
+
+// The kB sequential decisions of block `blk` for the TN neurons of one tile; executed by a whole CTA.
+template <int TN>
+__device__ void recur_tile(const PersistArgs& a, int row0, int blk, double (*Gs)[kB + 1], double (*Hs)[kB + 1],
+                           float* ns) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blk * kB;
+    const int bvalid = min(kB, a.d - t0);
+    __syncthreads();
+    for (int e = tid; e < kB * kB; e += kThreads) {
+        Gs[e / kB][e % kB] = a.G[(size_t)blk * kB * kB + e];
+        Hs[e / kB][e % kB] = a.H[(size_t)blk * kB * kB + e];
+    }
+    if (tid < kB) ns[tid] = a.norm32[(size_t)blk * kB + tid];
+    __syncthreads();
+    const float delta = *a.delta;
+    for (int round = 0; round * (kWarps * kRNB) < TN; ++round) {
+        double p[kRNB];
+        float w[kRNB], qm[kRNB];
+        int lvm[kRNB], n[kRNB];
+#pragma unroll
+        for (int i = 0; i < kRNB; ++i) {
+            const int nl = round * (kWarps * kRNB) + warp * kRNB + i;
+            n[i] = (nl < TN && row0 + nl < a.n_rows) ? row0 + nl : -1;
+            p[i] = 0.0;
+            w[i] = 0.f;
+            qm[i] = 0.f;
+            lvm[i] = 0;
+            if (n[i] >= 0) {
+                if (blk > 0) {
+                    const double* src = a.part + (int64_t)n[i] * kB + lane;
+                    const int64_t stride = a.Npad * kB;
+                    for (int jt = 0; jt < a.j_tiles; ++jt) p[i] += __ldcg(src + (int64_t)jt * stride);   // fixed order
+                }
+                if (t0 + lane < a.d) w[i] = a.W[(int64_t)n[i] * a.ldw + t0 + lane];
+            }
+        }
+        for (int t = 0; t < bvalid; ++t) {
+            const double gtt = Gs[t][t], gl = Gs[t][lane], hl = Hs[t][lane];
+            const float nrm = ns[t];
+#pragma unroll
+            for (int i = 0; i < kRNB; ++i) {
+                const double pt = __shfl_sync(0xffffffffu, p[i], t);
+                const float wt = __shfl_sync(0xffffffffu, w[i], t);
+                const double dot = fma((double)wt, gtt, pt);
+                const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                int lv;
+                const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv);
+                if (lane == t) {
+                    qm[i] = q;
+                    lvm[i] = lv;
+                }
+                if (lane > t) {
+                    p[i] = fma((double)wt, gl, p[i]);
+                    p[i] = fma(-(double)q, hl, p[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kRNB; ++i)
+            if (n[i] >= 0 && t0 + lane < a.d) {
+                a.Q[(int64_t)n[i] * a.ldq + t0 + lane] = qm[i];
+                if (a.levels) a.levels[(int64_t)n[i] * a.ldl + t0 + lane] = (int8_t)lvm[i];
+            }
+    }
+    __threadfence();
+    __syncthreads();
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads, 1)
+persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXq,
+                  const PersistArgs a) {
+    constexpr int TN = 32 * R;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    float* base = reinterpret_cast<float*>(smem_raw + 128);
+    float* wsm = base + 2 * kStageFloats;
+    float* qsm = wsm + kB * TN;
+    double(*Gs)[kB + 1] = reinterpret_cast<double(*)[kB + 1]>(qsm + kB * TN);
+    double(*Hs)[kB + 1] = Gs + kB;
+    float* ns = reinterpret_cast<float*>(Hs + kB);
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles = a.n_tiles * a.j_tiles;
+    unsigned int* tickets = a.sync;
+    unsigned int* flags = a.sync + a.n_tiles;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t gs = 0;   // stages issued so far by this CTA: buffer = gs & 1, mbarrier parity = (gs >> 1) & 1
+
+    // block 0 has no history: its recurrence runs on the CTA that owns the tile's first column range
+    for (int T = blockIdx.x; T < tiles; T += gridDim.x)
+        if (T % a.j_tiles == 0) {
+            recur_tile<TN>(a, (T / a.j_tiles) * TN, 0, Gs, Hs, ns);
+            if (tid == 0) st_release_u32(&flags[T / a.j_tiles], 1u);
+        }
+
+    float4* U4 = reinterpret_cast<float4*>(a.U);
+    for (int blk = 0; blk < a.nblk; ++blk) {
+        const int t0 = blk * kB;
+        const int bvalid = min(kB, a.d - t0);
+        const int nb4 = (bvalid + 3) >> 2;
+        const bool has_next = blk + 1 < a.nblk;
+        const bool first = blk == 0;
+        const bool store_u = has_next || a.store_last_u;
+        const bool want_err = !has_next && a.want_err;
+        const uint32_t stage_bytes = (uint32_t)((2 + (has_next ? 1 : 0)) * kB * kJS * sizeof(float));
+        for (int T = blockIdx.x; T < tiles; T += gridDim.x) {
+            const int ntile = T / a.j_tiles, jt = T % a.j_tiles;
+            const int row0 = ntile * TN;
+            const int64_t jbeg = (int64_t)jt * a.TJ;
+            const int64_t jend = min(jbeg + (int64_t)a.TJ, a.mpad);
+            const int nst = (int)((jend - jbeg) / kJS);
+
+            if (tid == 0) {
+                unsigned int spins = 0;
+                while (ld_acquire_u32(&flags[ntile]) < (unsigned)(blk + 1)) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 25)) __trap();    // seconds: a lost flag must not hang the GPU
+                }
+            }
+            __syncthreads();
+
+            auto issue = [&](int st, uint32_t g) {
+                float* buf = base + (g & 1) * kStageFloats;
+                uint64_t* bar = &bars[g & 1];
+                const int col = (int)(jbeg + (int64_t)st * kJS);
+                mbar_expect_tx(bar, stage_bytes);
+                tma_load_2d(buf, &tmX, col, t0, bar);
+                tma_load_2d(buf + kB * kJS, &tmXq, col, t0, bar);
+                if (has_next) tma_load_2d(buf + 2 * kB * kJS, &tmXq, col, t0 + kB, bar);
+            };
+            if (tid == 0 && nst > 0) issue(0, gs);
+
+            for (int e = tid; e < TN * (kB / 4); e += kThreads) {
+                const int nl = e >> 3, g = e & 7;
+                const int row = row0 + nl;
+                float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), qv = wv;
+                if (row < a.n_rows) {
+                    const float* wp = a.W + (int64_t)row * a.ldw;
+                    const float* qp = a.Q + (int64_t)row * a.ldq;
+                    const int t = t0 + 4 * g;
+                    if (t + 0 < a.d) { wv.x = wp[t + 0]; qv.x = __ldcg(qp + t + 0); }
+                    if (t + 1 < a.d) { wv.y = wp[t + 1]; qv.y = __ldcg(qp + t + 1); }
+                    if (t + 2 < a.d) { wv.z = wp[t + 2]; qv.z = __ldcg(qp + t + 2); }
+                    if (t + 3 < a.d) { wv.w = wp[t + 3]; qv.w = __ldcg(qp + t + 3); }
+                }
+                reinterpret_cast<float4*>(wsm)[g * TN + nl] = wv;
+                reinterpret_cast<float4*>(qsm)[g * TN + nl] = qv;
+            }
+            __syncthreads();
+
+            float P[R][kB];
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int s = 0; s < kB; ++s) P[i][s] = 0.f;
+            double esum[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) esum[i] = 0.0;
+
+            const int nq = nst * kChunksPerStage;
+            auto u_index = [&](int q) -> int64_t {
+                const int st = q / kChunksPerStage, c = q % kChunksPerStage;
+                const int64_t j = jbeg + (int64_t)st * kJS + warp * kColsPerWarp + c * 4;
+                return (j >> 2) * a.Npad + row0 + lane;
+            };
+            float4 ucur[R], unext[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) ucur[i] = unext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!first && nq > 0) {
+                const int64_t idx = u_index(0);
+#pragma unroll
+                for (int i = 0; i < R; ++i) ucur[i] = __ldcg(U4 + idx + 32 * i);
+            }
+            for (int q = 0; q < nq; ++q) {
+                const int st = q / kChunksPerStage, c = q % kChunksPerStage;
+                const uint32_t g = gs + (uint32_t)st;
+                if (c == 0) {
+                    if (tid == 0 && st + 1 < nst) issue(st + 1, g + 1);
+                    mbar_wait(&bars[g & 1], (g >> 1) & 1);
+                }
+                if (!first && q + 1 < nq) {
+                    const int64_t idx = u_index(q + 1);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) unext[i] = __ldcg(U4 + idx + 32 * i);
+                }
+                const float* buf = base + (g & 1) * kStageFloats;
+                const int jl = warp * kColsPerWarp + c * 4;
+                const float* sx = buf + jl;
+                const float* sxq = buf + kB * kJS + jl;
+                const float* sxn = buf + 2 * kB * kJS + jl;
+#pragma unroll 2
+                for (int g4 = 0; g4 < nb4; ++g4) {
+                    float4 wv[R], qv[R];
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        wv[i] = reinterpret_cast<const float4*>(wsm)[g4 * TN + lane + 32 * i];
+                        qv[i] = reinterpret_cast<const float4*>(qsm)[g4 * TN + lane + 32 * i];
+                    }
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss) {
+                        const float4 xs = *reinterpret_cast<const float4*>(sx + (4 * g4 + ss) * kJS);
+                        const float4 xq = *reinterpret_cast<const float4*>(sxq + (4 * g4 + ss) * kJS);
+#pragma unroll
+                        for (int i = 0; i < R; ++i) {
+                            const float w = ss == 0 ? wv[i].x : ss == 1 ? wv[i].y : ss == 2 ? wv[i].z : wv[i].w;
+                            const float qq = ss == 0 ? qv[i].x : ss == 1 ? qv[i].y : ss == 2 ? qv[i].z : qv[i].w;
+                            ucur[i].x = __fsub_rn(__fadd_rn(ucur[i].x, __fmul_rn(w, xs.x)), __fmul_rn(qq, xq.x));
+                            ucur[i].y = __fsub_rn(__fadd_rn(ucur[i].y, __fmul_rn(w, xs.y)), __fmul_rn(qq, xq.y));
+                            ucur[i].z = __fsub_rn(__fadd_rn(ucur[i].z, __fmul_rn(w, xs.z)), __fmul_rn(qq, xq.z));
+                            ucur[i].w = __fsub_rn(__fadd_rn(ucur[i].w, __fmul_rn(w, xs.w)), __fmul_rn(qq, xq.w));
+                        }
+                    }
+                }
+                if (store_u) {
+                    const int64_t idx = u_index(q);
+#pragma unroll
+                    for (int i = 0; i < R; ++i) U4[idx + 32 * i] = ucur[i];
+                }
+                if (has_next) {
+#pragma unroll
+                    for (int s = 0; s < kB; ++s) {
+                        const float4 xn = *reinterpret_cast<const float4*>(sxn + s * kJS);
+#pragma unroll
+                        for (int i = 0; i < R; ++i) {
+                            float acc = P[i][s];
+                            acc = fmaf(ucur[i].x, xn.x, acc);
+                            acc = fmaf(ucur[i].y, xn.y, acc);
+                            acc = fmaf(ucur[i].z, xn.z, acc);
+                            acc = fmaf(ucur[i].w, xn.w, acc);
+                            P[i][s] = acc;
+                        }
+                    }
+                }
+                if (want_err) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        float e = ucur[i].x * ucur[i].x;
+                        e = fmaf(ucur[i].y, ucur[i].y, e);
+                        e = fmaf(ucur[i].z, ucur[i].z, e);
+                        e = fmaf(ucur[i].w, ucur[i].w, e);
+                        esum[i] += (double)e;
+                    }
+                }
+                if (c == kChunksPerStage - 1) __syncthreads();
+#pragma unroll
+                for (int i = 0; i < R; ++i) ucur[i] = unext[i];
+            }
+            gs += (uint32_t)nst;
+            __syncthreads();
+
+            if (has_next) {
+                float* red = base;
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+#pragma unroll
+                    for (int s = 0; s < kB; ++s) red[(warp * TN + lane + 32 * i) * kRedStride + s] = P[i][s];
+                __syncthreads();
+                for (int e = tid; e < TN * kB; e += kThreads) {
+                    const int n = e / kB, s = e % kB;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) acc += (double)red[(w * TN + n) * kRedStride + s];
+                    a.part[((int64_t)jt * a.Npad + row0 + n) * kB + s] = acc;
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned int ticket = atomicAdd(&tickets[ntile], 1u);
+                    s_last = (ticket == (unsigned)((blk + 1) * a.j_tiles - 1));
+                    __threadfence();
+                }
+                __syncthreads();
+                if (s_last) {   // every column range of this neuron tile has delivered its dots for block blk+1
+                    recur_tile<TN>(a, row0, blk + 1, Gs, Hs, ns);
+                    if (tid == 0) st_release_u32(&flags[ntile], (unsigned)(blk + 2));
+                }
+            }
+            if (want_err) {
+                __syncthreads();
+                double* red2 = reinterpret_cast<double*>(base);
+#pragma unroll
+                for (int i = 0; i < R; ++i) red2[warp * TN + lane + 32 * i] = esum[i];
+                __syncthreads();
+                for (int n = tid; n < TN; n += kThreads) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) acc += red2[w * TN + n];
+                    a.epart[(int64_t)jt * a.Npad + row0 + n] = acc;
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+template <int R>
+static size_t persistent_smem_bytes() {
+    constexpr int TN = 32 * R;
+    return 128 + (size_t)(2 * kStageFloats + 2 * kB * TN) * sizeof(float) + 2 * kB * (kB + 1) * sizeof(double) +
+           kB * sizeof(float) + 64;
+}
+
 template <int R>
 static size_t sweep_smem_bytes() {
     constexpr int TN = 32 * R;
@@ -541,6 +926,37 @@ static int launch_sweep(const DirectPlan& p, const CUtensorMap& tmX, const CUten
     return 0;
 }
 
+template <int R>
+static int launch_persistent(const DirectPlan& p, const CUtensorMap& tmX, const CUtensorMap& tmXq, PersistArgs& a,
+                             cudaStream_t stream) {
+    static int max_ctas = 0;
+    const size_t smem = persistent_smem_bytes<R>();
+    if (max_ctas == 0) {
+        GPFQ_CUDA_TRY(cudaFuncSetAttribute(persistent_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0, sms = 0, per_sm = 0;
+        GPFQ_CUDA_TRY(cudaGetDevice(&dev));
+        GPFQ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GPFQ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel<R>, kThreads, smem));
+        GPFQ_REQUIRE(per_sm >= 1, "persistent_kernel does not fit on an SM");
+        max_ctas = sms * per_sm;
+    }
+    const int tiles = p.p_n_tiles * p.p_j_tiles;
+    const int grid = std::min(tiles, max_ctas);
+    void* params[] = {(void*)&tmX, (void*)&tmXq, (void*)&a};
+    profile_mark_begin(stream);
+    GPFQ_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)persistent_kernel<R>, dim3(grid), dim3(kThreads), params, smem,
+                                              stream));
+    if (profile_on()) {
+        const double nm = (double)a.n_rows * (double)a.mpad;
+        const double bytes = (2.0 * a.nblk - 1.0) * 4.0 * nm + 12.0 * kB * (double)a.mpad * a.nblk +
+                             8.0 * a.n_rows * kB * a.nblk + 8.0 * p.p_j_tiles * (double)a.n_rows * kB * a.nblk;
+        const double instr = nm * (4.0 * a.d + 1.0 * kB * (a.nblk - 1));
+        profile_mark_end(stream, bytes, instr);
+    }
+    count_launch();
+    return 0;
+}
+
 int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m, int n_rows,
                  const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
                  double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
@@ -567,6 +983,30 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
     block_gram_finish_kernel<<<(unsigned)ceil_div((int64_t)p.nblk * kB * kB, 256), 256, 0, stream>>>(
         gpart, p.gram_slices, p.nblk, G, H, norm32);
     GPFQ_CHECK_LAUNCH();
+
+    if (p.use_persistent) {
+        unsigned int* sync = (unsigned int*)(ws + p.off_sync);
+        GPFQ_CUDA_TRY(cudaMemsetAsync(sync, 0, (size_t)2 * p.p_n_tiles * sizeof(unsigned int), stream));
+        PersistArgs a{};
+        a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d; a.U = U; a.part = part; a.epart = epart;
+        a.G = G; a.H = H; a.norm32 = norm32; a.delta = delta; a.sync = sync; a.Npad = p.Npad; a.mpad = p.mpad;
+        a.n_rows = n_rows; a.d = d; a.nblk = p.nblk; a.TJ = p.pTJ; a.j_tiles = p.p_j_tiles; a.n_tiles = p.p_n_tiles;
+        a.mode = mode; a.want_err = (row_err2 != nullptr); a.store_last_u = (U_out != nullptr);
+        a.Kf = (float)K; a.lam = lam;
+        int rc = p.pR == 2 ? launch_persistent<2>(p, tmX, tmXq, a, stream) : launch_persistent<1>(p, tmX, tmXq, a, stream);
+        if (rc) return rc;
+        if (row_err2) {
+            err_finish_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, stream>>>(epart, p.p_j_tiles, p.Npad, n_rows,
+                                                                                 row_err2);
+            GPFQ_CHECK_LAUNCH();
+        }
+        if (U_out) {
+            untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)n_rows), 256, 0, stream>>>(U, p.Npad, n_rows, m,
+                                                                                                 U_out, ldu);
+            GPFQ_CHECK_LAUNCH();
+        }
+        return 0;
+    }
 
     for (int blk = 0; blk < p.nblk; ++blk) {
         const int t0 = blk * kB;
