@@ -119,7 +119,8 @@ class QuantizeNeuralNet:
                  mlp_alphabet_scalar, cnn_alphabet_scalar,
                  mlp_percentile, cnn_percentile,
                  reg, lamb, retain_rate, stochastic_quantization, device,
-                 *, process_group=None, solver=None, verbose=False, profile=False, shard_forward=False):
+                 *, process_group=None, solver=None, verbose=False, profile=False, shard_forward=False,
+                 overlap_solve=False):
         self.network_name = network_name
         self.analog_network = network_to_quantize          # not copied, as in the reference (:82)
         self.batch_size = batch_size
@@ -153,6 +154,11 @@ class QuantizeNeuralNet:
         self.process_group = process_group   # None = default group when torch.distributed is initialised; False = never shard
         self.shard_forward = shard_forward   # split each calibration batch over the ranks and all-gather X / X~ columns
         self.solver = solver
+        # Optional: run layer i's solve on a high-priority side stream while the main stream already runs the
+        # analog network for layer i+1 (it does not depend on Q_i); the quantized forward of layer i+1 waits
+        # for the solve.  Measured on 1 x B200 (r01): no gain -- the fp32 forward saturates the SMs, so the
+        # solver's kernels only time-slice with cuDNN's (3.90 s vs 3.80 s per ResNet-50 step); off by default.
+        self.overlap_solve = overlap_solve
         self.verbose = verbose
         self.layer_log = []      # (layer_idx, quantize_error tensor, relative_quantize_error tensor)
         self.profile = profile   # record CUDA-event timings of the phases of every layer
@@ -197,41 +203,68 @@ class QuantizeNeuralNet:
             print(f'Layer indices to quantize {layers_to_quantize}')
             print(f'Total number of layers to quantize {len(layers_to_quantize)}')
         deltas = self._layer_deltas(layers_to_quantize)
+        side = torch.cuda.Stream(device=self.device, priority=-1) if self.overlap_solve else None   # high priority
+        pending = None
         for layer_idx in layers_to_quantize:
-            analog_layer_input, quantized_layer_input = self._populate_linear_layer_input(layer_idx)
-            layer = self.analog_network_layers[layer_idx]
-            if type(layer) == LINEAR_MODULE_TYPE:
-                groups = 1
-                W = layer.weight.data
-                W_shape = W.shape
-                step, K, pct = self.mlp_alphabet_step_size, self.mlp_boundary_idx, self.mlp_percentile
-            elif type(layer) == CONV2D_MODULE_TYPE:
-                groups = layer.groups
-                W_shape = layer.weight.data.shape
-                W = layer.weight.data.view(W_shape[0], -1)
-                step, K, pct = self.cnn_alphabet_step_size, self.cnn_boundary_idx, self.cnn_percentile
-            else:
-                raise TypeError(f'The layer type {type(layer)} is not currently supported')
-
-            m = analog_layer_input.shape[0]
-            N = W.shape[0]
-            n0, n1 = neuron_slice(N, groups, self.process_group)
-            with self._Phase(self, layer_idx, 'solve'):
-                Q, err2, ref2 = quantize_layer_impl(W, analog_layer_input, quantized_layer_input, m, step, K, pct,
-                                                    self.reg, self.lamb, groups, self.stochastic_quantization,
-                                                    self.device, neuron_range=(n0, n1), solver=self.solver,
-                                                    return_partials=True, delta=deltas[layer_idx])
-            with self._Phase(self, layer_idx, 'gather'):
-                Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group)
-            quantize_error, relative_quantize_error, _, _ = reduce_errors(err2, ref2, groups)
-            self.quantized_network_layers[layer_idx].weight.data = Q.reshape(W_shape).float()
-            self.layer_log.append((layer_idx, quantize_error, relative_quantize_error))
-            if self.verbose:
-                print(f'The quantization error of layer {layer_idx} is {quantize_error.cpu().numpy()}.')
-                print(f'The relative quantization error of layer {layer_idx} is '
-                      f'{relative_quantize_error.cpu().numpy()}.\n')
+            capture = self._begin_capture(layer_idx)          # fresh batch, analog forward        (main stream)
+            if pending is not None:
+                self._finish_layer(pending)                   # wait for the solve, gather Q, write it back
+            analog_layer_input, quantized_layer_input = self._end_capture(capture)   # quantized forward
+            pending = self._launch_solve(layer_idx, analog_layer_input, quantized_layer_input, deltas[layer_idx], side)
             del analog_layer_input, quantized_layer_input
+        if pending is not None:
+            self._finish_layer(pending)
         return self.quantized_network
+
+    def _launch_solve(self, layer_idx, X, Xq, delta, side):
+        """Enqueue the solve of one layer (on the side stream when overlapping) and return the handle
+        ``_finish_layer`` completes."""
+        layer = self.analog_network_layers[layer_idx]
+        if type(layer) == LINEAR_MODULE_TYPE:
+            groups = 1
+            W = layer.weight.data
+            W_shape = W.shape
+        elif type(layer) == CONV2D_MODULE_TYPE:
+            groups = layer.groups
+            W_shape = layer.weight.data.shape
+            W = layer.weight.data.view(W_shape[0], -1)
+        else:
+            raise TypeError(f'The layer type {type(layer)} is not currently supported')
+        step, K, pct = self._layer_params(layer)
+        m = X.shape[0]
+        n0, n1 = neuron_slice(W.shape[0], groups, self.process_group)
+        main = torch.cuda.current_stream(self.device)
+        stream = side if side is not None else main
+        if side is not None:
+            side.wait_stream(main)                 # layer inputs are produced on the main stream
+            for t in (X, Xq):
+                t.record_stream(side)              # keep their memory alive until the side stream is done
+        with torch.cuda.stream(stream):
+            with self._Phase(self, layer_idx, 'solve'):
+                Q, err2, ref2 = quantize_layer_impl(W, X, Xq, m, step, K, pct, self.reg, self.lamb, groups,
+                                                    self.stochastic_quantization, self.device,
+                                                    neuron_range=(n0, n1), solver=self.solver, return_partials=True,
+                                                    delta=delta)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side
+
+    def _finish_layer(self, pending):
+        layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side = pending
+        main = torch.cuda.current_stream(self.device)
+        if side is not None:
+            main.wait_event(done)
+            for t in (Q, err2, ref2):
+                t.record_stream(main)
+        with self._Phase(self, layer_idx, 'gather'):
+            Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group)
+        quantize_error, relative_quantize_error, _, _ = reduce_errors(err2, ref2, groups)
+        self.quantized_network_layers[layer_idx].weight.data = Q.reshape(W_shape).float()
+        self.layer_log.append((layer_idx, quantize_error, relative_quantize_error))
+        if self.verbose:
+            print(f'The quantization error of layer {layer_idx} is {quantize_error.cpu().numpy()}.')
+            print(f'The relative quantization error of layer {layer_idx} is '
+                  f'{relative_quantize_error.cpu().numpy()}.\n')
 
     # ------------------------------------------------------------------
     def _layer_params(self, layer):
@@ -266,6 +299,20 @@ class QuantizeNeuralNet:
     def _populate_linear_layer_input(self, layer_idx):
         """Inputs of layer ``layer_idx`` in the analog and in the (partially) quantized network for
         one FRESH batch of the loader (reference quantize_neural_net.py:217-274)."""
+        return self._end_capture(self._begin_capture(layer_idx))
+
+    def _run_to_hook(self, name, network, layers, layer_idx, save_input, images):
+        handle = layers[layer_idx].register_forward_hook(save_input)
+        with torch.no_grad(), self._Phase(self, layer_idx, name):
+            try:
+                network(images)
+            except InterruptException:
+                pass
+            finally:
+                handle.remove()
+
+    def _begin_capture(self, layer_idx):
+        """Draw the layer's batch, copy it to the device and run the ANALOG network up to the layer."""
         raw_input_data, _ = next(self.data_loader_iter)
         analog_layer = self.analog_network_layers[layer_idx]
         if type(analog_layer) == LINEAR_MODULE_TYPE:
@@ -289,17 +336,14 @@ class QuantizeNeuralNet:
                 save_input.image_range, save_input.full_batch = (i0, i1), B
         with self._Phase(self, layer_idx, 'h2d'):
             images = raw_input_data.to(self.device, non_blocking=True)
-        with torch.no_grad():
-            for name, network, layers in (('forward_analog', self.analog_network, self.analog_network_layers),
-                                          ('forward_quantized', self.quantized_network, self.quantized_network_layers)):
-                handle = layers[layer_idx].register_forward_hook(save_input)
-                with self._Phase(self, layer_idx, name):
-                    try:
-                        network(images)
-                    except InterruptException:
-                        pass
-                    finally:
-                        handle.remove()
+        self._run_to_hook('forward_analog', self.analog_network, self.analog_network_layers, layer_idx, save_input, images)
+        return layer_idx, save_input, images, sharded
+
+    def _end_capture(self, capture):
+        """Run the (partially) QUANTIZED network up to the layer on the same batch; returns (X, X~)."""
+        layer_idx, save_input, images, sharded = capture
+        self._run_to_hook('forward_quantized', self.quantized_network, self.quantized_network_layers, layer_idx,
+                          save_input, images)
         if sharded:
             with self._Phase(self, layer_idx, 'gather_inputs'):
                 return gather_inputs(save_input.inputs[0], save_input.inputs[1], self.process_group)
