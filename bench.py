@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "resnet50_4bit_gpfq_weights_samples_per_s"
+METRIC = "resnet50_4bit_gpfq_weights_samples_per_s"   # the metric name follows --model/--bits when they differ
 UNIT = "weights*samples/s"
 
 
@@ -187,7 +187,7 @@ def run_reference_arm(args):
               "layer shapes (one per calibration-row class), extrapolated by N*d*m over the 54 layers; forward passes "
               "excluded")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
@@ -197,8 +197,10 @@ def run_reference_arm(args):
 
 
 def workload_config(args):
-    return {"workload": f"{args.model} {args.bits}-bit GPFQ, bs={args.batch}, retain_rate={args.retain}, scalar=1.16 "
-                        "(BASELINE.json configs[3]); one step = quantize_network() over all layers",
+    return {"workload": f"{args.model} {args.bits}-bit GPFQ, bs={args.batch}, retain_rate={args.retain}, scalar=1.16"
+                        + (f", reg={args.reg} lamb={args.lamb}" if args.reg else "")
+                        + (" (BASELINE.json configs[3])" if args.model == "resnet50" else "")
+                        + "; one step = quantize_network() over all layers",
             "global_batch": args.batch, "image": "3x224x224 Gaussian", "weights": "random init (torch.manual_seed(0))",
             "l2": "per-step inputs (8.3 GB of images, up to 400 MB of layer inputs) exceed the 126 MB L2",
             "parallelism": "single GPU" if args.gpus == 1 else
@@ -243,7 +245,7 @@ def run_cuda_arm(args):
         forward = forward or args.forward
         np.random.seed(0)
         qnn = qb.QuantizeNeuralNet(model, args.model, args.batch, BatchPool(pool), args.bits, args.bits, [],
-                                   1.16, 1.16, 1, 1, None, 0.1, args.retain, False, dev, profile=profile,
+                                   1.16, 1.16, 1, 1, args.reg, args.lamb, args.retain, False, dev, profile=profile,
                                    shard_forward=(forward == "sharded" and world > 1),
                                    solver=None if args.solver == "direct" else args.solver)
         barrier()
@@ -306,7 +308,7 @@ def run_cuda_arm(args):
         achieved = prof["sweep_bytes"] / sweep_s / 1e9 if sweep_s > 0 else 0.0
         ms_per_step = total_ms / args.steps
         out = {
-            "metric": METRIC, "value": units / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": metric_name(args), "value": units / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "wall_time_s": ms_per_step * 1e-3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": f"synthetic ({args.pool} Gaussian image batches cycled, random-init weights)",
@@ -362,6 +364,10 @@ def solver_choices():
             for (k, tm, ag, ch) in sa.AUTO_LOG}
 
 
+def metric_name(args):
+    return f"{args.model}_{args.bits}bit_gpfq_weights_samples_per_s"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -377,6 +383,8 @@ def main():
                     help="multi-GPU only: split each calibration batch over the ranks and all-gather the layer inputs "
                          "(default; removes the replicated-forward Amdahl term), or replicate the calibration forward "
                          "on every rank (BASELINE.json's sketch; Q bit-identical to the single-GPU run)")
+    ap.add_argument("--reg", default=None, choices=[None, "L0", "L1"], help="sparse-mode regulariser (main.py -reg)")
+    ap.add_argument("--lamb", type=float, default=0.1, help="regularisation strength (main.py -l)")
     ap.add_argument("--solver", default="auto", choices=["auto", "direct"],
                     help="auto: per layer, direct vs Gram (tcgen05 / fp64) picked from measured time behind a 99.9 %% "
                          "level-agreement gate during warm-up; direct: blocked direct solver everywhere")
