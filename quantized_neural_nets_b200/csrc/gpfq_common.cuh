@@ -71,13 +71,14 @@ __device__ __forceinline__ float shrinkf(float x, float lam) {
 
 // Returns the alphabet value; *level receives the signed level index
 // (msq/soft: value == level*delta; hard: value == sign*(lam + (|level|-1)*delta), level 0 == pruned).
-__device__ __forceinline__ float alphabet_map(float x, float delta, float Kf, int mode, float lam, int* level) {
-    if (mode == GPFQ_MODE_MSQ) {
+template <int MODE>
+__device__ __forceinline__ float alphabet_map_t(float x, float delta, float Kf, float lam, int* level) {
+    if (MODE == GPFQ_MODE_MSQ) {
         float k = level_count(x, delta, Kf);
         float s = sgnf(x);
         *level = (int)(s * k);
         return __fmul_rn(__fmul_rn(s, delta), k);
-    } else if (mode == GPFQ_MODE_SOFT) {
+    } else if (MODE == GPFQ_MODE_SOFT) {
         float y = shrinkf(x, lam);
         float k = level_count(y, delta, Kf);
         float s = sgnf(y);
@@ -93,6 +94,12 @@ __device__ __forceinline__ float alphabet_map(float x, float delta, float Kf, in
         *level = (int)(s * on * (k + 1.f));
         return __fmul_rn(__fmul_rn(s, __fadd_rn(lam, __fmul_rn(delta, k))), on);
     }
+}
+
+__device__ __forceinline__ float alphabet_map(float x, float delta, float Kf, int mode, float lam, int* level) {
+    if (mode == GPFQ_MODE_MSQ) return alphabet_map_t<GPFQ_MODE_MSQ>(x, delta, Kf, lam, level);
+    if (mode == GPFQ_MODE_SOFT) return alphabet_map_t<GPFQ_MODE_SOFT>(x, delta, Kf, lam, level);
+    return alphabet_map_t<GPFQ_MODE_HARD>(x, delta, Kf, lam, level);
 }
 
 // ---------------------------------------------------------------- device side: mbarrier + TMA

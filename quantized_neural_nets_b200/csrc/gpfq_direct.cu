@@ -41,6 +41,7 @@ constexpr int kMaxTJ = 4096;      // keeps every fp32 accumulation chain <= 512 
 struct DirectPlan {
     int R, TN, n_tiles, TJ, j_tiles, nblk, gram_slices, gram_slice_len;
     int pR, p_n_tiles, pTJ, p_j_tiles, use_persistent;     // single-launch variant
+    int use_resident;                                       // U resident in shared memory (small m)
     int64_t Npad, mpad;
     size_t off_U, off_G, off_H, off_norm, off_gpart, off_part, off_epart, off_sync, total;
 };
@@ -111,6 +112,18 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     // all SMs.  Kept for GPFQ_PERSISTENT=1 experiments; not selected by default.
     p.use_persistent = (force_p >= 0) ? force_p : 0;
     (void)pbest;
+    // Resident variant (one launch, U in shared memory, no cross-CTA traffic): per block one CTA spends the
+    // fp32 work of its 32 x m tile plus a ~6 us reduce + recurrence chain; the multi-launch path spends its
+    // sweep + two launches (~12 us of launch latency and gaps) + the recurrence kernel (~5 us).
+    static const int force_res = getenv("GPFQ_RESIDENT") ? atoi(getenv("GPFQ_RESIDENT")) : -1;   // tuning aid
+    {
+        // measured (r01): resident 30 us per block at m = 256 whatever N, 52 us at m = 768; multi-launch 43 us per
+        // block for (4096, ., 256), 32 us for (1000, 2048, 256), 31 us for (512, 4608, 768)
+        const int64_t mp64 = round_up(std::max(m, 1), 64);
+        const bool fits = mp64 <= 768;
+        const bool wins = mp64 <= 256 && n_rows >= 2048 && p.nblk >= 2;
+        p.use_resident = fits && ((force_res >= 0) ? force_res : wins);
+    }
     // block-Gram kernel: split the m-long dot products into slices so the grid fills the GPU
     int gs = std::max(1, std::min<int>((int)ceil_div(m, 256), (int)ceil_div(2 * 148, p.nblk)));
     p.gram_slice_len = (int)round_up(ceil_div(std::max(m, 1), gs), 32);
@@ -875,6 +888,290 @@ static size_t persistent_smem_bytes() {
            kB * sizeof(float) + 64;
 }
 
+
+// ==========================================================================================
+// Resident variant for small calibration sets (m_pad <= 768, e.g. every Linear layer at bs=256):
+// "each CTA owns a neuron slice of U, resident on chip" (BASELINE.json kernel (1)).  A CTA owns 32
+// neurons and ALL m columns, so nothing ever crosses CTAs: U lives in shared memory for the whole layer,
+// the dot products are combined through shared memory, the recurrence of the CTA's 32 neurons runs on
+// its own 8 warps (4 interleaved neurons each), and q goes straight back to shared memory for the apply
+// pass.  One launch per layer; X / Xq tiles stream through a 2-slot TMA ring that runs ahead across block
+// boundaries (they do not depend on q).  Same arithmetic, same order, same roundings as sweep + recur.
+constexpr int kRJS = 64;                          // calibration columns per TMA stage
+constexpr int kRStageFloats = 3 * kB * kRJS;      // x_k | xq_k | xq_{k+1}
+constexpr int kRCols = kRJS / kWarps;             // 8 columns = 2 quads per warp per stage
+
+struct ResidentArgs {
+    const float* W;
+    int64_t ldw;
+    float* Q;
+    int64_t ldq;
+    int8_t* levels;
+    int64_t ldl;
+    const double* G;
+    const double* H;
+    const float* norm32;
+    const float* delta;
+    double* row_err2;   // may be NULL
+    float* U;           // tiled global U, written once at the end when store_u
+    int64_t Npad;
+    int n_rows, d, nblk, mpad, mode, store_u, slots;   // slots = depth of the TMA ring (2..4)
+    float Kf, lam;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// TN = neurons per CTA: 32 (lane = neuron) or 16 (lane = neuron + 16 * column half; two CTAs share an SM so
+// that one CTA's recurrence overlaps the other's arithmetic).
+template <int TN, int MODE>
+__global__ void __launch_bounds__(kThreads, TN == 32 ? 1 : 2)
+resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXq,
+                const ResidentArgs a) {
+    constexpr int CH = 32 / TN;                 // column halves per warp (lanes sharing a neuron)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+    float* stages = reinterpret_cast<float*>(smem_raw + 128);                  // slots x kRStageFloats
+    const int S = a.slots;
+    double* Gs = reinterpret_cast<double*>(stages + S * kRStageFloats);        // [kB][2 kB], columns kB.. are zero
+    double* Hs = Gs + 2 * kB * kB;
+    double* P64 = Hs + 2 * kB * kB;                                            // [TN][kB + 1]
+    float* wsm = reinterpret_cast<float*>(P64 + TN * (kB + 1));                // [2][kB/4][TN] float4
+    float* qsm = wsm + 2 * kB * TN;                                            // [kB/4][TN] float4
+    float* ns = qsm + kB * TN;                                                 // [kB]
+    float* red = ns + kB;                                                      // [kWarps][TN][17]
+    float* Us = red + kWarps * TN * 17;                                        // [mpad/4][TN] float4
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nl_lane = lane % TN, ch = lane / TN;      // this lane's neuron and column half
+    const int row0 = blockIdx.x * TN;
+    const int nst = a.mpad / kRJS;
+    const int total_stages = a.nblk * nst;
+    const float delta = *a.delta;
+
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
+    }
+    for (int e = tid; e < a.mpad * TN; e += kThreads) Us[e] = 0.f;
+    for (int e = tid; e < 4 * kB * kB; e += kThreads) Gs[e] = 0.0;            // Gs and Hs incl. their zero padding
+    __syncthreads();
+
+    auto issue = [&](int g) {     // stage g = (block g / nst, column stage g % nst); slot g % S
+        const int k = g / nst, st = g % nst;
+        const bool nxt = k + 1 < a.nblk;
+        float* buf = stages + (g % S) * kRStageFloats;
+        uint64_t* bar = &bars[g % S];
+        mbar_expect_tx(bar, (uint32_t)((2 + (nxt ? 1 : 0)) * kB * kRJS * sizeof(float)));
+        tma_load_2d(buf, &tmX, st * kRJS, k * kB, bar);
+        tma_load_2d(buf + kB * kRJS, &tmXq, st * kRJS, k * kB, bar);
+        if (nxt) tma_load_2d(buf + 2 * kB * kRJS, &tmXq, st * kRJS, (k + 1) * kB, bar);
+    };
+    if (tid == 0)
+        for (int g = 0; g < S - 1 && g < total_stages; ++g) issue(g);     // the ring runs S-1 stages ahead
+
+    // w of block k -> wsm[k & 1]; G / H / norms of block k -> smem (cp.async), both issued ahead of use
+    auto stage_w = [&](int k) {
+        float4* dst = reinterpret_cast<float4*>(wsm) + (k & 1) * (kB / 4) * TN;
+        for (int e = tid; e < TN * (kB / 4); e += kThreads) {
+            const int nl = e >> 3, g = e & 7;
+            const int row = row0 + nl, t = k * kB + 4 * g;
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < a.n_rows) {
+                const float* wp = a.W + (int64_t)row * a.ldw;
+                if (t + 0 < a.d) wv.x = wp[t + 0];
+                if (t + 1 < a.d) wv.y = wp[t + 1];
+                if (t + 2 < a.d) wv.z = wp[t + 2];
+                if (t + 3 < a.d) wv.w = wp[t + 3];
+            }
+            dst[g * TN + nl] = wv;
+        }
+    };
+    auto stage_gram = [&](int k) {
+        const double* g = a.G + (size_t)k * kB * kB;
+        const double* h = a.H + (size_t)k * kB * kB;
+        for (int e = tid; e < kB * kB / 2; e += kThreads) {     // 16 bytes = 2 doubles per copy
+            const int r = e / (kB / 2), c2 = e % (kB / 2);
+            cp_async16(Gs + r * 2 * kB + 2 * c2, g + 2 * e);
+            cp_async16(Hs + r * 2 * kB + 2 * c2, h + 2 * e);
+        }
+        if (tid < kB / 4) cp_async16(ns + 4 * tid, a.norm32 + (size_t)k * kB + 4 * tid);
+    };
+    // The kB decisions of block k for this CTA's neurons, on ONE warp with lane = neuron: the 32 pending
+    // projections of a neuron live in the lane's registers, always shifted so that p[0] belongs to the
+    // current feature; per step the lane does its own division + alphabet map (no cross-lane redundancy)
+    // and 31 fp64 updates  p[j] <- p[j+1] + w_t G[t][t+1+j] - q_t H[t][t+1+j]  (rows of G / H are zero
+    // padded, so updates past the block edge add zero).  Identical arithmetic to recur_kernel.
+    auto recurrence = [&](int k, bool have_p) {
+        const int t0 = k * kB;
+        const int bvalid = min(kB, a.d - t0);
+        const float* wblk = wsm + (k & 1) * kB * TN;
+        if (warp == 0 && lane < TN) {
+            const int nl = lane;
+            double p[kB];
+#pragma unroll
+            for (int s = 0; s < kB; ++s) p[s] = have_p ? P64[nl * (kB + 1) + s] : 0.0;
+            for (int t = 0; t < bvalid; ++t) {
+                const float wt = wblk[((t >> 2) * TN + nl) * 4 + (t & 3)];
+                const double* g = Gs + t * (2 * kB) + t;
+                const double* h = Hs + t * (2 * kB) + t;
+                const double dot = fma((double)wt, g[0], p[0]);
+                const float nrm = ns[t];
+                const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                int lv;
+                const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv);
+                qsm[((t >> 2) * TN + nl) * 4 + (t & 3)] = q;
+                if (a.levels && row0 + nl < a.n_rows) a.levels[(int64_t)(row0 + nl) * a.ldl + t0 + t] = (int8_t)lv;
+                const double wd = (double)wt, qd = -(double)q;
+#pragma unroll
+                for (int j = 0; j < kB - 1; ++j) p[j] = fma(qd, h[1 + j], fma(wd, g[1 + j], p[j + 1]));
+                p[kB - 1] = 0.0;
+            }
+            for (int t = bvalid; t < kB; ++t) qsm[((t >> 2) * TN + nl) * 4 + (t & 3)] = 0.f;
+        }
+        __syncthreads();
+        for (int e = tid; e < TN * kB; e += kThreads) {       // coalesced copy of the block's q to global Q
+            const int nl = e / kB, t = e % kB;
+            if (row0 + nl < a.n_rows && t0 + t < a.d)
+                a.Q[(int64_t)(row0 + nl) * a.ldq + t0 + t] = qsm[((t >> 2) * TN + nl) * 4 + (t & 3)];
+        }
+    };
+
+    stage_w(0);
+    stage_gram(0);
+    cp_async_wait_all();
+    __syncthreads();
+    recurrence(0, false);
+    __syncthreads();
+
+    float4* Us4 = reinterpret_cast<float4*>(Us);
+    double esum = 0.0;
+    for (int k = 0; k < a.nblk; ++k) {
+        const int bvalid = min(kB, a.d - k * kB);
+        const int nb4 = (bvalid + 3) >> 2;
+        const bool has_next = k + 1 < a.nblk;
+        const bool want_err = !has_next && a.row_err2 != nullptr;
+        const float4* wblk = reinterpret_cast<const float4*>(wsm) + (k & 1) * (kB / 4) * TN;
+        const float4* qblk = reinterpret_cast<const float4*>(qsm);
+        if (has_next) {
+            stage_w(k + 1);        // other half of wsm
+            stage_gram(k + 1);     // Gs / Hs of block k were consumed by recurrence(k) already
+        }
+        float P[kB];
+#pragma unroll
+        for (int s = 0; s < kB; ++s) P[s] = 0.f;
+        for (int st = 0; st < nst; ++st) {
+            const int g = k * nst + st;
+            if (tid == 0 && g + S - 1 < total_stages) issue(g + S - 1);     // its slot was consumed at stage g-1
+            mbar_wait(&bars[g % S], (uint32_t)((g / S) & 1));
+            const float* buf = stages + (g % S) * kRStageFloats;
+#pragma unroll 1
+            for (int c = ch; c < kRCols / 4; c += CH) {
+                const int jl = warp * kRCols + c * 4;
+                const float* sx = buf + jl;
+                const float* sxq = buf + kB * kRJS + jl;
+                const float* sxn = buf + 2 * kB * kRJS + jl;
+                const int uidx = ((st * kRJS + jl) >> 2) * TN + nl_lane;
+                float4 u = Us4[uidx];
+#pragma unroll 2
+                for (int g4 = 0; g4 < nb4; ++g4) {
+                    const float4 wv = wblk[g4 * TN + nl_lane], qv = qblk[g4 * TN + nl_lane];
+#pragma unroll
+                    for (int ss = 0; ss < 4; ++ss) {
+                        const float4 xs = *reinterpret_cast<const float4*>(sx + (4 * g4 + ss) * kRJS);
+                        const float4 xq = *reinterpret_cast<const float4*>(sxq + (4 * g4 + ss) * kRJS);
+                        const float w = ss == 0 ? wv.x : ss == 1 ? wv.y : ss == 2 ? wv.z : wv.w;
+                        const float qq = ss == 0 ? qv.x : ss == 1 ? qv.y : ss == 2 ? qv.z : qv.w;
+                        u.x = __fsub_rn(__fadd_rn(u.x, __fmul_rn(w, xs.x)), __fmul_rn(qq, xq.x));
+                        u.y = __fsub_rn(__fadd_rn(u.y, __fmul_rn(w, xs.y)), __fmul_rn(qq, xq.y));
+                        u.z = __fsub_rn(__fadd_rn(u.z, __fmul_rn(w, xs.z)), __fmul_rn(qq, xq.z));
+                        u.w = __fsub_rn(__fadd_rn(u.w, __fmul_rn(w, xs.w)), __fmul_rn(qq, xq.w));
+                    }
+                }
+                Us4[uidx] = u;
+                if (has_next) {
+#pragma unroll
+                    for (int s = 0; s < kB; ++s) {
+                        const float4 xn = *reinterpret_cast<const float4*>(sxn + s * kRJS);
+                        float acc = P[s];
+                        acc = fmaf(u.x, xn.x, acc);
+                        acc = fmaf(u.y, xn.y, acc);
+                        acc = fmaf(u.z, xn.z, acc);
+                        acc = fmaf(u.w, xn.w, acc);
+                        P[s] = acc;
+                    }
+                }
+                if (want_err) {
+                    float e = u.x * u.x;
+                    e = fmaf(u.y, u.y, e);
+                    e = fmaf(u.z, u.z, e);
+                    e = fmaf(u.w, u.w, e);
+                    esum += (double)e;
+                }
+            }
+            __syncthreads();     // stage consumed: its slot may be refilled
+        }
+        if (has_next) {
+            if (CH == 2) {       // fold the two column halves of the warp (fixed order: half 0 + half 1)
+#pragma unroll
+                for (int s = 0; s < kB; ++s) {
+                    const float other = __shfl_xor_sync(0xffffffffu, P[s], 16);
+                    P[s] = (ch == 0) ? __fadd_rn(P[s], other) : __fadd_rn(other, P[s]);
+                }
+            }
+            // combine the 8 warps' column ranges (fixed order, fp64), 16 features at a time
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (ch == 0) {
+#pragma unroll
+                    for (int s = 0; s < 16; ++s) red[(warp * TN + nl_lane) * 17 + s] = P[half * 16 + s];
+                }
+                __syncthreads();
+                for (int e = tid; e < TN * 16; e += kThreads) {
+                    const int n = e >> 4, s = e & 15;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) acc += (double)red[(w * TN + n) * 17 + s];
+                    P64[n * (kB + 1) + half * 16 + s] = acc;
+                }
+                __syncthreads();
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            recurrence(k + 1, true);
+            __syncthreads();
+        }
+    }
+    if (a.row_err2 != nullptr) {
+        double* red2 = reinterpret_cast<double*>(red);       // [kWarps][TN]
+        if (CH == 2) esum += __shfl_xor_sync(0xffffffffu, esum, 16);
+        if (ch == 0) red2[warp * TN + nl_lane] = esum;
+        __syncthreads();
+        if (tid < TN && row0 + tid < a.n_rows) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) acc += red2[w * TN + tid];
+            a.row_err2[row0 + tid] = acc;
+        }
+    }
+    if (a.store_u) {
+        float4* U4 = reinterpret_cast<float4*>(a.U);
+        for (int e = tid; e < (a.mpad / 4) * TN; e += kThreads) {
+            const int quad = e / TN, nl = e % TN;
+            U4[(int64_t)quad * a.Npad + row0 + nl] = Us4[e];
+        }
+    }
+}
+
+static size_t resident_smem_bytes(int mpad, int slots, int TN) {
+    return 128 + (size_t)slots * kRStageFloats * sizeof(float) + (size_t)2 * kB * kB * sizeof(double) +
+           (size_t)2 * kB * kB * sizeof(double) /* zero padding of G, H rows */ +
+           (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + kB) * sizeof(float) +
+           (size_t)kWarps * TN * 17 * sizeof(float) + (size_t)mpad * TN * sizeof(float);
+}
+
 template <int R>
 static size_t sweep_smem_bytes() {
     constexpr int TN = 32 * R;
@@ -983,6 +1280,47 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
     block_gram_finish_kernel<<<(unsigned)ceil_div((int64_t)p.nblk * kB * kB, 256), 256, 0, stream>>>(
         gpart, p.gram_slices, p.nblk, G, H, norm32);
     GPFQ_CHECK_LAUNCH();
+
+    if (p.use_resident) {
+        const int mp = (int)round_up(m, kRJS);
+        CUtensorMap rX, rXq;
+        if (int rc = make_tensor_map_2d(&rX, X, d, m, ldx, kB, kRJS)) return rc;
+        if (int rc = make_tensor_map_2d(&rXq, Xq, d, m, ldx, kB, kRJS)) return rc;
+        ResidentArgs a{};
+        a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d; a.G = G; a.H = H; a.norm32 = norm32;
+        a.delta = delta; a.row_err2 = row_err2; a.U = U; a.Npad = p.Npad; a.n_rows = n_rows; a.d = d; a.nblk = p.nblk;
+        a.mpad = mp; a.mode = mode; a.store_u = (U_out != nullptr); a.Kf = (float)K; a.lam = lam;
+        // 16 neurons per CTA when two such CTAs fit on an SM (their recurrences and sweeps then overlap)
+        static const int force_tn = getenv("GPFQ_RESIDENT_TN") ? atoi(getenv("GPFQ_RESIDENT_TN")) : 0;   // tuning aid
+        const int TN = force_tn ? force_tn : (resident_smem_bytes(mp, 2, 16) <= 113 * 1024 ? 16 : 32);
+        a.slots = (TN == 16) ? 2 : 4;
+        while (a.slots > 2 && resident_smem_bytes(mp, a.slots, TN) > 225 * 1024) --a.slots;
+        const size_t smem = resident_smem_bytes(mp, a.slots, TN);
+        typedef void (*ResidentFn)(const CUtensorMap, const CUtensorMap, const ResidentArgs);
+        static const ResidentFn table[2][3] = {
+            {resident_kernel<32, GPFQ_MODE_MSQ>, resident_kernel<32, GPFQ_MODE_SOFT>, resident_kernel<32, GPFQ_MODE_HARD>},
+            {resident_kernel<16, GPFQ_MODE_MSQ>, resident_kernel<16, GPFQ_MODE_SOFT>, resident_kernel<16, GPFQ_MODE_HARD>}};
+        static size_t configured[2][3] = {{0, 0, 0}, {0, 0, 0}};
+        const ResidentFn fn = table[TN == 16][mode];
+        if (smem > configured[TN == 16][mode]) {
+            GPFQ_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[TN == 16][mode] = smem;
+        }
+        profile_mark_begin(stream);
+        fn<<<(unsigned)ceil_div(n_rows, TN), kThreads, smem, stream>>>(rX, rXq, a);
+        if (profile_on()) {
+            const double nm = (double)n_rows * (double)mp;
+            profile_mark_end(stream, 12.0 * kB * (double)mp * p.nblk * ceil_div(n_rows, 32) + 8.0 * n_rows * (double)d,
+                             nm * (4.0 * d + 1.0 * kB * (p.nblk - 1)));
+        }
+        GPFQ_CHECK_LAUNCH();
+        if (U_out) {
+            untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)n_rows), 256, 0, stream>>>(U, p.Npad, n_rows, m,
+                                                                                                 U_out, ldu);
+            GPFQ_CHECK_LAUNCH();
+        }
+        return 0;
+    }
 
     if (p.use_persistent) {
         unsigned int* sync = (unsigned int*)(ws + p.off_sync);
