@@ -576,71 +576,63 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr int kRNB = 4;   // neurons interleaved per warp in the in-kernel recurrence
 
 // The kB sequential decisions of block `blk` for the TN neurons of one tile; executed by a whole CTA.
+// lane = neuron (warps 0 .. TN/32-1): the neuron's 32 pending projections sit in the lane's registers, shifted so
+// that p[0] is the current feature; Gz / Hz are the block's Gram rows zero padded to 2*kB columns.
 template <int TN>
-__device__ void recur_tile(const PersistArgs& a, int row0, int blk, double (*Gs)[kB + 1], double (*Hs)[kB + 1],
-                           float* ns) {
+__device__ void recur_tile(const PersistArgs& a, int row0, int blk, double* Gz, double* Hz, float* ns, float* qstage) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t0 = blk * kB;
     const int bvalid = min(kB, a.d - t0);
     __syncthreads();
     for (int e = tid; e < kB * kB; e += kThreads) {
-        Gs[e / kB][e % kB] = a.G[(size_t)blk * kB * kB + e];
-        Hs[e / kB][e % kB] = a.H[(size_t)blk * kB * kB + e];
+        Gz[(e / kB) * 2 * kB + e % kB] = a.G[(size_t)blk * kB * kB + e];
+        Hz[(e / kB) * 2 * kB + e % kB] = a.H[(size_t)blk * kB * kB + e];
     }
     if (tid < kB) ns[tid] = a.norm32[(size_t)blk * kB + tid];
     __syncthreads();
     const float delta = *a.delta;
-    for (int round = 0; round * (kWarps * kRNB) < TN; ++round) {
-        double p[kRNB];
-        float w[kRNB], qm[kRNB];
-        int lvm[kRNB], n[kRNB];
+    const int nl = warp * 32 + lane;
+    if (nl < TN) {
+        const int n = row0 + nl;
+        const bool valid = n < a.n_rows;
+        double p[kB];
 #pragma unroll
-        for (int i = 0; i < kRNB; ++i) {
-            const int nl = round * (kWarps * kRNB) + warp * kRNB + i;
-            n[i] = (nl < TN && row0 + nl < a.n_rows) ? row0 + nl : -1;
-            p[i] = 0.0;
-            w[i] = 0.f;
-            qm[i] = 0.f;
-            lvm[i] = 0;
-            if (n[i] >= 0) {
-                if (blk > 0) {
-                    const double* src = a.part + (int64_t)n[i] * kB + lane;
-                    const int64_t stride = a.Npad * kB;
-                    for (int jt = 0; jt < a.j_tiles; ++jt) p[i] += __ldcg(src + (int64_t)jt * stride);   // fixed order
+        for (int s = 0; s < kB; ++s) p[s] = 0.0;
+        if (valid && blk > 0) {
+            for (int jt = 0; jt < a.j_tiles; ++jt) {           // fixed order
+                const double2* src = reinterpret_cast<const double2*>(a.part + ((int64_t)jt * a.Npad + n) * kB);
+#pragma unroll
+                for (int s = 0; s < kB / 2; ++s) {
+                    const double2 v = __ldcg(src + s);
+                    p[2 * s] += v.x;
+                    p[2 * s + 1] += v.y;
                 }
-                if (t0 + lane < a.d) w[i] = a.W[(int64_t)n[i] * a.ldw + t0 + lane];
             }
         }
+        const float* wrow = a.W + (int64_t)(valid ? n : 0) * a.ldw + t0;
         for (int t = 0; t < bvalid; ++t) {
-            const double gtt = Gs[t][t], gl = Gs[t][lane], hl = Hs[t][lane];
+            const float wt = valid ? wrow[t] : 0.f;
+            const double* g = Gz + t * (2 * kB) + t;
+            const double* h = Hz + t * (2 * kB) + t;
+            const double dot = fma((double)wt, g[0], p[0]);
             const float nrm = ns[t];
+            const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+            int lv;
+            const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv);
+            qstage[t * TN + nl] = q;
+            if (a.levels && valid) a.levels[(int64_t)n * a.ldl + t0 + t] = (int8_t)lv;
+            const double wd = (double)wt, qd = -(double)q;
 #pragma unroll
-            for (int i = 0; i < kRNB; ++i) {
-                const double pt = __shfl_sync(0xffffffffu, p[i], t);
-                const float wt = __shfl_sync(0xffffffffu, w[i], t);
-                const double dot = fma((double)wt, gtt, pt);
-                const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
-                int lv;
-                const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv);
-                if (lane == t) {
-                    qm[i] = q;
-                    lvm[i] = lv;
-                }
-                if (lane > t) {
-                    p[i] = fma((double)wt, gl, p[i]);
-                    p[i] = fma(-(double)q, hl, p[i]);
-                }
-            }
+            for (int j = 0; j < kB - 1; ++j) p[j] = fma(qd, h[1 + j], fma(wd, g[1 + j], p[j + 1]));
+            p[kB - 1] = 0.0;
         }
-#pragma unroll
-        for (int i = 0; i < kRNB; ++i)
-            if (n[i] >= 0 && t0 + lane < a.d) {
-                a.Q[(int64_t)n[i] * a.ldq + t0 + lane] = qm[i];
-                if (a.levels) a.levels[(int64_t)n[i] * a.ldl + t0 + lane] = (int8_t)lvm[i];
-            }
+    }
+    __syncthreads();
+    for (int e = tid; e < TN * bvalid; e += kThreads) {       // coalesced copy of the block's q to global Q
+        const int n2 = e / bvalid, t = e % bvalid;
+        if (row0 + n2 < a.n_rows) a.Q[(int64_t)(row0 + n2) * a.ldq + t0 + t] = qstage[t * TN + n2];
     }
     __threadfence();
     __syncthreads();
@@ -656,9 +648,10 @@ persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     float* base = reinterpret_cast<float*>(smem_raw + 128);
     float* wsm = base + 2 * kStageFloats;
     float* qsm = wsm + kB * TN;
-    double(*Gs)[kB + 1] = reinterpret_cast<double(*)[kB + 1]>(qsm + kB * TN);
-    double(*Hs)[kB + 1] = Gs + kB;
-    float* ns = reinterpret_cast<float*>(Hs + kB);
+    double* Gs = reinterpret_cast<double*>(qsm + kB * TN);          // [kB][2 kB], columns kB.. stay zero
+    double* Hs = Gs + 2 * kB * kB;
+    float* ns = reinterpret_cast<float*>(Hs + 2 * kB * kB);         // [kB]
+    float* qstage = ns + kB;                                        // [kB][TN]
     __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -671,13 +664,14 @@ persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_init(&bars[1], 1);
         fence_barrier_init();
     }
+    for (int e = tid; e < 4 * kB * kB; e += kThreads) Gs[e] = 0.0;
     __syncthreads();
     uint32_t gs = 0;   // stages issued so far by this CTA: buffer = gs & 1, mbarrier parity = (gs >> 1) & 1
 
     // block 0 has no history: its recurrence runs on the CTA that owns the tile's first column range
     for (int T = blockIdx.x; T < tiles; T += gridDim.x)
         if (T % a.j_tiles == 0) {
-            recur_tile<TN>(a, (T / a.j_tiles) * TN, 0, Gs, Hs, ns);
+            recur_tile<TN>(a, (T / a.j_tiles) * TN, 0, Gs, Hs, ns, qstage);
             if (tid == 0) st_release_u32(&flags[T / a.j_tiles], 1u);
         }
 
@@ -859,7 +853,7 @@ persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 }
                 __syncthreads();
                 if (s_last) {   // every column range of this neuron tile has delivered its dots for block blk+1
-                    recur_tile<TN>(a, row0, blk + 1, Gs, Hs, ns);
+                    recur_tile<TN>(a, row0, blk + 1, Gs, Hs, ns, qstage);
                     if (tid == 0) st_release_u32(&flags[ntile], (unsigned)(blk + 2));
                 }
             }
@@ -884,8 +878,8 @@ persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 template <int R>
 static size_t persistent_smem_bytes() {
     constexpr int TN = 32 * R;
-    return 128 + (size_t)(2 * kStageFloats + 2 * kB * TN) * sizeof(float) + 2 * kB * (kB + 1) * sizeof(double) +
-           kB * sizeof(float) + 64;
+    return 128 + (size_t)(2 * kStageFloats + 2 * kB * TN) * sizeof(float) + 4 * kB * kB * sizeof(double) +
+           (size_t)(kB + kB * TN) * sizeof(float) + 64;
 }
 
 

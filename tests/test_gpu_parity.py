@@ -240,3 +240,20 @@ def test_gram_matrices_tcgen05_accuracy(qb):
         for got, want in zip(out, (Xd @ Xqd.T, Xqd @ Xqd.T, Xd @ Xd.T)):
             rel = ((got[:d, :d] - want).norm() / want.norm()).item()
             assert rel < tol, (solver, rel)
+
+
+@pytest.mark.parametrize("env", [{"GPFQ_RESIDENT": "1"}, {"GPFQ_PERSISTENT": "1", "GPFQ_RESIDENT": "0"},
+                                 {"GPFQ_RESIDENT": "0", "GPFQ_PERSISTENT": "0"}],
+                         ids=["resident", "persistent", "multi_launch"])
+def test_direct_solver_variants_in_subprocess(env):
+    """The three launch structures of the direct solver (multi-launch sweep+recur, single-launch resident,
+    single-launch persistent) are selected per layer by a heuristic; force each one over the same small
+    problems (oracle-checked inside tools/sanitize_smoke.py).  The switches are read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_smoke.py")], env={**os.environ, **env},
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "FAIL" not in out.stdout
