@@ -25,10 +25,12 @@
 extern "C" {
 #endif
 
-#define GPFQ_ABI_VERSION 2
+#define GPFQ_ABI_VERSION 3
 
-/* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0') */
-enum { GPFQ_MODE_MSQ = 0, GPFQ_MODE_SOFT = 1, GPFQ_MODE_HARD = 2 };
+/* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0'),
+ * :7-35 (STOCHASTIC, SGPFQ: stochastic rounding to the two neighbouring grid points, then clipping; the
+ * uniforms come from a Philox4x32-10 stream keyed by (seed, neuron index, feature index)) */
+enum { GPFQ_MODE_MSQ = 0, GPFQ_MODE_SOFT = 1, GPFQ_MODE_HARD = 2, GPFQ_MODE_STOCHASTIC = 3 };
 
 /* solver variants: 0 = blocked direct (exact reference update order, fp32 SIMT);
  *                  1 = Gram form, Gram matrices formed on tcgen05 tensor cores (split-TF32, 3 MMAs per product);
@@ -41,7 +43,7 @@ const char* gpfq_last_error(void);
 /* Elementwise alphabet map out[i] = quantizer(x[i]); replaces the three quantizer functions
  * of step_algorithm.py:38-104 for unit parity.  delta is read from device memory. */
 int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta, int32_t K,
-                      int32_t mode, float lam, void* stream);
+                      int32_t mode, float lam, uint64_t seed, void* stream);
 
 /* (rows x cols, ld_in) row-major  ->  (cols x ld_out) row-major, columns rows..ld_out-1 zeroed.
  * Turns the reference's (m x d) layer input (quantize_neural_net.py:291,347) into feature-major. */
@@ -72,7 +74,8 @@ int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, 
 /* The greedy path-following solve: replaces StepAlgorithm._quantization
  * (step_algorithm.py:107-148) plus the residual norms of _quantize_layer (:216-219) for
  * neurons [n0, n1) of W.
- *   W (N x d, ldw), X / Xq feature-major (d x ldx), *delta on device, K = 2^(bits-1).
+ *   W (N x d, ldw), X / Xq feature-major (d x ldx), *delta on device, K = 2^(bits-1); seed is used by
+ *   GPFQ_MODE_STOCHASTIC only (same seed => same Q whatever the neuron range or solver structure).
  *   Q (N x d, ldq): rows n0..n1-1 written (fp32 alphabet values, as the reference stores them).
  *   levels: optional int8 (N x d, ld = d) signed level indices, rows n0..n1-1 (may be NULL).
  *   row_err2: optional double[n1-n0], ||u_n||^2 of the final residual (may be NULL).
@@ -83,7 +86,7 @@ int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, 
  */
 int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq,
                    int64_t ldx, int32_t N, int32_t d, int32_t m, int32_t n0, int32_t n1,
-                   const float* delta, int32_t K, int32_t mode, float lam, float* Q, int64_t ldq,
+                   const float* delta, int32_t K, int32_t mode, float lam, uint64_t seed, float* Q, int64_t ldq,
                    int8_t* levels, double* row_err2, double* row_ref2, float* U_out, int64_t ldu,
                    void* workspace, size_t workspace_bytes, void* stream);
 

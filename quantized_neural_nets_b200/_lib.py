@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpfq_b200.so")
 
-MODE_MSQ, MODE_SOFT, MODE_HARD = 0, 1, 2
+MODE_MSQ, MODE_SOFT, MODE_HARD, MODE_STOCHASTIC = 0, 1, 2, 3
 SOLVER_DIRECT, SOLVER_GRAM, SOLVER_GRAM_F64 = 0, 1, 2
 
 c_ptr = ctypes.c_void_p  # device pointers travel as integers
@@ -27,14 +27,14 @@ SIGNATURES = {
     "gpfq_launch_count": (c_i64, []),
     "gpfq_profile_begin": (c_i32, []),
     "gpfq_profile_end": (c_i32, [ctypes.POINTER(ctypes.c_double)]),
-    "gpfq_quantize_f32": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, c_ptr]),
+    "gpfq_quantize_f32": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, ctypes.c_uint64, c_ptr]),
     "gpfq_transpose_f32": (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gpfq_im2col_gather_f32": (c_i32, [c_ptr] + [c_i32] * 12 + [c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gpfq_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     "gpfq_gram_f32": (c_i32, [c_i32, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
     "gpfq_solve_f32": (c_i32, [c_i32, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
-                               c_ptr, c_i32, c_i32, c_f32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
-                               ctypes.c_size_t, c_ptr]),
+                               c_ptr, c_i32, c_i32, c_f32, ctypes.c_uint64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
+                               c_ptr, ctypes.c_size_t, c_ptr]),
 }
 
 

@@ -102,11 +102,12 @@ int make_tensor_map_2d_sw128(CUtensorMap* map, const float* base, int64_t rows, 
 
 // ------------------------------------------------------------------------------------------
 __global__ void quantize_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n,
-                                const float* __restrict__ delta_p, float Kf, int mode, float lam) {
+                                const float* __restrict__ delta_p, float Kf, int mode, float lam,
+                                unsigned long long seed) {
     const float delta = *delta_p;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int lv;
-        out[i] = alphabet_map(x[i], delta, Kf, mode, lam, &lv);
+        out[i] = alphabet_map(x[i], delta, Kf, mode, lam, &lv, seed, (uint32_t)i, (uint32_t)(i >> 32));
     }
 }
 
@@ -204,12 +205,13 @@ int gpfq_profile_end(double* out_host) {
 }
 
 int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
-                      void* stream) {
-    GPFQ_REQUIRE(mode >= 0 && mode <= 2, "gpfq_quantize_f32: bad mode %d", mode);
+                      uint64_t seed, void* stream) {
+    GPFQ_REQUIRE(mode >= 0 && mode <= 3, "gpfq_quantize_f32: bad mode %d", mode);
     GPFQ_REQUIRE(n >= 0 && K >= 1, "gpfq_quantize_f32: bad size/K");
     if (n == 0) return 0;
     int blocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
-    quantize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n, delta, (float)K, mode, lam);
+    quantize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n, delta, (float)K, mode, lam,
+                                                              (unsigned long long)seed);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

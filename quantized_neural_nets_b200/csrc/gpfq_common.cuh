@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "../../include/gpfq_b200.h"
@@ -48,6 +49,25 @@ void profile_mark_begin(cudaStream_t stream);
 void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr);
 void profile_count_other(int n);
 
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    // Measured on B200 (r01): with the attribute the sweep/recur chain of launch-bound layers gets SLOWER
+    // (512x4608x768: 4.04 ms vs 3.67 ms), only large layers gain 3-9 %; opt-in with GPFQ_PDL=1.
+    static const bool enabled = getenv("GPFQ_PDL") && atoi(getenv("GPFQ_PDL")) == 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
@@ -69,11 +89,41 @@ __device__ __forceinline__ float shrinkf(float x, float lam) {
     return __fmul_rn(sgnf(x), fmaxf(__fsub_rn(fabsf(x), lam), 0.f));
 }
 
+// Philox4x32-10 counter-based generator: one uniform in [0, 1) per (seed, neuron, feature), so the stochastic
+// alphabet map does not depend on how neurons are distributed over threads, CTAs or GPUs.
+__device__ __forceinline__ float philox_u01(unsigned long long seed, uint32_t c0, uint32_t c1) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t x0 = c0, x1 = c1, x2 = 0x9E3779B9u, x3 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+        const uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+        x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return (float)(x0 >> 8) * (1.0f / 16777216.0f);
+}
+
 // Returns the alphabet value; *level receives the signed level index
-// (msq/soft: value == level*delta; hard: value == sign*(lam + (|level|-1)*delta), level 0 == pruned).
+// (msq/soft/stochastic: value == level*delta; hard: value == sign*(lam + (|level|-1)*delta), level 0 == pruned).
+// GPFQ_MODE_STOCHASTIC (step_algorithm.py:7-35): round down with probability 1 - x/delta + floor(x/delta), else up,
+// then clip to +-delta*K; the uniform comes from philox_u01(seed, neuron, feature).
 template <int MODE>
-__device__ __forceinline__ float alphabet_map_t(float x, float delta, float Kf, float lam, int* level) {
-    if (MODE == GPFQ_MODE_MSQ) {
+__device__ __forceinline__ float alphabet_map_t(float x, float delta, float Kf, float lam, int* level,
+                                                unsigned long long seed = 0, uint32_t neuron = 0, uint32_t feature = 0) {
+    if (MODE == GPFQ_MODE_STOCHASTIC) {
+        const float r = __fdiv_rn(x, delta);
+        const float fl = floorf(r);
+        const float p_down = __fadd_rn(__fsub_rn(1.f, r), fl);
+        const bool down = philox_u01(seed, neuron, feature) < p_down;
+        const float k = down ? fl : __fadd_rn(fl, 1.f);
+        float q = __fmul_rn(delta, k);
+        if (fabsf(q) > __fmul_rn(delta, Kf)) q = __fmul_rn(__fmul_rn(sgnf(q), delta), Kf);
+        *level = (int)fmaxf(fminf(k, Kf), -Kf);
+        return q;
+    } else if (MODE == GPFQ_MODE_MSQ) {
         float k = level_count(x, delta, Kf);
         float s = sgnf(x);
         *level = (int)(s * k);
@@ -96,10 +146,12 @@ __device__ __forceinline__ float alphabet_map_t(float x, float delta, float Kf, 
     }
 }
 
-__device__ __forceinline__ float alphabet_map(float x, float delta, float Kf, int mode, float lam, int* level) {
+__device__ __forceinline__ float alphabet_map(float x, float delta, float Kf, int mode, float lam, int* level,
+                                              unsigned long long seed = 0, uint32_t neuron = 0, uint32_t feature = 0) {
     if (mode == GPFQ_MODE_MSQ) return alphabet_map_t<GPFQ_MODE_MSQ>(x, delta, Kf, lam, level);
     if (mode == GPFQ_MODE_SOFT) return alphabet_map_t<GPFQ_MODE_SOFT>(x, delta, Kf, lam, level);
-    return alphabet_map_t<GPFQ_MODE_HARD>(x, delta, Kf, lam, level);
+    if (mode == GPFQ_MODE_HARD) return alphabet_map_t<GPFQ_MODE_HARD>(x, delta, Kf, lam, level);
+    return alphabet_map_t<GPFQ_MODE_STOCHASTIC>(x, delta, Kf, lam, level, seed, neuron, feature);
 }
 
 // ---------------------------------------------------------------- device side: mbarrier + TMA
@@ -145,6 +197,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still running; pdl_wait() blocks until that predecessor has completed and its writes are visible,
+// pdl_trigger() lets the successor start launching.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Host: encode a 2-D fp32 tensor map over a (rows x cols) row-major matrix with leading dimension ld.
 int make_tensor_map_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,

@@ -256,7 +256,8 @@ struct RecurArgs {
     const float* norm32; // this block: [kB]
     const float* delta;
     int64_t Npad;
-    int n_rows, d, t0, bvalid, j_tiles, first, mode;
+    int n_rows, d, t0, bvalid, j_tiles, first, mode, n_base;
+    unsigned long long seed;
     float Kf, lam;
 };
 
@@ -268,6 +269,8 @@ __global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
     __shared__ double Hs[kB][kB + 1];
     __shared__ float ns[kB];
     __shared__ double psum[8][kB];
+    pdl_trigger();
+    pdl_wait();
     for (int e = threadIdx.x; e < kB * kB; e += blockDim.x) {
         Gs[e / kB][e % kB] = a.G[e];
         Hs[e / kB][e % kB] = a.H[e];
@@ -312,7 +315,8 @@ __global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
         const float nrm = ns[t];
         const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;   // step_algorithm.py:143-146
         int lv;
-        const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv);
+        const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv, a.seed, (uint32_t)(a.n_base + n),
+                                     (uint32_t)(a.t0 + t));
         if (lane == t) {
             q_mine = q;
             lv_mine = lv;
@@ -367,7 +371,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         mbar_init(&bars[1], 1);
         fence_barrier_init();
     }
+    pdl_trigger();        // the next kernel of the chain (the block's recurrence) may start launching
     __syncthreads();
+    pdl_wait();           // Q of this block / U of the previous sweep come from the preceding kernels
 
     const uint32_t stage_bytes = (uint32_t)((2 + (a.has_next ? 1 : 0)) * kB * kJS * sizeof(float));
     auto issue = [&](int st) {
@@ -563,7 +569,8 @@ struct PersistArgs {
     const float* delta;
     unsigned int* sync;     // tickets[n_tiles] | flags[n_tiles], zeroed before the launch
     int64_t Npad, mpad;
-    int n_rows, d, nblk, TJ, j_tiles, n_tiles, mode, want_err, store_last_u;
+    int n_rows, d, nblk, TJ, j_tiles, n_tiles, mode, want_err, store_last_u, n_base;
+    unsigned long long seed;
     float Kf, lam;
 };
 
@@ -620,7 +627,8 @@ __device__ void recur_tile(const PersistArgs& a, int row0, int blk, double* Gz, 
             const float nrm = ns[t];
             const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
             int lv;
-            const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv);
+            const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv, a.seed, (uint32_t)(a.n_base + n),
+                                         (uint32_t)(t0 + t));
             qstage[t * TN + nl] = q;
             if (a.levels && valid) a.levels[(int64_t)n * a.ldl + t0 + t] = (int8_t)lv;
             const double wd = (double)wt, qd = -(double)q;
@@ -910,6 +918,8 @@ struct ResidentArgs {
     float* U;           // tiled global U, written once at the end when store_u
     int64_t Npad;
     int n_rows, d, nblk, mpad, mode, store_u, slots;   // slots = depth of the TMA ring (2..4)
+    int n_base;
+    unsigned long long seed;
     float Kf, lam;
 };
 
@@ -1015,7 +1025,8 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const float nrm = ns[t];
                 const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
                 int lv;
-                const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv);
+                const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
+                                                     (uint32_t)(a.n_base + row0 + nl), (uint32_t)(t0 + t));
                 qsm[((t >> 2) * TN + nl) * 4 + (t & 3)] = q;
                 if (a.levels && row0 + nl < a.n_rows) a.levels[(int64_t)(row0 + nl) * a.ldl + t0 + t] = (int8_t)lv;
                 const double wd = (double)wt, qd = -(double)q;
@@ -1202,7 +1213,7 @@ static int launch_sweep(const DirectPlan& p, const CUtensorMap& tmX, const CUten
     }
     dim3 grid((unsigned)p.j_tiles, (unsigned)p.n_tiles);
     profile_mark_begin(stream);
-    sweep_kernel<R><<<grid, kThreads, smem, stream>>>(tmX, tmXq, a);
+    GPFQ_CUDA_TRY(launch_pdl(sweep_kernel<R>, grid, dim3(kThreads), smem, stream, tmX, tmXq, a));
     if (profile_on()) {
         // algorithmic HBM bytes of one sweep: U read (unless first) + U write (if stored), the three
         // kB-row X / Xq tiles once, the W / Q block tiles, and the fp64 partials written for the recurrence
@@ -1249,8 +1260,8 @@ static int launch_persistent(const DirectPlan& p, const CUtensorMap& tmX, const 
 }
 
 int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m, int n_rows,
-                 const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
-                 double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
+                 const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q, int64_t ldq,
+                 int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream) {
     const DirectPlan p = make_plan(n_rows, d, m);
     GPFQ_REQUIRE(workspace_bytes >= p.total, "gpfq_solve_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
@@ -1284,6 +1295,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d; a.G = G; a.H = H; a.norm32 = norm32;
         a.delta = delta; a.row_err2 = row_err2; a.U = U; a.Npad = p.Npad; a.n_rows = n_rows; a.d = d; a.nblk = p.nblk;
         a.mpad = mp; a.mode = mode; a.store_u = (U_out != nullptr); a.Kf = (float)K; a.lam = lam;
+        a.seed = seed; a.n_base = n_base;
         // 16 neurons per CTA when two such CTAs fit on an SM (their recurrences and sweeps then overlap)
         static const int force_tn = getenv("GPFQ_RESIDENT_TN") ? atoi(getenv("GPFQ_RESIDENT_TN")) : 0;   // tuning aid
         const int TN = force_tn ? force_tn : (resident_smem_bytes(mp, 2, 16) <= 113 * 1024 ? 16 : 32);
@@ -1291,10 +1303,12 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         while (a.slots > 2 && resident_smem_bytes(mp, a.slots, TN) > 225 * 1024) --a.slots;
         const size_t smem = resident_smem_bytes(mp, a.slots, TN);
         typedef void (*ResidentFn)(const CUtensorMap, const CUtensorMap, const ResidentArgs);
-        static const ResidentFn table[2][3] = {
-            {resident_kernel<32, GPFQ_MODE_MSQ>, resident_kernel<32, GPFQ_MODE_SOFT>, resident_kernel<32, GPFQ_MODE_HARD>},
-            {resident_kernel<16, GPFQ_MODE_MSQ>, resident_kernel<16, GPFQ_MODE_SOFT>, resident_kernel<16, GPFQ_MODE_HARD>}};
-        static size_t configured[2][3] = {{0, 0, 0}, {0, 0, 0}};
+        static const ResidentFn table[2][4] = {
+            {resident_kernel<32, GPFQ_MODE_MSQ>, resident_kernel<32, GPFQ_MODE_SOFT>, resident_kernel<32, GPFQ_MODE_HARD>,
+             resident_kernel<32, GPFQ_MODE_STOCHASTIC>},
+            {resident_kernel<16, GPFQ_MODE_MSQ>, resident_kernel<16, GPFQ_MODE_SOFT>, resident_kernel<16, GPFQ_MODE_HARD>,
+             resident_kernel<16, GPFQ_MODE_STOCHASTIC>}};
+        static size_t configured[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
         const ResidentFn fn = table[TN == 16][mode];
         if (smem > configured[TN == 16][mode]) {
             GPFQ_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1324,7 +1338,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         a.G = G; a.H = H; a.norm32 = norm32; a.delta = delta; a.sync = sync; a.Npad = p.Npad; a.mpad = p.mpad;
         a.n_rows = n_rows; a.d = d; a.nblk = p.nblk; a.TJ = p.pTJ; a.j_tiles = p.p_j_tiles; a.n_tiles = p.p_n_tiles;
         a.mode = mode; a.want_err = (row_err2 != nullptr); a.store_last_u = (U_out != nullptr);
-        a.Kf = (float)K; a.lam = lam;
+        a.Kf = (float)K; a.lam = lam; a.seed = seed; a.n_base = n_base;
         int rc = p.pR == 2 ? launch_persistent<2>(p, tmX, tmXq, a, stream) : launch_persistent<1>(p, tmX, tmXq, a, stream);
         if (rc) return rc;
         if (row_err2) {
@@ -1348,10 +1362,10 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         r.part = part; r.G = G + (size_t)blk * kB * kB; r.H = H + (size_t)blk * kB * kB;
         r.norm32 = norm32 + (size_t)blk * kB; r.delta = delta; r.Npad = p.Npad;
         r.n_rows = n_rows; r.d = d; r.t0 = t0; r.bvalid = bvalid; r.j_tiles = p.j_tiles;
-        r.first = (blk == 0); r.mode = mode; r.Kf = (float)K; r.lam = lam;
-        if (p.j_tiles >= 24) recur_kernel<8><<<(unsigned)n_rows, 256, 0, stream>>>(r);
-        else if (p.j_tiles >= 8) recur_kernel<2><<<(unsigned)ceil_div(n_rows, 4), 256, 0, stream>>>(r);
-        else recur_kernel<1><<<(unsigned)ceil_div(n_rows, 8), 256, 0, stream>>>(r);
+        r.first = (blk == 0); r.mode = mode; r.Kf = (float)K; r.lam = lam; r.seed = seed; r.n_base = n_base;
+        if (p.j_tiles >= 24) GPFQ_CUDA_TRY(launch_pdl(recur_kernel<8>, dim3(n_rows), dim3(256), 0, stream, r));
+        else if (p.j_tiles >= 8) GPFQ_CUDA_TRY(launch_pdl(recur_kernel<2>, dim3((unsigned)ceil_div(n_rows, 4)), dim3(256), 0, stream, r));
+        else GPFQ_CUDA_TRY(launch_pdl(recur_kernel<1>, dim3((unsigned)ceil_div(n_rows, 8)), dim3(256), 0, stream, r));
         GPFQ_CHECK_LAUNCH();
         profile_count_other(1);
 

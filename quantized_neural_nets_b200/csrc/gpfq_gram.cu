@@ -167,7 +167,8 @@ struct GramPathArgs {
     const float* delta;
     double* row_err2;
     double* row_ref2;
-    int n_rows, d, mode;
+    int n_rows, d, mode, n_base;
+    unsigned long long seed;
     float Kf, lam;
 };
 
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
                 const double dot = fma((double)wt, gtt, pt);
                 const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
                 int lv;
-                const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv);
+                const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv, a.seed,
+                                             (uint32_t)(a.n_base + n_base + warp * kNB + i), (uint32_t)(t0 + t));
                 if (lane == t) {
                     qmine[i] = q;
                     lvmine[i] = lv;
@@ -351,8 +353,9 @@ int gram_matrices(int solver, const float* X, const float* Xq, int64_t ldx, int 
 }
 
 int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m,
-               int n_rows, const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
-               double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+               int n_rows, const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q,
+               int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream) {
     const GramPlan p = gram_plan(solver, d, m);
     GPFQ_REQUIRE(workspace_bytes >= p.total, "gpfq_solve_f32: workspace too small (%zu < %zu)", workspace_bytes, p.total);
     GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "gpfq_solve_f32: workspace must be 256-byte aligned");
@@ -375,7 +378,7 @@ int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const fl
     GramPathArgs a{};
     a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d;
     a.GT = GT; a.H = H; a.A = A; a.ldg = p.dpad; a.delta = delta; a.row_err2 = row_err2; a.row_ref2 = row_ref2;
-    a.n_rows = n_rows; a.d = d; a.mode = mode; a.Kf = (float)K; a.lam = lam;
+    a.n_rows = n_rows; a.d = d; a.mode = mode; a.Kf = (float)K; a.lam = lam; a.seed = seed; a.n_base = n_base;
     const int dpad32 = (int)round_up(d, kGB);
     auto smem_for = [&](int nb) {
         return (size_t)2 * nb * kPathWarps * dpad32 * sizeof(float) + 3 * kGB * 33 * sizeof(double);

@@ -4,13 +4,14 @@
 namespace gpfq {
 size_t direct_workspace_bytes(int n_rows, int d, int m);
 int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m, int n_rows,
-                 const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
-                 double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
+                 const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q, int64_t ldq,
+                 int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream);
 size_t gram_workspace_bytes(int solver, int n_rows, int d, int m);
 int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m,
-               int n_rows, const float* delta, int K, int mode, float lam, float* Q, int64_t ldq, int8_t* levels,
-               double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+               int n_rows, const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q,
+               int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream);
 int gram_matrices(int solver, const float* X, const float* Xq, int64_t ldx, int d, int m, double* GT, double* H,
                   double* A, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace gpfq
@@ -37,11 +38,11 @@ int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, 
 
 int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int32_t N,
                    int32_t d, int32_t m, int32_t n0, int32_t n1, const float* delta, int32_t K, int32_t mode, float lam,
-                   float* Q, int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, float* U_out, int64_t ldu,
+                   uint64_t seed, float* Q, int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, float* U_out, int64_t ldu,
                    void* workspace, size_t workspace_bytes, void* stream) {
     GPFQ_REQUIRE(N >= 0 && d >= 0 && m >= 0, "gpfq_solve_f32: negative dimension");
     GPFQ_REQUIRE(0 <= n0 && n0 <= n1 && n1 <= N, "gpfq_solve_f32: bad neuron range [%d, %d) of %d", n0, n1, N);
-    GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_HARD, "gpfq_solve_f32: bad mode %d", mode);
+    GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_STOCHASTIC, "gpfq_solve_f32: bad mode %d", mode);
     GPFQ_REQUIRE(K >= 1 && K <= 127, "gpfq_solve_f32: boundary index K=%d outside [1,127]", K);
     GPFQ_REQUIRE(ldw >= d && ldq >= d, "gpfq_solve_f32: ldw/ldq smaller than d");
     GPFQ_REQUIRE(ldx >= m && (ldx % 4) == 0, "gpfq_solve_f32: ldx must be >= m and a multiple of 4");
@@ -55,13 +56,13 @@ int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, 
     int8_t* Ls = levels ? levels + (int64_t)n0 * d : nullptr;
     if (solver == GPFQ_SOLVER_GRAM || solver == GPFQ_SOLVER_GRAM_F64) {
         GPFQ_REQUIRE(U_out == nullptr, "gpfq_solve_f32: the Gram solvers do not materialise U (U_out must be NULL)");
-        return gram_solve(solver, Ws, ldw, X, Xq, ldx, d, m, n_rows, delta, K, mode, lam, Qs, ldq, Ls, row_err2,
+        return gram_solve(solver, Ws, ldw, X, Xq, ldx, d, m, n_rows, delta, K, mode, lam, seed, n0, Qs, ldq, Ls, row_err2,
                           row_ref2, workspace, workspace_bytes, (cudaStream_t)stream);
     }
     GPFQ_REQUIRE(row_ref2 == nullptr || solver != GPFQ_SOLVER_DIRECT,
                  "gpfq_solve_f32: row_ref2 is produced by the Gram solvers only");
     if (solver == GPFQ_SOLVER_DIRECT)
-        return direct_solve(Ws, ldw, X, Xq, ldx, d, m, n_rows, delta, K, mode, lam, Qs, ldq, Ls, row_err2, U_out, ldu,
+        return direct_solve(Ws, ldw, X, Xq, ldx, d, m, n_rows, delta, K, mode, lam, seed, n0, Qs, ldq, Ls, row_err2, U_out, ldu,
                             workspace, workspace_bytes, (cudaStream_t)stream);
     GPFQ_REQUIRE(false, "gpfq_solve_f32: unknown solver %d", solver);
 }

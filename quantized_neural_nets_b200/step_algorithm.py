@@ -24,13 +24,19 @@ def _delta_tensor(step_size, device):
     return torch.tensor([float(step_size)], dtype=torch.float32, device=device)
 
 
-def _elementwise(mode, step_size, x, boundary_idx, lamb):
+def draw_seed():
+    """Seed of one stochastic solve, taken from torch's global CPU generator (so ``torch.manual_seed`` makes SGPFQ
+    runs reproducible, and ranks seeded alike draw alike)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def _elementwise(mode, step_size, x, boundary_idx, lamb, seed=0):
     require_cuda(x)
     xc = x.contiguous()
     out = torch.empty_like(xc)
     delta = _delta_tensor(step_size, x.device)
     check(lib.gpfq_quantize_f32(ptr(xc), ptr(out), xc.numel(), ptr(delta), int(boundary_idx), mode, float(lamb),
-                                stream_ptr()))
+                                int(seed), stream_ptr()))
     return out
 
 
@@ -52,7 +58,7 @@ def feature_major(X):
 
 
 def solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, want_err=True, want_residual=False,
-               levels=None, solver=None, want_ref=False):
+               levels=None, solver=None, want_ref=False, seed=0):
     """Run the greedy path for neurons [n0, n1) of W (N x d) against feature-major inputs.
     Writes rows n0..n1-1 of Q.  Returns (row_err2 | None, U (n1-n0, m) | None, row_ref2 | None);
     row_ref2 (||X w_n||^2) is produced by the Gram solvers only."""
@@ -74,7 +80,7 @@ def solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, want_err=T
         raise RuntimeError(f"libgpfq_b200: solver {solver} does not support a (d={d}, m={m}) layer")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib.gpfq_solve_f32(solver, ptr(W), W.stride(0), ptr(Xfm), ptr(Xqfm), ldx, N, d, m, n0, n1, ptr(delta),
-                             int(K), mode, float(lamb), ptr(Q), Q.stride(0), ptr(levels), ptr(row_err2),
+                             int(K), mode, float(lamb), int(seed), ptr(Q), Q.stride(0), ptr(levels), ptr(row_err2),
                              ptr(row_ref2), ptr(U), m, ptr(ws), nbytes, stream_ptr()))
     if want_residual and gram:      # the Gram solvers never form U; rebuild it only when somebody asks for it
         U = torch.matmul(W[n0:n1], Xfm[:, :m]) - torch.matmul(Q[n0:n1], Xqfm[:, :m])
@@ -96,7 +102,7 @@ def gram_eligible(rows, d, m):
     return d <= 2048 and m >= 2 * d and rows * 2 >= d
 
 
-def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates):
+def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates, seed=0):
     N, d = W.shape
     times, results = {}, {}
     for sv in candidates:
@@ -104,7 +110,8 @@ def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates):
         for rep in range(2):                                   # first repetition warms caches / attributes
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Qs, n0, n1, want_err=True, solver=sv, want_ref=True)
+            solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Qs, n0, n1, want_err=True, solver=sv, want_ref=True,
+                       seed=seed)
             b.record()
         b.synchronize()
         times[sv] = a.elapsed_time(b)
@@ -120,7 +127,7 @@ def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates):
     return best, times, agree_best
 
 
-def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1):
+def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, seed=0):
     if solver != AUTO:
         return DEFAULT_SOLVER if solver is None else solver
     rows, d = n1 - n0, W.shape[1]
@@ -134,7 +141,7 @@ def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1):
         if len(candidates) == 1:
             _AUTO_CHOICE[key] = _lib.SOLVER_DIRECT
         else:
-            best, times, agree = _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates)
+            best, times, agree = _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates, seed)
             _AUTO_CHOICE[key] = best
             AUTO_LOG.append((key, times, agree, best))
     return _AUTO_CHOICE[key]
@@ -158,10 +165,13 @@ class StepAlgorithm:
         return _elementwise(_lib.MODE_HARD, step_size, x, boundary_idx, lamb)
 
     def _stochastic_msq(step_size, x, boundary_idx, lamb):
-        """SGPFQ map (reference step_algorithm.py:7-35).  Its Bernoulli draws come from torch's
-        global generator and cannot be reproduced by a custom kernel; listed as a 'next' row in
-        SURVEY.md section 8f and not part of this library yet."""
-        raise NotImplementedError("stochastic quantization (SGPFQ) is not implemented by libgpfq_b200 yet")
+        """SGPFQ map (reference step_algorithm.py:7-35): stochastic rounding to the two neighbouring grid
+        points, then clipping; works IN PLACE on ``x`` like the reference.  The reference's Bernoulli draws
+        come from torch's global generator, ours from a Philox stream seeded from it, so results agree in
+        distribution (E[q] = x inside the alphabet), not bit for bit."""
+        out = _elementwise(_lib.MODE_STOCHASTIC, step_size, x, boundary_idx, lamb, seed=draw_seed())
+        x.copy_(out.view_as(x))
+        return x
 
     _MODE_OF = {}
 
@@ -184,8 +194,9 @@ class StepAlgorithm:
             Xqfm, ldq = _repack(Xqfm, m, ldx)
         delta = _delta_tensor(step_size, W.device)
         Qc = Q if (Q.stride(1) == 1) else torch.empty((N, d), dtype=torch.float32, device=W.device)
+        seed = draw_seed() if mode == _lib.MODE_STOCHASTIC else 0
         _, Ures, _ = solve_rows(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Qc, 0, N,
-                                want_err=False, want_residual=True)
+                                want_err=False, want_residual=True, seed=seed)
         if Qc is not Q:
             Q.copy_(Qc)
         U.copy_(Ures)
@@ -206,6 +217,7 @@ StepAlgorithm._MODE_OF = {
     StepAlgorithm._msq: _lib.MODE_MSQ,
     StepAlgorithm._soft_thresholding_msq: _lib.MODE_SOFT,
     StepAlgorithm._hard_thresholding_msq: _lib.MODE_HARD,
+    StepAlgorithm._stochastic_msq: _lib.MODE_STOCHASTIC,
 }
 
 
@@ -242,14 +254,12 @@ def mode_of(reg, stochastic_quantization):
         return _lib.MODE_SOFT
     if reg == 'L0':
         return _lib.MODE_HARD
-    if stochastic_quantization:
-        raise NotImplementedError("stochastic quantization (SGPFQ) is not implemented by libgpfq_b200 yet")
-    return _lib.MODE_MSQ
+    return _lib.MODE_STOCHASTIC if stochastic_quantization else _lib.MODE_MSQ
 
 
 def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, lamb, groups,
                         stochastic_quantization, device, want_adder=False, neuron_range=None, levels=None,
-                        solver=None, return_partials=False, delta=None):
+                        solver=None, return_partials=False, delta=None, seed=None):
     """Shared body of ``StepAlgorithm._quantize_layer`` and of the sharded orchestrator.
 
     neuron_range=(n0, n1) restricts the solve to a contiguous slice of output neurons (rows
@@ -262,6 +272,8 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
         raise RuntimeError("libgpfq_b200 runs on CUDA devices only; there is no CPU fallback")
     require_cuda(W, X, Xq)
     mode = mode_of(reg, stochastic_quantization)
+    if seed is None:    # one seed per layer; every neuron slice / rank must be handed the same one
+        seed = draw_seed() if mode == _lib.MODE_STOCHASTIC else 0
     N, d = W.shape
     dev = W.device
     n0, n1 = (0, N) if neuron_range is None else neuron_range
@@ -284,10 +296,10 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
             continue
         Xg = Xfm[g * d:(g + 1) * d]
         Xqg = Xqfm[g * d:(g + 1) * d]
-        sv = resolve_solver(solver, Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, g0, g1)
+        sv = resolve_solver(solver, Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, g0, g1, seed)
         e2, Ures, r2 = solve_rows(Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, Q, g0, g1,
                                   want_err=True, want_residual=(want_adder and groups == 1), levels=levels,
-                                  solver=sv, want_ref=True)
+                                  solver=sv, want_ref=True, seed=seed)
         err2[g0:g1] = e2
         if r2 is not None:
             ref2[g0:g1] = r2

@@ -93,6 +93,21 @@ def layer_cases():
     save("quantize_layer.npz", **out)
 
 
+def stochastic_cases():
+    """SGPFQ (step_algorithm.py:7-35, 198-208): consumes torch's global generator, so the fixtures fix its seed."""
+    out = {}
+    x, delta, K, lam = gc.quantizer_inputs()["rand"]
+    torch.manual_seed(7)
+    out["map"] = SA._stochastic_msq(delta, x.clone(), K, lam)
+    c = gc.layer_inputs()["l_msq"]
+    torch.manual_seed(8)
+    with quiet():
+        Q, err, rel, _, _ = SA._quantize_layer(c["W"], c["X"], c["Xq"], c["X"].shape[0], c["step"], c["K"], c["pct"], None,
+                                               c["lam"], 1, True, torch.device("cpu"))
+    out["layer_Q"], out["layer_err"], out["layer_rel"] = Q, err, rel
+    save("stochastic.npz", **out)
+
+
 def conv_capture_cases():
     out = {}
     for tag, c in gc.conv_inputs().items():
@@ -144,6 +159,7 @@ if __name__ == "__main__":
     quantizer_tables()
     greedy_cases()
     layer_cases()
+    stochastic_cases()
     conv_capture_cases()
     tiny_network()
     if "--skip-cfg1" not in sys.argv:

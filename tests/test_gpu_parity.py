@@ -178,8 +178,8 @@ def test_errors_are_loud(qb):
                                          1, False, torch.device("cpu"))
     with pytest.raises(NotImplementedError):
         z = torch.zeros(4, 4, device=DEV)
-        qb.StepAlgorithm._quantize_layer(z, torch.zeros(8, 4, device=DEV), torch.zeros(8, 4, device=DEV), 8, 0.1, 8, 1,
-                                         None, 0.1, 1, True, DEV)
+        qb.StepAlgorithm._quantization(z, z.clone(), torch.zeros(4, 8, device=DEV), torch.zeros(8, 4, device=DEV),
+                                       torch.zeros(8, 4, device=DEV), (lambda *a: None), 0.1, 8, 0.0)
 
 
 @pytest.mark.parametrize("solver", [2, 1], ids=["gram_f64", "gram_tcgen05"])
@@ -257,3 +257,54 @@ def test_direct_solver_variants_in_subprocess(env):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "FAIL" not in out.stdout
+
+
+def test_stochastic_map_distribution(qb):
+    """SGPFQ map (reference step_algorithm.py:7-35): every output is one of the two neighbouring grid points,
+    the mean over draws is the input (unbiased) inside the alphabet, and clipping holds."""
+    delta, K = torch.tensor(0.25), 4
+    x0 = torch.tensor([0.10, -0.10, 0.30, 0.70, -0.62, 0.0, 0.25, 3.0, -3.0], device=DEV)
+    torch.manual_seed(0)
+    draws = torch.stack([qb.StepAlgorithm._stochastic_msq(delta.to(DEV), x0.clone(), K, 0.0) for _ in range(4000)])
+    lo = torch.floor(x0 / 0.25) * 0.25
+    inside = x0.abs() < 1.0
+    for j in range(x0.numel()):
+        vals = set(draws[:, j].tolist())
+        if inside[j]:
+            assert vals <= {float(lo[j]), float(lo[j]) + 0.25}, (j, vals)
+            sigma = 0.25 * 0.5 / (4000 ** 0.5)
+            assert abs(draws[:, j].mean().item() - x0[j].item()) < 5 * sigma
+        else:
+            assert vals == {float(torch.sign(x0[j])) * 1.0}, (j, vals)      # clipped to +-delta*K
+    # in place, like the reference
+    y = x0.clone()
+    out = qb.StepAlgorithm._stochastic_msq(delta.to(DEV), y, K, 0.0)
+    assert out.data_ptr() == y.data_ptr()
+
+
+def test_stochastic_solver_statistics_and_invariance(qb):
+    """SGPFQ through the solver: reproducible for a fixed torch seed, independent of neuron slicing and of the
+    solver structure, and statistically equivalent to the oracle's stochastic run (its RNG differs)."""
+    from quantized_neural_nets_b200 import _lib
+    from quantized_neural_nets_b200.step_algorithm import quantize_layer_impl
+    W, X, Xq = gc._problem(seed=81, N=120, d=90, m=1500, relu=True, xq_noise=0.02)
+    Wd, Xd, Xqd = W.to(DEV), X.to(DEV), Xq.to(DEV)
+
+    def run(solver, rng=(0, 120), seed=1234):
+        Q, e2, r2 = quantize_layer_impl(Wd, Xd, Xqd, 1500, 1.16 / 8, 8, 1, None, 0.1, 1, True, DEV, solver=solver,
+                                        neuron_range=rng, return_partials=True, seed=seed)
+        return Q, float((e2.sum() / r2.sum()).sqrt())
+
+    Q0, rel0 = run(_lib.SOLVER_DIRECT)
+    Q1, _ = run(_lib.SOLVER_DIRECT)
+    assert torch.equal(Q0, Q1)
+    Qa, _ = run(_lib.SOLVER_DIRECT, (0, 50))
+    Qb, _ = run(_lib.SOLVER_DIRECT, (50, 120))
+    assert torch.equal(Qa[:50], Q0[:50]) and torch.equal(Qb[50:], Q0[50:])
+    Qg, relg = run(_lib.SOLVER_GRAM_F64)
+    assert (Qg == Q0).float().mean().item() >= 0.999
+    Q2, _ = run(_lib.SOLVER_DIRECT, seed=99)
+    assert not torch.equal(Q2, Q0)
+    torch.manual_seed(3)
+    _, _, relo, _, _ = orc.quantize_layer(W, X, Xq, 1500, 1.16 / 8, 8, 1, None, 0.1, 1, True)
+    assert abs(rel0 - float(relo)) <= 0.15 * float(relo), (rel0, float(relo))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(dll, name), f"{name} declared in gpfq_b200.h but not exported"
     assert declared == set(L.SIGNATURES), "ctypes binding and header disagree"
-    assert L.lib.gpfq_abi_version() == 2
+    assert L.lib.gpfq_abi_version() == 3
 
 
 def test_workspace_and_argument_validation_without_gpu():
@@ -32,10 +32,10 @@ def test_workspace_and_argument_validation_without_gpu():
     assert L.lib.gpfq_workspace_bytes(L.SOLVER_GRAM_F64, 512, 256, 200960) >= 3 * 256 * 256 * 8
     assert L.lib.gpfq_workspace_bytes(L.SOLVER_GRAM_F64, 512, 4608, 768) == 0      # d too large for the Gram form
     # invalid arguments are rejected before anything touches the device
-    rc = L.lib.gpfq_solve_f32(0, None, 4, None, None, 8, 4, 4, 8, 3, 2, None, 8, 0, 0.0, None, 4, None, None, None,
+    rc = L.lib.gpfq_solve_f32(0, None, 4, None, None, 8, 4, 4, 8, 3, 2, None, 8, 0, 0.0, 0, None, 4, None, None, None,
                               None, 8, None, 0, None)
     assert rc != 0 and b"neuron range" in L.lib.gpfq_last_error()
-    rc = L.lib.gpfq_quantize_f32(None, None, 4, None, 8, 7, 0.0, None)
+    rc = L.lib.gpfq_quantize_f32(None, None, 4, None, 8, 7, 0.0, 0, None)
     assert rc != 0 and b"mode" in L.lib.gpfq_last_error()
 
 

@@ -124,3 +124,16 @@ def test_config1_matches_reference(golden):
     assert abs(float(rel) - float(g["rel"])) <= 1e-3 * float(g["rel"])
     assert abs(float(rel) - 0.06468) < 5e-5       # value probed in SURVEY.md section 6
     assert lv.min() >= -8 and lv.max() <= 8
+
+
+def test_stochastic_paths_bit_exact_under_a_fixed_torch_seed(golden):
+    g = golden("stochastic.npz")
+    x, delta, K, lam = gc.quantizer_inputs()["rand"]
+    torch.manual_seed(7)
+    np.testing.assert_array_equal(orc.stochastic_msq(x.clone(), delta, K, lam).numpy(), g["map"])
+    c = gc.layer_inputs()["l_msq"]
+    torch.manual_seed(8)
+    Q, err, rel, _, _ = orc.quantize_layer(c["W"], c["X"], c["Xq"], c["X"].shape[0], c["step"], c["K"], c["pct"], None,
+                                           c["lam"], 1, True)
+    np.testing.assert_array_equal(Q.numpy(), g["layer_Q"])
+    np.testing.assert_array_equal(np.asarray(rel), g["layer_rel"])

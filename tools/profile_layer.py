@@ -22,13 +22,13 @@ Xqfm = torch.relu(Xfm + 0.02 * torch.randn(d, ld, device=dev, generator=g))
 X, Xq = Xfm[:, :m].t(), Xqfm[:, :m].t()
 for r in range(reps):
     torch.cuda.synchronize()
-    _lib.profile_begin()
+    if not os.environ.get('NO_PROFILE'): _lib.profile_begin()
     t0 = time.perf_counter()
     Q, e2, r2 = quantize_layer_impl(W, X, Xq, m, 1.16 / 8, 8, 1, None, 0.1, 1, False, dev, return_partials=True,
                                     solver=solver)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    p = _lib.profile_end()
+    p = _lib.profile_end() if not os.environ.get('NO_PROFILE') else dict(sweep_ms=0.0, sweep_launches=0, sweep_fp32_instr=0.0)
     units = float(N) * d * m
     print(f"rep {r}: {dt*1e3:.3f} ms total, sweep {p['sweep_ms']:.3f} ms in {p['sweep_launches']} launches, "
           f"{units/dt:.3e} w*s/s, sweep fp32 {p['sweep_fp32_instr']/max(p['sweep_ms'],1e-9)/1e6:.1f} Ginstr/s, "
