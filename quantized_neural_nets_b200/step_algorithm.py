@@ -98,8 +98,10 @@ AUTO_LOG = []          # (key, {solver: ms}, agreement, chosen) for reports
 
 
 def gram_eligible(rows, d, m):
-    """Gram form pays off when the 3 Gram products (~ 3 d^2 m) are cheaper than the direct sweeps (~ 5 N d m)."""
-    return d <= 2048 and m >= 2 * d and rows * 2 >= d
+    """Shapes worth TIMING the Gram form on: many more calibration rows than features and Gram matrices of
+    moderate size.  Whether it is used is decided by the measurement (3 d^2 m tensor-core flops + O(N d^2) fp64
+    against 5 N d m fp32 instructions plus the direct path's per-block latency), not by this rule."""
+    return d <= 2048 and m >= 2 * d
 
 
 def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates, seed=0):
@@ -136,6 +138,8 @@ def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, s
         candidates = [_lib.SOLVER_DIRECT]
         if gram_eligible(rows, d, m):
             for sv in AUTO_GRAM_CANDIDATES:
+                if sv == _lib.SOLVER_GRAM_F64 and float(d) * d * m > 2e10:
+                    continue            # fp64 SIMT Gram matrices of this size cannot win; do not spend warm-up on them
                 if lib.gpfq_workspace_bytes(sv, rows, d, m) > 0:
                     candidates.append(sv)
         if len(candidates) == 1:
