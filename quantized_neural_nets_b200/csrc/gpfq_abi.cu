@@ -3,7 +3,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "gpfq_common.cuh"
@@ -20,6 +23,20 @@ void set_error(const char* fmt, ...) {
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     g_error = buf;
+}
+
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> configured;
+    int dev = 0;
+    GPFQ_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = configured[std::make_pair(dev, kernel)];
+    if (bytes > have) {
+        GPFQ_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return 0;
 }
 
 struct ProfileRec {

@@ -43,6 +43,10 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
         GPFQ_CUDA_TRY(cudaGetLastError());  \
     } while (0)
 
+// Raises a kernel's dynamic shared memory limit when needed; remembered per (device, kernel) so that a process
+// that drives several GPUs configures each of them.
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 // bench-only per-launch timing of the dominant kernel (see gpfq_profile_begin/end)
 bool profile_on();
 void profile_mark_begin(cudaStream_t stream);

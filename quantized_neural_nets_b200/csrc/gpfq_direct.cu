@@ -1197,20 +1197,15 @@ __global__ void err_finish_kernel(const double* __restrict__ epart, int j_tiles,
 __global__ void untile_kernel(const float* __restrict__ U, int64_t Npad, int n_rows, int m, float* __restrict__ out,
                               int64_t ldu) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = blockIdx.y;
-    if (j >= m || n >= n_rows) return;
-    out[(int64_t)n * ldu + j] = U[((j >> 2) * Npad + n) * 4 + (j & 3)];
+    if (j >= m) return;
+    for (int n = blockIdx.y; n < n_rows; n += gridDim.y) out[(int64_t)n * ldu + j] = U[((j >> 2) * Npad + n) * 4 + (j & 3)];
 }
 
 template <int R>
 static int launch_sweep(const DirectPlan& p, const CUtensorMap& tmX, const CUtensorMap& tmXq, const SweepArgs& a,
                         cudaStream_t stream) {
-    static bool configured = false;
     const size_t smem = sweep_smem_bytes<R>();
-    if (!configured) {
-        GPFQ_CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_dynamic_smem((const void*)sweep_kernel<R>, smem)) return rc;
     dim3 grid((unsigned)p.j_tiles, (unsigned)p.n_tiles);
     profile_mark_begin(stream);
     GPFQ_CUDA_TRY(launch_pdl(sweep_kernel<R>, grid, dim3(kThreads), smem, stream, tmX, tmXq, a));
@@ -1231,10 +1226,10 @@ static int launch_sweep(const DirectPlan& p, const CUtensorMap& tmX, const CUten
 template <int R>
 static int launch_persistent(const DirectPlan& p, const CUtensorMap& tmX, const CUtensorMap& tmXq, PersistArgs& a,
                              cudaStream_t stream) {
-    static int max_ctas = 0;
+    int max_ctas = 0;
     const size_t smem = persistent_smem_bytes<R>();
-    if (max_ctas == 0) {
-        GPFQ_CUDA_TRY(cudaFuncSetAttribute(persistent_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_dynamic_smem((const void*)persistent_kernel<R>, smem)) return rc;
+    {
         int dev = 0, sms = 0, per_sm = 0;
         GPFQ_CUDA_TRY(cudaGetDevice(&dev));
         GPFQ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1308,12 +1303,8 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
              resident_kernel<32, GPFQ_MODE_STOCHASTIC>},
             {resident_kernel<16, GPFQ_MODE_MSQ>, resident_kernel<16, GPFQ_MODE_SOFT>, resident_kernel<16, GPFQ_MODE_HARD>,
              resident_kernel<16, GPFQ_MODE_STOCHASTIC>}};
-        static size_t configured[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
         const ResidentFn fn = table[TN == 16][mode];
-        if (smem > configured[TN == 16][mode]) {
-            GPFQ_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured[TN == 16][mode] = smem;
-        }
+        if (int rc = ensure_dynamic_smem((const void*)fn, smem)) return rc;
         profile_mark_begin(stream);
         fn<<<(unsigned)ceil_div(n_rows, TN), kThreads, smem, stream>>>(rX, rXq, a);
         if (profile_on()) {
@@ -1323,7 +1314,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         }
         GPFQ_CHECK_LAUNCH();
         if (U_out) {
-            untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)n_rows), 256, 0, stream>>>(U, p.Npad, n_rows, m,
+            untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)std::min(n_rows, 65535)), 256, 0, stream>>>(U, p.Npad, n_rows, m,
                                                                                                  U_out, ldu);
             GPFQ_CHECK_LAUNCH();
         }
@@ -1347,7 +1338,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
             GPFQ_CHECK_LAUNCH();
         }
         if (U_out) {
-            untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)n_rows), 256, 0, stream>>>(U, p.Npad, n_rows, m,
+            untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)std::min(n_rows, 65535)), 256, 0, stream>>>(U, p.Npad, n_rows, m,
                                                                                                  U_out, ldu);
             GPFQ_CHECK_LAUNCH();
         }
@@ -1387,7 +1378,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         GPFQ_CHECK_LAUNCH();
     }
     if (U_out) {
-        untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)n_rows), 256, 0, stream>>>(U, p.Npad, n_rows, m, U_out, ldu);
+        untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)std::min(n_rows, 65535)), 256, 0, stream>>>(U, p.Npad, n_rows, m, U_out, ldu);
         GPFQ_CHECK_LAUNCH();
     }
     return 0;

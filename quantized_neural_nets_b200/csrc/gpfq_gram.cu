@@ -390,14 +390,9 @@ int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const fl
     while (nb > 1 && (smem_for(nb) > 200 * 1024 || ceil_div(n_rows, nb * kPathWarps) < 148)) nb >>= 1;
     const size_t smem = smem_for(nb);
     GPFQ_REQUIRE(smem <= 227 * 1024, "gpfq_solve_f32: Gram solver supports d <= %d (got %d)", kGramMaxD, d);
-    static size_t configured[5] = {0, 0, 0, 0, 0};
-    if (smem > configured[nb]) {
-        cudaError_t e = nb == 4 ? cudaFuncSetAttribute(gram_path_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                      : nb == 2 ? cudaFuncSetAttribute(gram_path_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                : cudaFuncSetAttribute(gram_path_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        GPFQ_CUDA_TRY(e);
-        configured[nb] = smem;
-    }
+    const void* fn = nb == 4 ? (const void*)gram_path_kernel<4> : nb == 2 ? (const void*)gram_path_kernel<2>
+                                                                             : (const void*)gram_path_kernel<1>;
+    if (int rc = ensure_dynamic_smem(fn, smem)) return rc;
     const unsigned grid = (unsigned)ceil_div(n_rows, nb * kPathWarps);
     if (nb == 4) gram_path_kernel<4><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
     else if (nb == 2) gram_path_kernel<2><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);

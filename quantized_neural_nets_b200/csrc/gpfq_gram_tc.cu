@@ -340,11 +340,7 @@ int gram_tc_form(const float* X, const float* Xq, int64_t ldx, int d, int m, dou
     a.partial = partial; a.tiles = p.tiles; a.pairs_full = p.pairs_full; a.pairs_sym = p.pairs_sym;
     a.chunks = p.chunks; a.ldk = p.ldk;
     const size_t smem = (size_t)kStages * kStageFloatsTC * sizeof(float) + 256;
-    static bool configured = false;
-    if (!configured) {
-        GPFQ_CUDA_TRY(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_dynamic_smem((const void*)gram_tc_kernel, smem)) return rc;
     dim3 grid((unsigned)(p.pairs_full + 2 * p.pairs_sym), (unsigned)p.chunks);
     gram_tc_kernel<<<grid, kTcThreads, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], a);
     GPFQ_CHECK_LAUNCH();
