@@ -71,6 +71,14 @@ size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m
 int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, int32_t d, int32_t m,
                   double* GT, double* H, double* A, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The Gram-form recurrence and error norms from GIVEN Gram matrices (as produced by gpfq_gram_f32, or summed over
+ * ranks that each hold a slice of the calibration columns): neurons [n0, n1) of W; outputs as gpfq_solve_f32.
+ * The rows of GT/H/A must be readable up to column round_up(d, 32) (zero beyond d), i.e. ldg >= round_up(d, 32). */
+int gpfq_gram_path_f32(const float* W, int64_t ldw, int32_t N, int32_t d, int32_t n0, int32_t n1,
+                       const double* GT, const double* H, const double* A, int64_t ldg, const float* delta,
+                       int32_t K, int32_t mode, float lam, uint64_t seed, float* Q, int64_t ldq,
+                       int8_t* levels, double* row_err2, double* row_ref2, void* stream);
+
 /* The greedy path-following solve: replaces StepAlgorithm._quantization
  * (step_algorithm.py:107-148) plus the residual norms of _quantize_layer (:216-219) for
  * neurons [n0, n1) of W.

@@ -352,6 +352,38 @@ int gram_matrices(int solver, const float* X, const float* Xq, int64_t ldx, int 
     return gram_tc_form(X, Xq, ldx, d, m, GT, H, A, p.dpad, ws + p.off_scratch, workspace_bytes - p.off_scratch, stream);
 }
 
+// The recurrence + error norms from GIVEN Gram matrices (C ABI gpfq_gram_path_f32).  Used directly when the Gram
+// matrices were assembled elsewhere, e.g. all-reduced over ranks that each hold a slice of the calibration columns.
+int gram_path(const float* W, int64_t ldw, int d, int n_rows, const double* GT, const double* H, const double* A,
+              int64_t ldg, const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q,
+              int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, cudaStream_t stream) {
+    GramPathArgs a{};
+    a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d;
+    a.GT = GT; a.H = H; a.A = A; a.ldg = ldg; a.delta = delta; a.row_err2 = row_err2; a.row_ref2 = row_ref2;
+    a.n_rows = n_rows; a.d = d; a.mode = mode; a.Kf = (float)K; a.lam = lam; a.seed = seed; a.n_base = n_base;
+    const int dpad32 = (int)round_up(d, kGB);
+    auto smem_for = [&](int nb) {
+        return (size_t)2 * nb * kPathWarps * dpad32 * sizeof(float) + 3 * kGB * 33 * sizeof(double);
+    };
+    // 4 neurons per warp amortise the Gram tiles best; fall back to 2 / 1 when the w,q rows of the CTA's
+    // neurons would not fit in shared memory (large d) or when there are too few neurons to fill the GPU
+    // (measured r01, 2048 x 1024: 1 neuron per warp / 256 CTAs 5.2 ms, 2 per warp / 128 CTAs 6.1 ms)
+    int nb = 4;
+    while (nb > 1 && (smem_for(nb) > 200 * 1024 || ceil_div(n_rows, nb * kPathWarps) < 148)) nb >>= 1;
+    const size_t smem = smem_for(nb);
+    GPFQ_REQUIRE(smem <= 227 * 1024, "gpfq_solve_f32: Gram solver supports d <= %d (got %d)", kGramMaxD, d);
+    const void* fn = nb == 4 ? (const void*)gram_path_kernel<4> : nb == 2 ? (const void*)gram_path_kernel<2>
+                                                                             : (const void*)gram_path_kernel<1>;
+    if (int rc = ensure_dynamic_smem(fn, smem)) return rc;
+    const unsigned grid = (unsigned)ceil_div(n_rows, nb * kPathWarps);
+    if (nb == 4) gram_path_kernel<4><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
+    else if (nb == 2) gram_path_kernel<2><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
+    else gram_path_kernel<1><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+
 int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m,
                int n_rows, const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q,
                int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes,
@@ -375,30 +407,8 @@ int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const fl
                                   workspace_bytes - p.off_scratch, stream))
             return rc;
     }
-    GramPathArgs a{};
-    a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d;
-    a.GT = GT; a.H = H; a.A = A; a.ldg = p.dpad; a.delta = delta; a.row_err2 = row_err2; a.row_ref2 = row_ref2;
-    a.n_rows = n_rows; a.d = d; a.mode = mode; a.Kf = (float)K; a.lam = lam; a.seed = seed; a.n_base = n_base;
-    const int dpad32 = (int)round_up(d, kGB);
-    auto smem_for = [&](int nb) {
-        return (size_t)2 * nb * kPathWarps * dpad32 * sizeof(float) + 3 * kGB * 33 * sizeof(double);
-    };
-    // 4 neurons per warp amortise the Gram tiles best; fall back to 2 / 1 when the w,q rows of the CTA's
-    // neurons would not fit in shared memory (large d) or when there are too few neurons to fill the GPU
-    // (measured r01, 2048 x 1024: 1 neuron per warp / 256 CTAs 5.2 ms, 2 per warp / 128 CTAs 6.1 ms)
-    int nb = 4;
-    while (nb > 1 && (smem_for(nb) > 200 * 1024 || ceil_div(n_rows, nb * kPathWarps) < 148)) nb >>= 1;
-    const size_t smem = smem_for(nb);
-    GPFQ_REQUIRE(smem <= 227 * 1024, "gpfq_solve_f32: Gram solver supports d <= %d (got %d)", kGramMaxD, d);
-    const void* fn = nb == 4 ? (const void*)gram_path_kernel<4> : nb == 2 ? (const void*)gram_path_kernel<2>
-                                                                             : (const void*)gram_path_kernel<1>;
-    if (int rc = ensure_dynamic_smem(fn, smem)) return rc;
-    const unsigned grid = (unsigned)ceil_div(n_rows, nb * kPathWarps);
-    if (nb == 4) gram_path_kernel<4><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
-    else if (nb == 2) gram_path_kernel<2><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
-    else gram_path_kernel<1><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
-    GPFQ_CHECK_LAUNCH();
-    return 0;
+    return gram_path(W, ldw, d, n_rows, GT, H, A, p.dpad, delta, K, mode, lam, seed, n_base, Q, ldq, levels, row_err2,
+                     row_ref2, stream);
 }
 
 }  // namespace gpfq

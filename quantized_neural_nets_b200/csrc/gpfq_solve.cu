@@ -12,6 +12,9 @@ int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const fl
                int n_rows, const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q,
                int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes,
                cudaStream_t stream);
+int gram_path(const float* W, int64_t ldw, int d, int n_rows, const double* GT, const double* H, const double* A,
+              int64_t ldg, const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q,
+              int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, cudaStream_t stream);
 int gram_matrices(int solver, const float* X, const float* Xq, int64_t ldx, int d, int m, double* GT, double* H,
                   double* A, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 }  // namespace gpfq
@@ -34,6 +37,20 @@ int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, 
     GPFQ_REQUIRE(X && Xq && GT && H && A && workspace, "gpfq_gram_f32: null pointer");
     GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "gpfq_gram_f32: workspace must be 256-byte aligned");
     return gram_matrices(solver, X, Xq, ldx, d, m, GT, H, A, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gpfq_gram_path_f32(const float* W, int64_t ldw, int32_t N, int32_t d, int32_t n0, int32_t n1, const double* GT,
+                       const double* H, const double* A, int64_t ldg, const float* delta, int32_t K, int32_t mode, float lam,
+                       uint64_t seed, float* Q, int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2,
+                       void* stream) {
+    GPFQ_REQUIRE(N >= 0 && d > 0 && 0 <= n0 && n0 <= n1 && n1 <= N, "gpfq_gram_path_f32: bad shape or neuron range");
+    GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_STOCHASTIC && K >= 1 && K <= 127, "gpfq_gram_path_f32: bad mode or K");
+    GPFQ_REQUIRE(ldw >= d && ldq >= d && ldg >= (d + 31) / 32 * 32, "gpfq_gram_path_f32: leading dimension too small");
+    if (n0 == n1) return 0;
+    GPFQ_REQUIRE(W && GT && H && A && delta && Q, "gpfq_gram_path_f32: null pointer");
+    return gram_path(W + (int64_t)n0 * ldw, ldw, d, n1 - n0, GT, H, A, ldg, delta, K, mode, lam, seed, n0,
+                     Q + (int64_t)n0 * ldq, ldq, levels ? levels + (int64_t)n0 * d : nullptr, row_err2, row_ref2,
+                     (cudaStream_t)stream);
 }
 
 int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int32_t N,

@@ -20,11 +20,17 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr, require_cuda
 from .sharding import neuron_slice, gather_layer, gather_inputs, world_and_rank
-from .step_algorithm import quantize_layer_impl, reduce_errors, row_radius, delta_from_radii
+from .step_algorithm import (quantize_layer_impl, reduce_errors, row_radius, delta_from_radii,
+                             gram_reduce_eligible)
 from .utils import InterruptException, extract_layers
 
 LINEAR_MODULE_TYPE = nn.Linear
 CONV2D_MODULE_TYPE = nn.Conv2d
+
+
+def _default_group():
+    import torch.distributed as dist
+    return dist.group.WORLD
 
 
 def _pair(v):
@@ -120,7 +126,7 @@ class QuantizeNeuralNet:
                  mlp_percentile, cnn_percentile,
                  reg, lamb, retain_rate, stochastic_quantization, device,
                  *, process_group=None, solver=None, verbose=False, profile=False, shard_forward=False,
-                 overlap_solve=False):
+                 overlap_solve=False, gram_reduce=True):
         self.network_name = network_name
         self.analog_network = network_to_quantize          # not copied, as in the reference (:82)
         self.batch_size = batch_size
@@ -159,6 +165,11 @@ class QuantizeNeuralNet:
         # for the solve.  Measured on 1 x B200 (r01): no gain -- the fp32 forward saturates the SMs, so the
         # solver's kernels only time-slice with cuDNN's (3.90 s vs 3.80 s per ResNet-50 step); off by default.
         self.overlap_solve = overlap_solve
+        # With shard_forward: for the layers the Gram solver is best at, do not all-gather the layer inputs but
+        # all-reduce the d x d Gram matrices of each rank's own calibration rows (24 d^2 instead of 8 m d bytes,
+        # and the Gram formation is divided by the world size).
+        self.gram_reduce = gram_reduce
+        self._rows_split = False
         self.verbose = verbose
         self.layer_log = []      # (layer_idx, quantize_error tensor, relative_quantize_error tensor)
         self.profile = profile   # record CUDA-event timings of the phases of every layer
@@ -244,7 +255,9 @@ class QuantizeNeuralNet:
                 Q, err2, ref2 = quantize_layer_impl(W, X, Xq, m, step, K, pct, self.reg, self.lamb, groups,
                                                     self.stochastic_quantization, self.device,
                                                     neuron_range=(n0, n1), solver=self.solver, return_partials=True,
-                                                    delta=delta)
+                                                    delta=delta,
+                                                    rows_split_over=((self.process_group or _default_group())
+                                                                     if self._rows_split else None))
             done = torch.cuda.Event()
             done.record(stream)
         return layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side
@@ -344,7 +357,17 @@ class QuantizeNeuralNet:
         layer_idx, save_input, images, sharded = capture
         self._run_to_hook('forward_quantized', self.quantized_network, self.quantized_network_layers, layer_idx,
                           save_input, images)
+        self._rows_split = False
         if sharded:
+            layer = self.analog_network_layers[layer_idx]
+            world, _ = world_and_rank(self.process_group)
+            N = layer.weight.shape[0]
+            d = layer.weight[0].numel()
+            m_total = save_input.inputs[0].shape[0] * world
+            if self.gram_reduce and getattr(layer, 'groups', 1) == 1 and gram_reduce_eligible(N, d, m_total) \
+                    and not self.stochastic_quantization:
+                self._rows_split = True          # the solve exchanges Gram matrices instead (see _launch_solve)
+                return save_input.inputs[0], save_input.inputs[1]
             with self._Phase(self, layer_idx, 'gather_inputs'):
                 return gather_inputs(save_input.inputs[0], save_input.inputs[1], self.process_group)
         return save_input.inputs[0], save_input.inputs[1]

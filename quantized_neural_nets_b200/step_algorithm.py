@@ -154,6 +154,38 @@ def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, s
 AUTO_GRAM_CANDIDATES = [_lib.SOLVER_GRAM, _lib.SOLVER_GRAM_F64]
 
 
+def gram_reduce_eligible(N, d, m_total):
+    """Layers for which, with the calibration rows split over ranks, summing d x d Gram matrices over the ranks
+    beats all-gathering the (m x d) inputs: the Gram solver is the faster one on a single GPU for these shapes
+    (profiles/r01_bench_auto_solver_n1.json) and the exchanged volume drops from 8*m*d to 24*d*d bytes."""
+    return m_total >= 2 * d and (d <= 512 or (d <= 1024 and N >= 2 * d))
+
+
+def solve_rows_gram_reduced(W, Xfm_local, Xqfm_local, ldx, m_local, delta, K, mode, lamb, Q, n0, n1, group, seed=0):
+    """Gram solver over calibration rows that are SPLIT over the ranks of ``group``: every rank forms the Gram
+    matrices of its own rows on the tensor cores, one all-reduce (fp64, 3*d*d values) sums them, then the rank
+    runs the recurrence for its neuron slice.  Returns (row_err2, row_ref2) for neurons [n0, n1)."""
+    import torch.distributed as dist
+    N, d = W.shape
+    dev = W.device
+    ldg = (d + 63) // 64 * 64
+    grams = torch.empty((3, ldg, ldg), dtype=torch.float64, device=dev)
+    nbytes = lib.gpfq_workspace_bytes(_lib.SOLVER_GRAM, 1, d, m_local)
+    if nbytes == 0:
+        raise RuntimeError(f"libgpfq_b200: the Gram solver does not support d={d}")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.gpfq_gram_f32(_lib.SOLVER_GRAM, ptr(Xfm_local), ptr(Xqfm_local), ldx, d, m_local, ptr(grams[0]),
+                            ptr(grams[1]), ptr(grams[2]), ptr(ws), nbytes, stream_ptr()))
+    dist.all_reduce(grams, group=group)
+    rows = n1 - n0
+    e2 = torch.zeros(rows, dtype=torch.float64, device=dev)
+    r2 = torch.zeros(rows, dtype=torch.float64, device=dev)
+    check(lib.gpfq_gram_path_f32(ptr(W), W.stride(0), N, d, n0, n1, ptr(grams[0]), ptr(grams[1]), ptr(grams[2]), ldg,
+                                 ptr(delta), int(K), mode, float(lamb), int(seed), ptr(Q), Q.stride(0), None, ptr(e2),
+                                 ptr(r2), stream_ptr()))
+    return e2, r2
+
+
 class StepAlgorithm:
     # ------------------------------------------------------------------ alphabet maps
     def _msq(step_size, x, boundary_idx, lamb):
@@ -263,7 +295,7 @@ def mode_of(reg, stochastic_quantization):
 
 def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, lamb, groups,
                         stochastic_quantization, device, want_adder=False, neuron_range=None, levels=None,
-                        solver=None, return_partials=False, delta=None, seed=None):
+                        solver=None, return_partials=False, delta=None, seed=None, rows_split_over=None):
     """Shared body of ``StepAlgorithm._quantize_layer`` and of the sharded orchestrator.
 
     neuron_range=(n0, n1) restricts the solve to a contiguous slice of output neurons (rows
@@ -293,6 +325,14 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
     err2 = torch.zeros(N, dtype=torch.float64, device=dev)
     ref2 = torch.zeros(N, dtype=torch.float64, device=dev)
     adder = None
+    if rows_split_over is not None:
+        # X / Xq hold only this rank's calibration rows (m of them); the ranks of the group exchange Gram matrices
+        if groups != 1 or want_adder:
+            raise ValueError("rows_split_over supports ungrouped layers without the adder output")
+        e2, r2 = solve_rows_gram_reduced(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Q, n0, n1,
+                                         rows_split_over, seed)
+        err2[n0:n1], ref2[n0:n1] = e2, r2
+        return (Q, err2, ref2) if return_partials else (Q,) + reduce_errors(err2, ref2, groups, None)
     n_per_group = N // groups
     for g in range(groups):
         g0, g1 = max(n0, g * n_per_group), min(n1, (g + 1) * n_per_group)

@@ -50,7 +50,8 @@ def same_on_all_ranks(ws):
 
 w_single, rel_single = run(process_group=False)
 w_shard, rel_shard = run()
-w_fwd, rel_fwd = run(shard_forward=True)
+w_fwd, rel_fwd = run(shard_forward=True, gram_reduce=False)
+w_red, rel_red = run(shard_forward=True, gram_reduce=True)
 ok1 = all(torch.equal(a, b) for a, b in zip(w_single, w_shard)) and same_on_all_ranks(w_shard)
 ok2 = same_on_all_ranks(w_fwd)
 agree = [float((a == b).float().mean()) for a, b in zip(w_single, w_fwd)]
@@ -58,6 +59,13 @@ agree = [float((a == b).float().mean()) for a, b in zip(w_single, w_fwd)]
 # see activations that differ by cuDNN batch-size effects and by upstream tie flips, which GPFQ amplifies, so
 # only the relative errors are expected to stay close there
 ok3 = agree[0] == 1.0 and max(abs(a - b) / a for a, b in zip(rel_single, rel_fwd)) < 5e-2
+# 3. same, but the Gram-eligible layers all-reduce d x d Gram matrices instead of all-gathering their inputs
+ok4 = same_on_all_ranks(w_red)
+agree_red = [float((a == b).float().mean()) for a, b in zip(w_single, w_red)]
+ok5 = agree_red[0] >= 0.999 and max(abs(a - b) / a for a, b in zip(rel_single, rel_red)) < 5e-2
+if rank == 0:
+    print(f"gram-reduce identical on all ranks: {ok4}; per-layer agreement with unsharded: {[round(a, 4) for a in agree_red]}")
+    print("per-layer rel err (gram-reduce):", [round(a, 5) for a in rel_red])
 if rank == 0:
     print(f"world={world} model={model_name} batch={batch}")
     print(f"neuron-sharded == unsharded, identical on all ranks: {ok1}")
@@ -67,4 +75,4 @@ if rank == 0:
     print("per-layer rel err (unsharded):", [round(a, 5) for a in rel_single])
     print("per-layer rel err (sharded fwd):", [round(a, 5) for a in rel_fwd])
 dist.destroy_process_group()
-sys.exit(0 if (ok1 and ok2 and ok3) else 1)
+sys.exit(0 if (ok1 and ok2 and ok3 and ok4 and ok5) else 1)
