@@ -170,6 +170,10 @@ class QuantizeNeuralNet:
         # and the Gram formation is divided by the world size).
         self.gram_reduce = gram_reduce
         self._rows_split = False
+        # host -> device copy of the NEXT layer's batch runs on a copy stream while this layer computes
+        self._copy_stream = None
+        self._prefetched = None      # (device images, ready event, sharded?) of the next layer
+        self._layers_left = 0
         self.verbose = verbose
         self.layer_log = []      # (layer_idx, quantize_error tensor, relative_quantize_error tensor)
         self.profile = profile   # record CUDA-event timings of the phases of every layer
@@ -216,7 +220,9 @@ class QuantizeNeuralNet:
         deltas = self._layer_deltas(layers_to_quantize)
         side = torch.cuda.Stream(device=self.device, priority=-1) if self.overlap_solve else None   # high priority
         pending = None
+        self._layers_left = len(layers_to_quantize)
         for layer_idx in layers_to_quantize:
+            self._layers_left -= 1
             capture = self._begin_capture(layer_idx)          # fresh batch, analog forward        (main stream)
             if pending is not None:
                 self._finish_layer(pending)                   # wait for the solve, gather Q, write it back
@@ -324,9 +330,44 @@ class QuantizeNeuralNet:
             finally:
                 handle.remove()
 
+    def _fetch(self, stream):
+        """Draw the next batch from the loader and enqueue its host -> device copy on ``stream``."""
+        raw_input_data, _ = next(self.data_loader_iter)
+        world, rank = world_and_rank(self.process_group)
+        sharded = self.shard_forward and world > 1
+        shard_range, B = None, raw_input_data.shape[0]
+        if sharded:
+            if B % world != 0:
+                raise ValueError(f"shard_forward needs the batch ({B}) to be a multiple of the world size ({world})")
+            shard_range = (rank * (B // world), (rank + 1) * (B // world))
+            raw_input_data = raw_input_data[shard_range[0]:shard_range[1]]
+        with torch.cuda.stream(stream):
+            images = raw_input_data.to(self.device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        return images, ready, sharded, shard_range, B
+
+    def _next_images(self):
+        """Device images of the layer about to be captured; the copy of the FOLLOWING layer's batch (the loader is
+        consumed one batch per layer, in order, exactly as the reference does) is started on a copy stream so that
+        it overlaps this layer's forward passes and solve."""
+        main = torch.cuda.current_stream(self.device)
+        if self._prefetched is None:
+            images, ready, sharded, shard_range, B = self._fetch(main)
+        else:
+            images, ready, sharded, shard_range, B = self._prefetched
+            self._prefetched = None
+            main.wait_event(ready)
+            images.record_stream(main)
+        if self._layers_left > 0:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._prefetched = self._fetch(self._copy_stream)
+        return images, sharded, shard_range, B
+
     def _begin_capture(self, layer_idx):
         """Draw the layer's batch, copy it to the device and run the ANALOG network up to the layer."""
-        raw_input_data, _ = next(self.data_loader_iter)
+        images, sharded, shard_range, full_batch = self._next_images()
         analog_layer = self.analog_network_layers[layer_idx]
         if type(analog_layer) == LINEAR_MODULE_TYPE:
             save_input = SaveInputMLP()
@@ -337,18 +378,8 @@ class QuantizeNeuralNet:
         else:
             raise TypeError(f'The layer type {type(analog_layer)} is not currently supported')
 
-        world, rank = world_and_rank(self.process_group)
-        sharded = self.shard_forward and world > 1
-        if sharded:
-            B = raw_input_data.shape[0]
-            if B % world != 0:
-                raise ValueError(f"shard_forward needs the batch ({B}) to be a multiple of the world size ({world})")
-            i0, i1 = rank * (B // world), (rank + 1) * (B // world)
-            raw_input_data = raw_input_data[i0:i1]
-            if isinstance(save_input, SaveInputConv2d):
-                save_input.image_range, save_input.full_batch = (i0, i1), B
-        with self._Phase(self, layer_idx, 'h2d'):
-            images = raw_input_data.to(self.device, non_blocking=True)
+        if sharded and isinstance(save_input, SaveInputConv2d):
+            save_input.image_range, save_input.full_batch = shard_range, full_batch
         self._run_to_hook('forward_analog', self.analog_network, self.analog_network_layers, layer_idx, save_input, images)
         return layer_idx, save_input, images, sharded
 
