@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GPFQ_ABI_VERSION 3
+#define GPFQ_ABI_VERSION 4
 
 /* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0'),
  * :7-35 (STOCHASTIC, SGPFQ: stochastic rounding to the two neighbouring grid points, then clipping; the
@@ -44,6 +44,21 @@ const char* gpfq_last_error(void);
  * of step_algorithm.py:38-104 for unit parity.  delta is read from device memory. */
 int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta, int32_t K,
                       int32_t mode, float lam, uint64_t seed, void* stream);
+
+/* Packed low-bit export of a quantized layer (the reference stores fp32 values that lie on the alphabet,
+ * quantize_neural_net.py:163,193; main.py:127-131 saves them as fp32).  A weight is one of the 2K+1 values
+ * delta*{-K..K} (MSQ / SOFT / STOCHASTIC) or of the 2K+3 values {0, +-(lam + k*delta), k = 0..K} (HARD), so it is
+ * stored as a code of gpfq_packed_bits(K, mode) = ceil(log2(count)) bits; 8 consecutive codes occupy that many
+ * bytes, little-endian, so `packed` holds ceil(n/8) * bits bytes.
+ *   gpfq_pack_levels_f32: Q (n fp32 alphabet values) -> packed; *n_off_alphabet (device) receives the number of
+ *     entries that are NOT exactly on the alphabet (they are stored as level 0); 0 means the export is lossless.
+ *   gpfq_unpack_levels_f32: packed -> Q (fp32, bit-identical to what the solver wrote, up to the sign of zero)
+ *     and / or int8 signed level indices (either may be NULL). */
+int32_t gpfq_packed_bits(int32_t K, int32_t mode);
+int gpfq_pack_levels_f32(const float* Q, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
+                         uint8_t* packed, uint32_t* n_off_alphabet, void* stream);
+int gpfq_unpack_levels_f32(const uint8_t* packed, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
+                           float* Q, int8_t* levels, void* stream);
 
 /* (rows x cols, ld_in) row-major  ->  (cols x ld_out) row-major, columns rows..ld_out-1 zeroed.
  * Turns the reference's (m x d) layer input (quantize_neural_net.py:291,347) into feature-major. */

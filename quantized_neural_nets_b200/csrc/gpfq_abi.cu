@@ -128,6 +128,75 @@ __global__ void quantize_kernel(const float* __restrict__ x, float* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Packed low-bit export.  A quantized weight is one of 2K+1 alphabet values (2K+3 for the L0 alphabet, whose
+// level 0 means "pruned"), i.e. a code in [0, 2^nbits) with nbits = ceil(log2(count)); 8 consecutive codes are
+// stored little-endian in nbits bytes.  One thread packs / unpacks one group of 8.
+__device__ __forceinline__ int level_of_value(float q, float delta, int mode, float lam) {
+    if (mode == GPFQ_MODE_HARD) {
+        if (q == 0.f) return 0;
+        const int k = (int)rintf(__fdiv_rn(__fsub_rn(fabsf(q), lam), delta)) + 1;
+        return q > 0.f ? k : -k;
+    }
+    return (int)rintf(__fdiv_rn(q, delta));
+}
+
+// the alphabet value of a level, with the operation order of alphabet_map_t (i.e. of step_algorithm.py:56,78-81,104)
+__device__ __forceinline__ float value_of_level(int lv, float delta, int mode, float lam) {
+    if (lv == 0) return 0.f;
+    const float s = lv > 0 ? 1.f : -1.f;
+    const float k = fabsf((float)lv);
+    if (mode == GPFQ_MODE_HARD) return __fmul_rn(s, __fadd_rn(lam, __fmul_rn(delta, k - 1.f)));
+    return __fmul_rn(__fmul_rn(s, delta), k);
+}
+
+__global__ void pack_levels_kernel(const float* __restrict__ q, int64_t n, const float* __restrict__ delta_p, int offset,
+                                   int nbits, int mode, float lam, uint8_t* __restrict__ out,
+                                   unsigned int* __restrict__ bad) {
+    const float delta = *delta_p;
+    const int64_t groups = (n + 7) / 8;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long word = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t e = g * 8 + i;
+            int code = offset;                                   // padding encodes level 0
+            if (e < n) {
+                const float v = q[e];
+                const int lv = level_of_value(v, delta, mode, lam);
+                code = lv + offset;
+                // not on the alphabet (or outside it): reported, never silently clamped
+                if (code < 0 || code >= (1 << nbits) || value_of_level(lv, delta, mode, lam) != v) {
+                    atomicAdd(bad, 1u);
+                    code = offset;
+                }
+            }
+            word |= (unsigned long long)code << (i * nbits);
+        }
+        for (int b = 0; b < nbits; ++b) out[g * nbits + b] = (uint8_t)(word >> (8 * b));
+    }
+}
+
+__global__ void unpack_levels_kernel(const uint8_t* __restrict__ in, int64_t n, const float* __restrict__ delta_p,
+                                     int offset, int nbits, int mode, float lam, float* __restrict__ q,
+                                     int8_t* __restrict__ levels) {
+    const float delta = *delta_p;
+    const int64_t groups = (n + 7) / 8;
+    const unsigned mask = (1u << nbits) - 1u;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long word = 0;
+        for (int b = 0; b < nbits; ++b) word |= (unsigned long long)in[g * nbits + b] << (8 * b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t e = g * 8 + i;
+            if (e >= n) break;
+            const int lv = (int)((word >> (i * nbits)) & mask) - offset;
+            if (q) q[e] = value_of_level(lv, delta, mode, lam);
+            if (levels) levels[e] = (int8_t)lv;
+        }
+    }
+}
+
 // (rows x cols) -> (cols x ld_out); pad columns rows..ld_out-1 are zero-filled.
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
                                  float* __restrict__ out, int64_t ld_out) {
@@ -229,6 +298,50 @@ int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta,
     int blocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
     quantize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n, delta, (float)K, mode, lam,
                                                               (unsigned long long)seed);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+static int level_layout(int32_t K, int32_t mode, int* offset, int* nbits) {
+    const int top = (mode == GPFQ_MODE_HARD) ? K + 1 : K;       // levels are -top .. top
+    int b = 1;
+    while ((1 << b) < 2 * top + 1) ++b;
+    *offset = top;
+    *nbits = b;
+    return 0;
+}
+
+int32_t gpfq_packed_bits(int32_t K, int32_t mode) {
+    if (K < 1 || K > 126 || mode < 0 || mode > 3) return 0;
+    int offset, nbits;
+    level_layout(K, mode, &offset, &nbits);
+    return nbits;
+}
+
+int gpfq_pack_levels_f32(const float* Q, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
+                         uint8_t* packed, uint32_t* n_off_alphabet, void* stream) {
+    GPFQ_REQUIRE(n >= 0 && K >= 1 && K <= 126 && mode >= 0 && mode <= 3, "gpfq_pack_levels_f32: bad size/K/mode");
+    GPFQ_REQUIRE(n_off_alphabet != nullptr, "gpfq_pack_levels_f32: n_off_alphabet is required");
+    GPFQ_CUDA_TRY(cudaMemsetAsync(n_off_alphabet, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    if (n == 0) return 0;
+    int offset, nbits;
+    level_layout(K, mode, &offset, &nbits);
+    const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(n, 8), 256), 148 * 8);
+    pack_levels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Q, n, delta, offset, nbits, mode, lam, packed,
+                                                                 n_off_alphabet);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int gpfq_unpack_levels_f32(const uint8_t* packed, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
+                           float* Q, int8_t* levels, void* stream) {
+    GPFQ_REQUIRE(n >= 0 && K >= 1 && K <= 126 && mode >= 0 && mode <= 3, "gpfq_unpack_levels_f32: bad size/K/mode");
+    GPFQ_REQUIRE(Q != nullptr || levels != nullptr, "gpfq_unpack_levels_f32: no output requested");
+    if (n == 0) return 0;
+    int offset, nbits;
+    level_layout(K, mode, &offset, &nbits);
+    const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(n, 8), 256), 148 * 8);
+    unpack_levels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(packed, n, delta, offset, nbits, mode, lam, Q, levels);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

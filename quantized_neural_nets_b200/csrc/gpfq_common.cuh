@@ -202,6 +202,22 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
+// Thread-block clusters: distributed shared memory stores and the cluster-wide barrier.
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem_ptr)), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_dsmem_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_dsmem_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {     // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // Programmatic dependent launch: a kernel launched with launch_pdl() may start while its predecessor in the
 // stream is still running; pdl_wait() blocks until that predecessor has completed and its writes are visible,
 // pdl_trigger() lets the successor start launching.  Without the launch attribute both are no-ops.

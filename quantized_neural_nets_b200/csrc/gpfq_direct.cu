@@ -21,6 +21,7 @@
 //
 // U lives in a solver-private tiled layout  U[j/4][Npad][4]  so that a warp whose lanes own 32
 // consecutive neurons reads/writes 512 contiguous bytes per column quad.
+#include <cstdio>
 #include <algorithm>
 #include <cstdlib>
 
@@ -38,10 +39,14 @@ constexpr int kStageFloats = 3 * kB * kJS;       // x_prev | xq_prev | xq_next
 constexpr int kRedStride = kB + 1;
 constexpr int kMaxTJ = 4096;      // keeps every fp32 accumulation chain <= 512 terms
 
+constexpr int kRJSHost = 64;   // = kRJS (columns per TMA stage of the resident kernel)
+static size_t resident_smem_host(int64_t mc, int slots, int TN, int cluster);
+static int resident_max_clusters(int TN, int CS, size_t smem);
+
 struct DirectPlan {
     int R, TN, n_tiles, TJ, j_tiles, nblk, gram_slices, gram_slice_len;
     int pR, p_n_tiles, pTJ, p_j_tiles, use_persistent;     // single-launch variant
-    int use_resident;                                       // U resident in shared memory (small m)
+    int use_resident, r_cluster, r_TN, r_mpad;              // U resident in shared memory (+ cluster split of m)
     int64_t Npad, mpad;
     size_t off_U, off_G, off_H, off_norm, off_gpart, off_part, off_epart, off_sync, total;
 };
@@ -53,7 +58,7 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     p.nblk = (int)ceil_div(d, kB);
     const int stages = (int)(p.mpad / kJS);
     const int min_jt = (int)ceil_div(p.mpad, kMaxTJ);
-    static const int force_r = getenv("GPFQ_FORCE_R") ? atoi(getenv("GPFQ_FORCE_R")) : 0;   // tuning aid
+    const int force_r = getenv("GPFQ_FORCE_R") ? atoi(getenv("GPFQ_FORCE_R")) : 0;   // tuning aid
     // Pick (R, j_tiles) with a small cost model: CTAs run in waves of 148 x (CTAs per SM); a CTA costs a fixed
     // start-up/teardown (barriers, first TMA and U loads, cross-warp combine) plus its stages; lanes of padded
     // neurons are wasted work.  Measured issue efficiencies: R=4 0.63, R=2 0.50 (2 CTAs/SM), R=1 0.40.
@@ -112,17 +117,49 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     // all SMs.  Kept for GPFQ_PERSISTENT=1 experiments; not selected by default.
     p.use_persistent = (force_p >= 0) ? force_p : 0;
     (void)pbest;
-    // Resident variant (one launch, U in shared memory, no cross-CTA traffic): per block one CTA spends the
-    // fp32 work of its 32 x m tile plus a ~6 us reduce + recurrence chain; the multi-launch path spends its
-    // sweep + two launches (~12 us of launch latency and gaps) + the recurrence kernel (~5 us).
-    static const int force_res = getenv("GPFQ_RESIDENT") ? atoi(getenv("GPFQ_RESIDENT")) : -1;   // tuning aid
+    // Resident variant (one launch per layer, U in shared memory).  A cluster of CS CTAs shares TN neurons and
+    // splits the columns.  Fitted to B200 measurements (tools/resident_sweep.py, r01), per
+    // 32-feature block:
+    //   resident     14 us chain (reduce, DSMEM hand-off, recurrence, barriers) + 1.46 ns per (neuron, column) of
+    //                ONE CTA's TN x (m/CS) tile (45 % fp32 issue efficiency), times the number of waves -- CTAs
+    //                beyond one per SM, or clusters beyond what the GPCs can co-schedule, run as a further wave
+    //                (two CTAs sharing an SM measured no better than two waves);
+    //   multi-launch 26 us of launches, gaps and fixed kernel costs + the layer's work spread over all SMs at
+    //                ~50 % issue efficiency.
+    const int force_res = getenv("GPFQ_RESIDENT") ? atoi(getenv("GPFQ_RESIDENT")) : -1;   // tuning aids
+    const int force_tn = getenv("GPFQ_RESIDENT_TN") ? atoi(getenv("GPFQ_RESIDENT_TN")) : 0;
+    const int force_cs = getenv("GPFQ_RESIDENT_CLUSTER") ? atoi(getenv("GPFQ_RESIDENT_CLUSTER")) : 0;
     {
-        // measured (r01): resident 30 us per block at m = 256 whatever N, 52 us at m = 768; multi-launch 43 us per
-        // block for (4096, ., 256), 32 us for (1000, 2048, 256), 31 us for (512, 4608, 768)
-        const int64_t mp64 = round_up(std::max(m, 1), 64);
-        const bool fits = mp64 <= 768;
-        const bool wins = mp64 <= 256 && n_rows >= 2048 && p.nblk >= 2;
-        p.use_resident = fits && ((force_res >= 0) ? force_res : wins);
+        const double multi_us = 26.0 + (double)n_rows * (double)p.mpad * (5.0 * kB) / (148.0 * 128.0 * 1.9e3 * 0.5);
+        double rbest = 1e300;
+        p.use_resident = 0;
+        for (int CS : {1, 2, 4, 8}) {
+            if (force_cs && CS != force_cs) continue;
+            for (int TN : {32, 16}) {
+                if (force_tn && TN != force_tn) continue;
+                const int64_t mp = round_up(std::max(m, 1), (int64_t)kRJSHost * CS);
+                const int64_t mc = mp / CS;
+                const size_t smem = resident_smem_host(mc, 2, TN, CS);
+                if (smem > 225 * 1024) continue;
+                const int64_t clusters = ceil_div(n_rows, TN);
+                const int64_t conc = std::max(1, std::min(resident_max_clusters(TN, CS, smem), 148 / CS));
+                const double waves = (double)ceil_div(clusters, conc);
+                const double cost = waves * (14.0 + 1.46e-3 * (double)TN * (double)mc);
+                if (cost < rbest) {
+                    rbest = cost;
+                    p.r_cluster = CS;
+                    p.r_TN = TN;
+                    p.r_mpad = (int)mp;
+                }
+            }
+        }
+        const bool fits = rbest < 1e299;
+        p.use_resident = fits && ((force_res >= 0) ? force_res : (p.nblk >= 2 && rbest < 0.93 * multi_us));
+        if (getenv("GPFQ_DEBUG_PLAN"))
+            fprintf(stderr, "[gpfq plan] %d x %d x %d: multi %.1f us/block, resident %.1f us/block (cluster %d, TN %d, "
+                    "max clusters %d) -> %s\n", n_rows, d, m, multi_us, rbest, p.r_cluster, p.r_TN,
+                    fits ? resident_max_clusters(p.r_TN, p.r_cluster, resident_smem_host(p.r_mpad / p.r_cluster, 2, p.r_TN, p.r_cluster)) : 0,
+                    p.use_resident ? "resident" : "multi-launch");
     }
     // block-Gram kernel: split the m-long dot products into slices so the grid fills the GPU
     int gs = std::max(1, std::min<int>((int)ceil_div(m, 256), (int)ceil_div(2 * 148, p.nblk)));
@@ -134,7 +171,7 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
         off += (bytes + 255) & ~(size_t)255;
         return o;
     };
-    p.off_U = take((size_t)p.mpad * p.Npad * sizeof(float));
+    p.off_U = take((size_t)std::max<int64_t>(p.mpad, p.use_resident ? p.r_mpad : 0) * p.Npad * sizeof(float));
     p.off_G = take((size_t)p.nblk * kB * kB * sizeof(double));
     p.off_H = take((size_t)p.nblk * kB * kB * sizeof(double));
     p.off_norm = take((size_t)p.nblk * kB * sizeof(float));
@@ -918,7 +955,7 @@ struct ResidentArgs {
     float* U;           // tiled global U, written once at the end when store_u
     int64_t Npad;
     int n_rows, d, nblk, mpad, mode, store_u, slots;   // slots = depth of the TMA ring (2..4)
-    int n_base;
+    int n_base, cluster;                               // cluster = CTAs per thread-block cluster (1 = none)
     unsigned long long seed;
     float Kf, lam;
 };
@@ -928,8 +965,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// TN = neurons per CTA: 32 (lane = neuron) or 16 (lane = neuron + 16 * column half; two CTAs share an SM so
-// that one CTA's recurrence overlaps the other's arithmetic).
+// TN = neurons per CTA: 32 (lane = neuron) or 16 (lane = neuron + 16 * column half).
+// a.cluster = CTAs per thread-block cluster (1, 2, 4, 8).  With a cluster, its CTAs share the TN neurons and
+// split the calibration columns: every CTA keeps its own column slice of U in shared memory, the per-block
+// partial dot products are written into the leader CTA's shared memory over DSMEM, the leader runs the block's
+// recurrence and broadcasts q back over DSMEM; two cluster barriers per 32-feature block replace two kernel
+// launches and two trips through global memory.  This is what lets layers with FEW neurons use many SMs.
 template <int TN, int MODE>
 __global__ void __launch_bounds__(kThreads, TN == 32 ? 1 : 2)
 resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXq,
@@ -946,12 +987,18 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     float* qsm = wsm + 2 * kB * TN;                                            // [kB/4][TN] float4
     float* ns = qsm + kB * TN;                                                 // [kB]
     float* red = ns + kB;                                                      // [kWarps][TN][17]
-    float* Us = red + kWarps * TN * 17;                                        // [mpad/4][TN] float4
+    const int CS = a.cluster;
+    double* slots64 = reinterpret_cast<double*>(red + kWarps * TN * 17);       // [CS][TN][kB + 1] (cluster only)
+    float* Us = reinterpret_cast<float*>(slots64 + (CS > 1 ? CS * TN * (kB + 1) : 0));   // [mc/4][TN] float4
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nl_lane = lane % TN, ch = lane / TN;      // this lane's neuron and column half
-    const int row0 = blockIdx.x * TN;
-    const int nst = a.mpad / kRJS;
+    const int crank = (int)(blockIdx.x % CS);           // == %cluster_ctarank for cluster dims (CS, 1, 1)
+    const bool leader = crank == 0;
+    const int row0 = (int)(blockIdx.x / CS) * TN;
+    const int mc = a.mpad / CS;                         // this CTA's calibration columns [col0, col0 + mc)
+    const int col0 = crank * mc;
+    const int nst = mc / kRJS;
     const int total_stages = a.nblk * nst;
     const float delta = *a.delta;
 
@@ -959,7 +1006,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int i = 0; i < S; ++i) mbar_init(&bars[i], 1);
         fence_barrier_init();
     }
-    for (int e = tid; e < a.mpad * TN; e += kThreads) Us[e] = 0.f;
+    for (int e = tid; e < mc * TN; e += kThreads) Us[e] = 0.f;
     for (int e = tid; e < 4 * kB * kB; e += kThreads) Gs[e] = 0.0;            // Gs and Hs incl. their zero padding
     __syncthreads();
 
@@ -969,9 +1016,9 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         float* buf = stages + (g % S) * kRStageFloats;
         uint64_t* bar = &bars[g % S];
         mbar_expect_tx(bar, (uint32_t)((2 + (nxt ? 1 : 0)) * kB * kRJS * sizeof(float)));
-        tma_load_2d(buf, &tmX, st * kRJS, k * kB, bar);
-        tma_load_2d(buf + kB * kRJS, &tmXq, st * kRJS, k * kB, bar);
-        if (nxt) tma_load_2d(buf + 2 * kB * kRJS, &tmXq, st * kRJS, (k + 1) * kB, bar);
+        tma_load_2d(buf, &tmX, col0 + st * kRJS, k * kB, bar);
+        tma_load_2d(buf + kB * kRJS, &tmXq, col0 + st * kRJS, k * kB, bar);
+        if (nxt) tma_load_2d(buf + 2 * kB * kRJS, &tmXq, col0 + st * kRJS, (k + 1) * kB, bar);
     };
     if (tid == 0)
         for (int g = 0; g < S - 1 && g < total_stages; ++g) issue(g);     // the ring runs S-1 stages ahead
@@ -994,6 +1041,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
     };
     auto stage_gram = [&](int k) {
+        if (!leader) return;                                  // only the leader runs the recurrence
         const double* g = a.G + (size_t)k * kB * kB;
         const double* h = a.H + (size_t)k * kB * kB;
         for (int e = tid; e < kB * kB / 2; e += kThreads) {     // 16 bytes = 2 doubles per copy
@@ -1012,7 +1060,27 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int t0 = k * kB;
         const int bvalid = min(kB, a.d - t0);
         const float* wblk = wsm + (k & 1) * kB * TN;
-        if (warp == 0 && lane < TN) {
+        if (CS > 1) {
+            if (have_p) {
+                // every CTA hands its partial projections to the leader (slot = its rank) ...
+                const uint32_t dst = dsmem_addr(slots64 + (size_t)crank * TN * (kB + 1), 0);
+                for (int e = tid; e < TN * kB; e += kThreads) {
+                    const int n = e / kB, sft = e % kB;
+                    st_dsmem_f64(dst + (uint32_t)((n * (kB + 1) + sft) * sizeof(double)), P64[n * (kB + 1) + sft]);
+                }
+            }
+            cluster_sync_all();
+            if (leader && have_p) {                           // ... which sums them in rank order
+                for (int e = tid; e < TN * kB; e += kThreads) {
+                    const int n = e / kB, sft = e % kB;
+                    double acc = 0.0;
+                    for (int r = 0; r < CS; ++r) acc += slots64[((size_t)r * TN + n) * (kB + 1) + sft];
+                    P64[n * (kB + 1) + sft] = acc;
+                }
+            }
+            __syncthreads();
+        }
+        if (leader && warp == 0 && lane < TN) {
             const int nl = lane;
             double p[kB];
 #pragma unroll
@@ -1037,11 +1105,18 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             for (int t = bvalid; t < kB; ++t) qsm[((t >> 2) * TN + nl) * 4 + (t & 3)] = 0.f;
         }
         __syncthreads();
-        for (int e = tid; e < TN * kB; e += kThreads) {       // coalesced copy of the block's q to global Q
-            const int nl = e / kB, t = e % kB;
-            if (row0 + nl < a.n_rows && t0 + t < a.d)
-                a.Q[(int64_t)(row0 + nl) * a.ldq + t0 + t] = qsm[((t >> 2) * TN + nl) * 4 + (t & 3)];
+        if (leader) {
+            for (int e = tid; e < TN * kB; e += kThreads) {   // coalesced copy of the block's q to global Q
+                const int nl = e / kB, t = e % kB;
+                if (row0 + nl < a.n_rows && t0 + t < a.d)
+                    a.Q[(int64_t)(row0 + nl) * a.ldq + t0 + t] = qsm[((t >> 2) * TN + nl) * 4 + (t & 3)];
+            }
+            for (int r = 1; r < CS; ++r) {                    // and q goes to the other CTAs of the cluster
+                const uint32_t dst = dsmem_addr(qsm, (uint32_t)r);
+                for (int e = tid; e < TN * kB; e += kThreads) st_dsmem_f32(dst + (uint32_t)(e * sizeof(float)), qsm[e]);
+            }
         }
+        if (CS > 1) cluster_sync_all();
     };
 
     stage_w(0);
@@ -1078,7 +1153,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const float* sx = buf + jl;
                 const float* sxq = buf + kB * kRJS + jl;
                 const float* sxn = buf + 2 * kB * kRJS + jl;
-                const int uidx = ((st * kRJS + jl) >> 2) * TN + nl_lane;
+                const int uidx = ((st * kRJS + jl) >> 2) * TN + nl_lane;      // local column index
                 float4 u = Us4[uidx];
 #pragma unroll 2
                 for (int g4 = 0; g4 < nb4; ++g4) {
@@ -1154,27 +1229,73 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (CH == 2) esum += __shfl_xor_sync(0xffffffffu, esum, 16);
         if (ch == 0) red2[warp * TN + nl_lane] = esum;
         __syncthreads();
-        if (tid < TN && row0 + tid < a.n_rows) {
-            double acc = 0.0;
+        double acc = 0.0;
+        if (tid < TN) {
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) acc += red2[w * TN + tid];
-            a.row_err2[row0 + tid] = acc;
         }
+        if (CS > 1) {                                         // column slices of the cluster, summed in rank order
+            if (tid < TN) st_dsmem_f64(dsmem_addr(slots64 + crank * TN + tid, 0), acc);
+            cluster_sync_all();
+            if (leader && tid < TN) {
+                acc = 0.0;
+                for (int r = 0; r < CS; ++r) acc += slots64[r * TN + tid];
+            }
+        }
+        if (leader && tid < TN && row0 + tid < a.n_rows) a.row_err2[row0 + tid] = acc;
     }
     if (a.store_u) {
         float4* U4 = reinterpret_cast<float4*>(a.U);
-        for (int e = tid; e < (a.mpad / 4) * TN; e += kThreads) {
+        for (int e = tid; e < (mc / 4) * TN; e += kThreads) {
             const int quad = e / TN, nl = e % TN;
-            U4[(int64_t)quad * a.Npad + row0 + nl] = Us4[e];
+            U4[(int64_t)(col0 / 4 + quad) * a.Npad + row0 + nl] = Us4[e];
         }
     }
+    if (CS > 1) cluster_sync_all();      // no CTA may exit while a peer can still address its shared memory
 }
 
-static size_t resident_smem_bytes(int mpad, int slots, int TN) {
+static size_t resident_smem_host(int64_t mc, int slots, int TN, int cluster) {
+    return 128 + (size_t)slots * (3 * kB * kRJSHost) * sizeof(float) + (size_t)4 * kB * kB * sizeof(double) +
+           (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + kB) * sizeof(float) +
+           (size_t)8 * TN * 17 * sizeof(float) + (cluster > 1 ? (size_t)cluster * TN * (kB + 1) * sizeof(double) : 0) +
+           (size_t)mc * TN * sizeof(float);
+}
+
+// mc = calibration columns held by one CTA (= m_pad / cluster)
+static size_t resident_smem_bytes(int mc, int slots, int TN, int cluster = 1) {
     return 128 + (size_t)slots * kRStageFloats * sizeof(float) + (size_t)2 * kB * kB * sizeof(double) +
            (size_t)2 * kB * kB * sizeof(double) /* zero padding of G, H rows */ +
            (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + kB) * sizeof(float) +
-           (size_t)kWarps * TN * 17 * sizeof(float) + (size_t)mpad * TN * sizeof(float);
+           (size_t)kWarps * TN * 17 * sizeof(float) +
+           (cluster > 1 ? (size_t)cluster * TN * (kB + 1) * sizeof(double) : 0) + (size_t)mc * TN * sizeof(float);
+}
+
+// How many clusters of CS CTAs of the resident kernel the GPU runs at once (the GPCs decide: 148 SMs do not
+// hold 18 clusters of 8).  Asked from the driver once per (TN, CS, one-or-two CTAs per SM); without a device
+// (gpfq_workspace_bytes on a CPU-only host) the values measured on B200 are used.
+static int resident_max_clusters(int TN, int CS, size_t smem) {
+    static int cache[2][4][2];       // 0 = not asked yet
+    const int ti = TN == 16, ci = CS == 1 ? 0 : CS == 2 ? 1 : CS == 4 ? 2 : 3, si = smem <= 113 * 1024;
+    if (cache[ti][ci][si]) return cache[ti][ci][si];
+    static const int fallback[4] = {148, 74, 33, 8};
+    int n = 0;
+    const void* fn = TN == 16 ? (const void*)resident_kernel<16, GPFQ_MODE_MSQ> : (const void*)resident_kernel<32, GPFQ_MODE_MSQ>;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(148 * CS));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (ensure_dynamic_smem(fn, smem) != 0 || cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return fallback[ci];         // not cached: a device may become available later
+    }
+    return cache[ti][ci][si] = n;
 }
 
 template <int R>
@@ -1282,7 +1403,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
     GPFQ_CHECK_LAUNCH();
 
     if (p.use_resident) {
-        const int mp = (int)round_up(m, kRJS);
+        const int mp = p.r_mpad, CS = p.r_cluster, TN = p.r_TN, mc = mp / CS;
         CUtensorMap rX, rXq;
         if (int rc = make_tensor_map_2d(&rX, X, d, m, ldx, kB, kRJS)) return rc;
         if (int rc = make_tensor_map_2d(&rXq, Xq, d, m, ldx, kB, kRJS)) return rc;
@@ -1290,13 +1411,11 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d; a.G = G; a.H = H; a.norm32 = norm32;
         a.delta = delta; a.row_err2 = row_err2; a.U = U; a.Npad = p.Npad; a.n_rows = n_rows; a.d = d; a.nblk = p.nblk;
         a.mpad = mp; a.mode = mode; a.store_u = (U_out != nullptr); a.Kf = (float)K; a.lam = lam;
-        a.seed = seed; a.n_base = n_base;
-        // 16 neurons per CTA when two such CTAs fit on an SM (their recurrences and sweeps then overlap)
-        static const int force_tn = getenv("GPFQ_RESIDENT_TN") ? atoi(getenv("GPFQ_RESIDENT_TN")) : 0;   // tuning aid
-        const int TN = force_tn ? force_tn : (resident_smem_bytes(mp, 2, 16) <= 113 * 1024 ? 16 : 32);
-        a.slots = (TN == 16) ? 2 : 4;
-        while (a.slots > 2 && resident_smem_bytes(mp, a.slots, TN) > 225 * 1024) --a.slots;
-        const size_t smem = resident_smem_bytes(mp, a.slots, TN);
+        a.seed = seed; a.n_base = n_base; a.cluster = CS;
+        a.slots = 4;
+        while (a.slots > 2 && resident_smem_bytes(mc, a.slots, TN, CS) > 225 * 1024) --a.slots;
+        if (resident_smem_bytes(mc, 2, TN, CS) <= 113 * 1024) a.slots = 2;       // keep two CTAs per SM possible
+        const size_t smem = resident_smem_bytes(mc, a.slots, TN, CS);
         typedef void (*ResidentFn)(const CUtensorMap, const CUtensorMap, const ResidentArgs);
         static const ResidentFn table[2][4] = {
             {resident_kernel<32, GPFQ_MODE_MSQ>, resident_kernel<32, GPFQ_MODE_SOFT>, resident_kernel<32, GPFQ_MODE_HARD>,
@@ -1305,11 +1424,23 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
              resident_kernel<16, GPFQ_MODE_STOCHASTIC>}};
         const ResidentFn fn = table[TN == 16][mode];
         if (int rc = ensure_dynamic_smem((const void*)fn, smem)) return rc;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(ceil_div(n_rows, TN) * CS));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = CS > 1 ? 1 : 0;
         profile_mark_begin(stream);
-        fn<<<(unsigned)ceil_div(n_rows, TN), kThreads, smem, stream>>>(rX, rXq, a);
+        GPFQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, rX, rXq, a));
         if (profile_on()) {
             const double nm = (double)n_rows * (double)mp;
-            profile_mark_end(stream, 12.0 * kB * (double)mp * p.nblk * ceil_div(n_rows, 32) + 8.0 * n_rows * (double)d,
+            profile_mark_end(stream, 12.0 * kB * (double)mp * p.nblk * ceil_div(n_rows, TN) + 8.0 * n_rows * (double)d,
                              nm * (4.0 * d + 1.0 * kB * (p.nblk - 1)));
         }
         GPFQ_CHECK_LAUNCH();

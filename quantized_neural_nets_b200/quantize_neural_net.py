@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import lib, check, ptr, stream_ptr, require_cuda
 from .sharding import neuron_slice, gather_layer, gather_inputs, world_and_rank
 from .step_algorithm import (quantize_layer_impl, reduce_errors, row_radius, delta_from_radii,
-                             gram_reduce_eligible)
+                             gram_reduce_eligible, feature_major)
 from .utils import InterruptException, extract_layers
 
 LINEAR_MODULE_TYPE = nn.Linear
@@ -46,8 +46,11 @@ class SaveInputMLP:
     def __call__(self, module, module_in, module_out):
         if len(module_in) != 1:
             raise TypeError('The number of input layer is not equal to one!')
-        self.inputs.append(module_in[0])
+        self.inputs.append(self.capture(module_in[0]))
         raise InterruptException
+
+    def capture(self, x):
+        return x
 
 
 class SaveInputConv2d:
@@ -86,7 +89,12 @@ class SaveInputConv2d:
     def __call__(self, module, module_in, module_out):
         if len(module_in) != 1:
             raise TypeError('The number of input layer is not equal to one!')
-        x = module_in[0]
+        self.inputs.append(self.capture(module_in[0]))
+        raise InterruptException
+
+    def capture(self, x):
+        """The sub-sampled patch matrix of one (B, C, H, W) layer input as an (m x C*kh*kw) view of a
+        feature-major buffer.  The first call draws the patch indices, later calls reuse them."""
         require_cuda(x)
         x = x.contiguous()
         B, C, H, W = x.shape
@@ -111,8 +119,7 @@ class SaveInputConv2d:
         out = torch.empty((feats, ld), dtype=torch.float32, device=x.device)
         check(lib.gpfq_im2col_gather_f32(ptr(x), B, C, H, W, kh, kw, dh, dw, ph, pw, 0, C,
                                          ptr(self._idx_dev), m, ptr(out), ld, stream_ptr()))
-        self.inputs.append(out[:, :m].t())
-        raise InterruptException
+        return out[:, :m].t()
 
 
 class QuantizeNeuralNet:
@@ -126,7 +133,7 @@ class QuantizeNeuralNet:
                  mlp_percentile, cnn_percentile,
                  reg, lamb, retain_rate, stochastic_quantization, device,
                  *, process_group=None, solver=None, verbose=False, profile=False, shard_forward=False,
-                 overlap_solve=False, gram_reduce=True):
+                 overlap_solve=False, gram_reduce=True, calibration='fresh'):
         self.network_name = network_name
         self.analog_network = network_to_quantize          # not copied, as in the reference (:82)
         self.batch_size = batch_size
@@ -170,11 +177,20 @@ class QuantizeNeuralNet:
         # and the Gram formation is divided by the world size).
         self.gram_reduce = gram_reduce
         self._rows_split = False
+        # 'fresh' (reference behaviour, :234): a new loader batch and two forward passes from the image for EVERY
+        # layer, O(L^2) layer evaluations.  'reuse' (SURVEY.md section 8f rank 1): ONE batch calibrates all layers --
+        # one pass of the analog network records every layer's input, then one pass of the quantized network
+        # quantizes each layer when the pass reaches it, O(L) layer evaluations.  'reuse' computes what the
+        # reference computes when its loader yields the same batch for every layer.
+        if calibration not in ('fresh', 'reuse'):
+            raise ValueError(f"calibration must be 'fresh' or 'reuse', not {calibration!r}")
+        self.calibration = calibration
         # host -> device copy of the NEXT layer's batch runs on a copy stream while this layer computes
         self._copy_stream = None
         self._prefetched = None      # (device images, ready event, sharded?) of the next layer
         self._layers_left = 0
         self.verbose = verbose
+        self.layer_deltas = {}
         self.layer_log = []      # (layer_idx, quantize_error tensor, relative_quantize_error tensor)
         self.profile = profile   # record CUDA-event timings of the phases of every layer
         self._marks = []         # (layer_idx, phase, start_event, end_event)
@@ -218,6 +234,10 @@ class QuantizeNeuralNet:
             print(f'Layer indices to quantize {layers_to_quantize}')
             print(f'Total number of layers to quantize {len(layers_to_quantize)}')
         deltas = self._layer_deltas(layers_to_quantize)
+        self.layer_deltas = deltas             # {layer index: alphabet step}; read by export.export_packed
+        if self.calibration == 'reuse':
+            self._quantize_network_reuse(layers_to_quantize, deltas)
+            return self.quantized_network
         side = torch.cuda.Stream(device=self.device, priority=-1) if self.overlap_solve else None   # high priority
         pending = None
         self._layers_left = len(layers_to_quantize)
@@ -232,6 +252,68 @@ class QuantizeNeuralNet:
         if pending is not None:
             self._finish_layer(pending)
         return self.quantized_network
+
+    def _quantize_network_reuse(self, layers_to_quantize, deltas):
+        """calibration='reuse': one batch for all layers, two network passes in total.
+
+        Pass 1 runs the analog network once; a forward pre-hook on every layer to be quantized turns the layer's
+        input into its (sub-sampled) X matrix on the spot.  Pass 2 runs the quantized copy once; when it reaches a
+        layer, the pre-hook builds X~ from the activation that has just been computed by the already-quantized
+        layers before it, solves the layer and installs Q as the module's weight BEFORE the module's own forward
+        executes, so the rest of the pass sees the quantized layer.  Both passes stop at the last layer they need.
+        With a loader that yields the same batch every time this is the reference's computation
+        (quantize_neural_net.py:117-214, :217-274) provided the layers execute in the order extract_layers lists
+        them (true of the torchvision models the reference supports); conv patch indices are drawn when the analog
+        pass reaches the layer."""
+        if not layers_to_quantize:
+            return
+        self._layers_left = 0                      # a single batch: nothing to prefetch
+        images, sharded, shard_range, full_batch = self._next_images()
+        savers, analog_X = {}, {}
+
+        def run(network, layers, hook_of, name):
+            left = set(layers_to_quantize)
+            handles = [layers[i].register_forward_pre_hook(hook_of(i, left)) for i in layers_to_quantize]
+            with torch.no_grad(), self._Phase(self, -1, name):
+                try:
+                    network(images)
+                except InterruptException:
+                    pass
+                finally:
+                    for h in handles:
+                        h.remove()
+            if left:
+                raise RuntimeError(f"layers {sorted(left)} were not reached by the calibration forward pass")
+
+        def analog_hook(i, left):
+            def hook(module, module_in):
+                if len(module_in) != 1:
+                    raise TypeError('The number of input layer is not equal to one!')
+                savers[i] = self._make_saver(self.analog_network_layers[i], sharded, shard_range, full_batch)
+                X = savers[i].capture(module_in[0])
+                if isinstance(savers[i], SaveInputMLP):
+                    X = feature_major(X)[0][:, :X.shape[0]].t()     # a copy: later in-place ops cannot touch it
+                analog_X[i] = X
+                left.discard(i)
+                if not left:
+                    raise InterruptException
+            return hook
+
+        def quantized_hook(i, left):
+            def hook(module, module_in):
+                if len(module_in) != 1:
+                    raise TypeError('The number of input layer is not equal to one!')
+                Xq = savers.pop(i).capture(module_in[0])
+                X, Xq = self._exchange_inputs(i, analog_X.pop(i), Xq, sharded)
+                self._finish_layer(self._launch_solve(i, X, Xq, deltas[i], None))
+                left.discard(i)
+                if not left:
+                    raise InterruptException
+            return hook
+
+        run(self.analog_network, self.analog_network_layers, analog_hook, 'forward_analog')
+        run(self.quantized_network, self.quantized_network_layers, quantized_hook, 'quantized_pass')
+        self.layer_log.sort(key=lambda rec: rec[0])
 
     def _launch_solve(self, layer_idx, X, Xq, delta, side):
         """Enqueue the solve of one layer (on the side stream when overlapping) and return the handle
@@ -365,10 +447,7 @@ class QuantizeNeuralNet:
             self._prefetched = self._fetch(self._copy_stream)
         return images, sharded, shard_range, B
 
-    def _begin_capture(self, layer_idx):
-        """Draw the layer's batch, copy it to the device and run the ANALOG network up to the layer."""
-        images, sharded, shard_range, full_batch = self._next_images()
-        analog_layer = self.analog_network_layers[layer_idx]
+    def _make_saver(self, analog_layer, sharded, shard_range, full_batch):
         if type(analog_layer) == LINEAR_MODULE_TYPE:
             save_input = SaveInputMLP()
         elif type(analog_layer) == CONV2D_MODULE_TYPE:
@@ -377,9 +456,14 @@ class QuantizeNeuralNet:
                                          groups=analog_layer.groups, retain_rate=self.retain_rate)
         else:
             raise TypeError(f'The layer type {type(analog_layer)} is not currently supported')
-
         if sharded and isinstance(save_input, SaveInputConv2d):
             save_input.image_range, save_input.full_batch = shard_range, full_batch
+        return save_input
+
+    def _begin_capture(self, layer_idx):
+        """Draw the layer's batch, copy it to the device and run the ANALOG network up to the layer."""
+        images, sharded, shard_range, full_batch = self._next_images()
+        save_input = self._make_saver(self.analog_network_layers[layer_idx], sharded, shard_range, full_batch)
         self._run_to_hook('forward_analog', self.analog_network, self.analog_network_layers, layer_idx, save_input, images)
         return layer_idx, save_input, images, sharded
 
@@ -388,17 +472,22 @@ class QuantizeNeuralNet:
         layer_idx, save_input, images, sharded = capture
         self._run_to_hook('forward_quantized', self.quantized_network, self.quantized_network_layers, layer_idx,
                           save_input, images)
+        return self._exchange_inputs(layer_idx, save_input.inputs[0], save_input.inputs[1], sharded)
+
+    def _exchange_inputs(self, layer_idx, X, Xq, sharded):
+        """With a sharded calibration forward X / X~ hold this rank's calibration rows: either all-gather them,
+        or leave them split and let the solve all-reduce the layer's Gram matrices instead."""
         self._rows_split = False
         if sharded:
             layer = self.analog_network_layers[layer_idx]
             world, _ = world_and_rank(self.process_group)
             N = layer.weight.shape[0]
             d = layer.weight[0].numel()
-            m_total = save_input.inputs[0].shape[0] * world
+            m_total = X.shape[0] * world
             if self.gram_reduce and getattr(layer, 'groups', 1) == 1 and gram_reduce_eligible(N, d, m_total) \
                     and not self.stochastic_quantization:
                 self._rows_split = True          # the solve exchanges Gram matrices instead (see _launch_solve)
-                return save_input.inputs[0], save_input.inputs[1]
+                return X, Xq
             with self._Phase(self, layer_idx, 'gather_inputs'):
-                return gather_inputs(save_input.inputs[0], save_input.inputs[1], self.process_group)
-        return save_input.inputs[0], save_input.inputs[1]
+                return gather_inputs(X, Xq, self.process_group)
+        return X, Xq

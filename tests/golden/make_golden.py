@@ -143,6 +143,26 @@ def tiny_network():
     save("tiny_network.npz", **out)
 
 
+def model_utils():
+    """utils.fusion_layers_inplace (utils.py:96-130), eval_sparsity (:133-159), test_accuracy (:54-73)."""
+    import utils as ref_utils
+    out = {}
+    net = gc.bn_cnn(0)
+    probe = gc.image_batches(1, 4, 8, 62)[0][0]
+    with torch.no_grad():
+        out["logits_before"] = net(probe)
+    out["sparsity"] = ref_utils.eval_sparsity(net)
+    with quiet():
+        out["topk"] = ref_utils.test_accuracy(net, gc.labelled_loader(), torch.device("cpu"), topk=(1, 3))
+    ref_utils.fusion_layers_inplace(net, torch.device("cpu"))
+    for name, t in net.state_dict().items():
+        out["fused_" + name.replace(".", "_")] = t
+    out["fused_eps"] = np.array([m.eps for m in net if isinstance(m, nn.BatchNorm2d)])
+    with torch.no_grad():
+        out["logits_after"] = net(probe)
+    save("model_utils.npz", **out)
+
+
 def config1():
     c = gc.config1_inputs()
     with quiet():
@@ -162,5 +182,6 @@ if __name__ == "__main__":
     stochastic_cases()
     conv_capture_cases()
     tiny_network()
+    model_utils()
     if "--skip-cfg1" not in sys.argv:
         config1()

@@ -121,6 +121,34 @@ def network_inputs():
     return cases
 
 
+def bn_cnn(seed=0):
+    """Conv/BN pairs with and without a conv bias, non-trivial running statistics; some exact zeros in the weights."""
+    torch.manual_seed(seed)
+    net = nn.Sequential(
+        nn.Conv2d(3, 6, 3, padding=1, bias=False), nn.BatchNorm2d(6), nn.ReLU(),
+        nn.Conv2d(6, 8, 3, padding=1, bias=True), nn.BatchNorm2d(8, eps=1e-3), nn.ReLU(),
+        nn.Conv2d(8, 8, 1), nn.ReLU(),                       # no BN behind it: must stay untouched
+        nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(8, 5),
+    ).eval()
+    g = _gen(seed + 100)
+    for mod in net:
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.running_mean = torch.randn(mod.num_features, generator=g) * 0.3
+            mod.running_var = torch.rand(mod.num_features, generator=g) + 0.5
+            mod.weight.data = torch.randn(mod.num_features, generator=g)
+            mod.bias.data = torch.randn(mod.num_features, generator=g) * 0.2
+    net[0].weight.data[net[0].weight.data.abs() < 0.05] = 0.0
+    net[-1].bias.data[:2] = 0.0
+    return net
+
+
+def labelled_loader(n=23, batch=5, size=8, classes=5, seed=61):
+    g = _gen(seed)
+    x = torch.randn(n, 3, size, size, generator=g)
+    y = torch.randint(0, classes, (n,), generator=g)
+    return torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=batch, shuffle=False)
+
+
 def config1_inputs():
     """BASELINE.json configs[0]: Linear 1024->1024, m=2048 Gaussian inputs, 4-bit, scalar 1.16."""
     torch.manual_seed(0)

@@ -87,3 +87,39 @@ def test_alexnet_soft_threshold_teacher_forced():
     report = run_teacher_forced("alexnet", batch=4, reg="L1", lam=1e-4)
     assert len(report) == 8
     assert check(report) >= 0.999
+
+
+def _quantize(model, loader, calibration, batch, ignore=(), reg=None, lam=0.1):
+    import quantized_neural_nets_b200 as qb
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    np.random.seed(3)
+    qnn = qb.QuantizeNeuralNet(model, "net", batch, loader, 4, 4, list(ignore), 1.16, 1.16, 1, 1, reg, lam, 0.25, False,
+                               DEV, calibration=calibration, solver=0)
+    qnn.quantize_network()
+    return qnn
+
+
+@pytest.mark.parametrize("name", ["tiny", "resnet18"])
+def test_reuse_calibration_equals_reference_schedule_on_a_repeated_batch(name):
+    """calibration='reuse' (one analog pass + one quantizing pass) must compute exactly what
+    the reference's per-layer schedule (quantize_neural_net.py:117-214) computes when the loader yields the same
+    batch for every layer: same conv patch draws, same X / X~, hence bit-identical Q and errors."""
+    import copy
+    import golden_cases as gc
+    if name == "tiny":
+        model, batch, size, ignore = gc.tiny_cnn(0).to(DEV), 6, 16, [0]
+    else:
+        torch.manual_seed(0)
+        model, batch, size, ignore = torchvision.models.resnet18(weights=None).eval().to(DEV), 8, 224, []
+    images = torch.randn(batch, 3, size, size, generator=torch.Generator().manual_seed(7))
+    n_layers = len(_quantize(copy.deepcopy(model), [(images, None)], "reuse", batch, ignore).quantized_network_layers)
+    fresh = _quantize(copy.deepcopy(model), [(images, None)] * n_layers, "fresh", batch, ignore)
+    reuse = _quantize(copy.deepcopy(model), [(images, None)], "reuse", batch, ignore)
+    assert len(fresh.layer_log) == len(reuse.layer_log) == n_layers - len(ignore)
+    for lf, lr in zip(fresh.quantized_network_layers, reuse.quantized_network_layers):
+        assert torch.equal(lf.weight.data, lr.weight.data)
+    for (i, e, r), (j, e2, r2) in zip(fresh.layer_log, reuse.layer_log):
+        assert i == j and float(e) == float(e2) and float(r) == float(r2)
+    with torch.no_grad():
+        assert torch.equal(fresh.quantized_network(images.to(DEV)), reuse.quantized_network(images.to(DEV)))
