@@ -312,3 +312,32 @@ def exact_decision_margin(W, X, Xq, Q, delta, K, reg=None, lam=0.0) -> torch.Ten
         margin[:, t] = (z - torch.round(z)).abs()
         u -= torch.outer(Q[:, t], Xq[:, t])
     return margin
+
+
+# ----------------------------------------------------------------------------------------------
+# Packed low-bit export (no counterpart in the reference, which saves fp32 tensors, main.py:127-131): the
+# checker restates the container format documented in include/gpfq_b200.h in numpy.
+def packed_bits(K: int, reg: Optional[str] = None) -> int:
+    top = K + 1 if reg == "L0" else K
+    bits = 1
+    while (1 << bits) < 2 * top + 1:
+        bits += 1
+    return bits
+
+
+def pack_levels(levels, K: int, reg: Optional[str] = None):
+    """Signed level indices (any shape) -> uint8 array: codes level+top, 8 codes little-endian in `bits` bytes."""
+    import numpy as np
+    top = K + 1 if reg == "L0" else K
+    bits = packed_bits(K, reg)
+    codes = (np.asarray(levels).astype(np.int64).ravel() + top)
+    assert codes.min(initial=0) >= 0 and codes.max(initial=0) < (1 << bits)
+    pad = (-len(codes)) % 8
+    codes = np.concatenate([codes, np.full(pad, top, dtype=np.int64)]).reshape(-1, 8)
+    words = np.zeros(len(codes), dtype=np.uint64)
+    for i in range(8):
+        words |= codes[:, i].astype(np.uint64) << np.uint64(i * bits)
+    out = np.zeros((len(codes), bits), dtype=np.uint8)
+    for b in range(bits):
+        out[:, b] = ((words >> np.uint64(8 * b)) & np.uint64(0xFF)).astype(np.uint8)
+    return out.ravel()

@@ -8,7 +8,9 @@ it has not been built."""
 from . import _lib  # noqa: F401  (loads libgpfq_b200.so; raises ImportError when missing)
 from .step_algorithm import StepAlgorithm
 from .quantize_neural_net import QuantizeNeuralNet, SaveInputMLP, SaveInputConv2d
-from .utils import InterruptException, extract_layers
+from .utils import InterruptException, extract_layers, fusion_layers_inplace, eval_sparsity, test_accuracy
+from .export import PackedLayer, pack_layer, unpack_layer, export_packed, load_packed
 
 __all__ = ["StepAlgorithm", "QuantizeNeuralNet", "SaveInputMLP", "SaveInputConv2d", "InterruptException",
-           "extract_layers"]
+           "extract_layers", "fusion_layers_inplace", "eval_sparsity", "test_accuracy",
+           "PackedLayer", "pack_layer", "unpack_layer", "export_packed", "load_packed"]

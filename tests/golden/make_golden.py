@@ -158,6 +158,11 @@ def model_utils():
     for name, t in net.state_dict().items():
         out["fused_" + name.replace(".", "_")] = t
     out["fused_eps"] = np.array([m.eps for m in net if isinstance(m, nn.BatchNorm2d)])
+    # the reference leaves eps = 0 (utils.py:121), which torch >= 2.x rejects in F.batch_norm; the smallest normal
+    # fp32 is arithmetically the same (1 + tiny == 1), so the fused network is evaluated with it
+    for mod in net:
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.eps = float(torch.finfo(torch.float32).tiny)
     with torch.no_grad():
         out["logits_after"] = net(probe)
     save("model_utils.npz", **out)

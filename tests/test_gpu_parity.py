@@ -308,3 +308,48 @@ def test_stochastic_solver_statistics_and_invariance(qb):
     torch.manual_seed(3)
     _, _, relo, _, _ = orc.quantize_layer(W, X, Xq, 1500, 1.16 / 8, 8, 1, None, 0.1, 1, True)
     assert abs(rel0 - float(relo)) <= 0.15 * float(relo), (rel0, float(relo))
+
+
+@pytest.mark.parametrize("reg,lam,K", [(None, 0.0, 8), ("L1", 0.004, 8), ("L0", 0.004, 4), (None, 0.0, 2)])
+def test_packed_export_is_lossless_and_matches_format(qb, reg, lam, K):
+    """gpfq_pack_levels_f32 / gpfq_unpack_levels_f32: the codes equal the numpy restatement of the container format,
+    unpacking restores the solver's fp32 weights exactly, off-alphabet input is refused."""
+    N, d, m = 37, 45, 96      # 1665 weights: not a multiple of 8
+    W, X, Xq = (t.to(DEV) for t in gc._problem(11, N, d, m, relu=True, xq_noise=0.02))
+    Q, _, _, _, _ = qb.StepAlgorithm._quantize_layer(W, X, Xq, m, 1.16 / K, K, 1, reg, lam, 1, False, DEV)
+    delta = orc.layer_step_size(W.cpu(), 1.16 / K, K, 1, reg, lam)
+    packed = qb.pack_layer(Q, delta, K, reg, lam)
+    assert packed.bits == orc.packed_bits(K, reg) and packed.nbytes == (N * d + 7) // 8 * packed.bits
+    levels = orc.level_index(Q.cpu(), delta, reg, lam).numpy()
+    np.testing.assert_array_equal(packed.codes.cpu().numpy(), orc.pack_levels(levels, K, reg))
+    back, lv = qb.unpack_layer(packed, want_levels=True)
+    assert torch.equal(back, Q)
+    np.testing.assert_array_equal(lv.cpu().numpy(), levels)
+    bad = Q.clone()
+    bad[3, 5] += 0.37 * float(delta)
+    with pytest.raises(ValueError, match="not on the alphabet"):
+        qb.pack_layer(bad, delta, K, reg, lam)
+
+
+def test_export_packed_network_round_trip(qb):
+    """Quantize the BN network after the reference's conv/BN fusion pre-pass, export it packed, and rebuild a
+    bit-identical network from the codes."""
+    import copy
+    torch.backends.cudnn.allow_tf32 = False
+    model = gc.bn_cnn(0).to(DEV)
+    qb.fusion_layers_inplace(model, DEV)
+    np.random.seed(5)
+    qnn = qb.QuantizeNeuralNet(model, "bn", 6, gc.image_batches(4, 6, 8, 51), 4, 3, [], 1.16, 1.16, 1, 1, None, 0.1,
+                               0.5, False, DEV)
+    qmodel = qnn.quantize_network()
+    packed = qb.export_packed(qnn)
+    assert sorted(packed) == [0, 1, 2, 3]
+    assert [p.bits for p in packed.values()] == [4, 4, 4, 5]        # 3-bit convs: 9 levels; 4-bit Linear: 17 levels
+    rebuilt = copy.deepcopy(model)
+    layers = []
+    qb.extract_layers(rebuilt, layers)
+    qb.load_packed(layers, packed)
+    probe = gc.image_batches(1, 5, 8, 52)[0][0].to(DEV)
+    with torch.no_grad():
+        assert torch.equal(rebuilt(probe), qmodel(probe))
+    assert sum(p.nbytes for p in packed.values()) * 6 < sum(l.weight.numel() * 4 for l in layers)

@@ -131,3 +131,44 @@ def test_all_gather_world2_gloo():
         out = mgr.dict()
         mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_model_utils_match_reference_fixture():
+    """fusion_layers_inplace / eval_sparsity / test_accuracy against outputs of the reference's own functions
+    (utils.py:96-130, :133-159, :54-73; fixture written by tests/golden/make_golden.py::model_utils)."""
+    import golden_cases as gc
+    import quantized_neural_nets_b200 as qb
+    g = np.load(os.path.join(ROOT, "tests", "golden", "model_utils.npz"))
+    net = gc.bn_cnn(0)
+    probe = gc.image_batches(1, 4, 8, 62)[0][0]
+    with torch.no_grad():
+        np.testing.assert_array_equal(net(probe).numpy(), g["logits_before"])
+    assert qb.eval_sparsity(net) == g["sparsity"]
+    np.testing.assert_array_equal(qb.test_accuracy(net, gc.labelled_loader(), torch.device("cpu"), topk=(1, 3)), g["topk"])
+    qb.fusion_layers_inplace(net, torch.device("cpu"))
+    for name, t in net.state_dict().items():
+        np.testing.assert_array_equal(t.numpy(), g["fused_" + name.replace(".", "_")], err_msg=name)
+    with torch.no_grad():
+        np.testing.assert_array_equal(net(probe).numpy(), g["logits_after"])
+    # layer indices are unchanged by the fusion (the BN modules stay in the graph)
+    layers = []
+    qb.extract_layers(net, layers)
+    assert [type(l) for l in layers] == [nn.Conv2d, nn.Conv2d, nn.Conv2d, nn.Linear]
+
+
+def test_packed_format_oracle_round_trip():
+    from oracle import gpfq_oracle as orc
+    rng = np.random.default_rng(0)
+    for K, reg in ((8, None), (4, "L1"), (8, "L0"), (1, None), (64, None)):
+        top = K + 1 if reg == "L0" else K
+        bits = orc.packed_bits(K, reg)
+        assert (1 << bits) >= 2 * top + 1 > (1 << (bits - 1))
+        lv = rng.integers(-top, top + 1, size=1003)
+        packed = orc.pack_levels(lv, K, reg)
+        assert packed.dtype == np.uint8 and packed.size == (1003 + 7) // 8 * bits
+        words = packed.reshape(-1, bits).astype(np.uint64)
+        word = sum(words[:, b] << np.uint64(8 * b) for b in range(bits))
+        back = np.stack([(word >> np.uint64(i * bits)) & np.uint64((1 << bits) - 1) for i in range(8)], axis=1)
+        np.testing.assert_array_equal(back.ravel()[:1003].astype(np.int64) - top, lv)
+    import quantized_neural_nets_b200._lib as L
+    assert [L.lib.gpfq_packed_bits(K, m) for K, m in ((8, 0), (4, 1), (8, 2), (1, 0), (64, 3))] == [5, 4, 5, 2, 8]
