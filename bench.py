@@ -413,8 +413,12 @@ def solver_choices():
     """{"N x d x m": solver name} for the shapes the autotuner timed (rank 0's slices)."""
     from quantized_neural_nets_b200 import step_algorithm as sa
     names = {0: "direct", 1: "gram_tcgen05", 2: "gram_f64"}
-    return {f"{k[0]}x{k[1]}x{k[2]}": {"chosen": names[ch], "agree": round(ag, 6),
-                                      "ms": {names[s]: round(t, 3) for s, t in tm.items()}}
+
+    def label(k):     # (rows, d, m, mode) for ungrouped layers, ("<groups>g", N, d_group, m) for grouped ones
+        return "x".join(str(v) for v in (k if isinstance(k[0], str) else k[:3]))
+
+    return {label(k): {"chosen": names.get(ch, ch), "agree": round(ag, 6),
+                       "ms": {names.get(s, s): round(t, 3) for s, t in tm.items()}}
             for (k, tm, ag, ch) in sa.AUTO_LOG}
 
 

@@ -113,6 +113,19 @@ int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, 
                    int8_t* levels, double* row_err2, double* row_ref2, float* U_out, int64_t ldu,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched solve of a grouped / depthwise convolution: replaces the Python loop over groups of
+ * StepAlgorithm._quantize_layer (step_algorithm.py:221-247), where group g quantizes neurons
+ * [g*N/groups, (g+1)*N/groups) of W (N x d_group) against rows [g*d_group, (g+1)*d_group) of the feature-major
+ * X / Xq ((groups*d_group) x ldx).  Gram form per group (d_group <= 32; gpfq_grouped_workspace_bytes returns 0
+ * otherwise and the caller loops over groups with gpfq_solve_f32): one pass over X and Xq forms every group's
+ * three d_group x d_group Gram matrices in fp64, one warp per neuron then makes the decisions.  [n0, n1) must
+ * cover whole groups when sharding.  Outputs as gpfq_solve_f32 (row_err2 / row_ref2 from the quadratic forms). */
+size_t gpfq_grouped_workspace_bytes(int32_t groups, int32_t d_group, int32_t m);
+int gpfq_solve_grouped_f32(const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int32_t N,
+                           int32_t d_group, int32_t m, int32_t groups, int32_t n0, int32_t n1, const float* delta,
+                           int32_t K, int32_t mode, float lam, uint64_t seed, float* Q, int64_t ldq, int8_t* levels,
+                           double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Optional per-kernel timing for bench.py's roofline object.  Between gpfq_profile_begin() and
  * gpfq_profile_end() every sweep launch of the direct solver is bracketed by CUDA events on its
  * own stream.  gpfq_profile_end() waits for them and fills out[8] = { sweep launches, sweep ms,

@@ -37,6 +37,10 @@ SIGNATURES = {
     "gpfq_gram_f32": (c_i32, [c_i32, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
     "gpfq_gram_path_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i32,
                                    c_i32, c_f32, ctypes.c_uint64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "gpfq_grouped_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32]),
+    "gpfq_solve_grouped_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr,
+                                       c_i32, c_i32, c_f32, ctypes.c_uint64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       ctypes.c_size_t, c_ptr]),
     "gpfq_solve_f32": (c_i32, [c_i32, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32,
                                c_ptr, c_i32, c_i32, c_f32, ctypes.c_uint64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                c_ptr, ctypes.c_size_t, c_ptr]),

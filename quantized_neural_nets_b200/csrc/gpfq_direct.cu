@@ -120,7 +120,8 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     // Resident variant (one launch per layer, U in shared memory).  A cluster of CS CTAs shares TN neurons and
     // splits the columns.  Fitted to B200 measurements (tools/resident_sweep.py, r01), per
     // 32-feature block:
-    //   resident     14 us chain (reduce, DSMEM hand-off, recurrence, barriers) + 1.46 ns per (neuron, column) of
+    //   resident     8.5 us chain (reduce, DSMEM hand-off, recurrence, barriers; 14 us when a CTA decides more than
+    //                8 neurons) + 1.46 ns per (neuron, column) of
     //                ONE CTA's TN x (m/CS) tile (45 % fp32 issue efficiency), times the number of waves -- CTAs
     //                beyond one per SM, or clusters beyond what the GPCs can co-schedule, run as a further wave
     //                (two CTAs sharing an SM measured no better than two waves);
@@ -144,7 +145,8 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
                 const int64_t clusters = ceil_div(n_rows, TN);
                 const int64_t conc = std::max(1, std::min(resident_max_clusters(TN, CS, smem), 148 / CS));
                 const double waves = (double)ceil_div(clusters, conc);
-                const double cost = waves * (14.0 + 1.46e-3 * (double)TN * (double)mc);
+                const double chain = TN / CS <= 8 ? 8.5 : 14.0;      // one neuron per warp, or several / lane = neuron
+                const double cost = waves * (chain + 1.46e-3 * (double)TN * (double)mc);
                 if (cost < rbest) {
                     rbest = cost;
                     p.r_cluster = CS;
@@ -967,9 +969,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // TN = neurons per CTA: 32 (lane = neuron) or 16 (lane = neuron + 16 * column half).
 // a.cluster = CTAs per thread-block cluster (1, 2, 4, 8).  With a cluster, its CTAs share the TN neurons and
-// split the calibration columns: every CTA keeps its own column slice of U in shared memory, the per-block
-// partial dot products are written into the leader CTA's shared memory over DSMEM, the leader runs the block's
-// recurrence and broadcasts q back over DSMEM; two cluster barriers per 32-feature block replace two kernel
+// split the calibration columns: every CTA keeps its own column slice of U in shared memory; per block the
+// partial dot products of neuron n are written over DSMEM into the shared memory of the CTA that decides n
+// (the tile's neurons are dealt out to the cluster's CTAs), that CTA runs the neuron's recurrence and writes
+// its q into every CTA's shared memory; two cluster barriers per 32-feature block replace two kernel
 // launches and two trips through global memory.  This is what lets layers with FEW neurons use many SMs.
 template <int TN, int MODE>
 __global__ void __launch_bounds__(kThreads, TN == 32 ? 1 : 2)
@@ -988,8 +991,10 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     float* ns = qsm + kB * TN;                                                 // [kB]
     float* red = ns + kB;                                                      // [kWarps][TN][17]
     const int CS = a.cluster;
-    double* slots64 = reinterpret_cast<double*>(red + kWarps * TN * 17);       // [CS][TN][kB + 1] (cluster only)
-    float* Us = reinterpret_cast<float*>(slots64 + (CS > 1 ? CS * TN * (kB + 1) : 0));   // [mc/4][TN] float4
+    // cluster: this CTA makes the decisions of OWN = TN / CS of the tile's neurons; P64 then holds the CS senders'
+    // partial projections of those neurons, [CS][OWN][kB + 1]
+    double* slots64 = P64;
+    float* Us = red + kWarps * TN * 17;                                        // [mc/4][TN] float4
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nl_lane = lane % TN, ch = lane / TN;      // this lane's neuron and column half
@@ -1040,8 +1045,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             dst[g * TN + nl] = wv;
         }
     };
-    auto stage_gram = [&](int k) {
-        if (!leader) return;                                  // only the leader runs the recurrence
+    auto stage_gram = [&](int k) {                            // every CTA of a cluster decides some neurons
         const double* g = a.G + (size_t)k * kB * kB;
         const double* h = a.H + (size_t)k * kB * kB;
         for (int e = tid; e < kB * kB / 2; e += kThreads) {     // 16 bytes = 2 doubles per copy
@@ -1051,72 +1055,152 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         if (tid < kB / 4) cp_async16(ns + 4 * tid, a.norm32 + (size_t)k * kB + 4 * tid);
     };
-    // The kB decisions of block k for this CTA's neurons, on ONE warp with lane = neuron: the 32 pending
-    // projections of a neuron live in the lane's registers, always shifted so that p[0] belongs to the
-    // current feature; per step the lane does its own division + alphabet map (no cross-lane redundancy)
-    // and 31 fp64 updates  p[j] <- p[j+1] + w_t G[t][t+1+j] - q_t H[t][t+1+j]  (rows of G / H are zero
-    // padded, so updates past the block edge add zero).  Identical arithmetic to recur_kernel.
+    // The kB decisions of block k.  Work item = neuron, one warp per neuron with lane = feature of the block (the
+    // arithmetic of recur_kernel): lane s keeps p_s = <u, xq_s>; per step the current p_t and w_t are shuffled to
+    // all lanes, every lane forms the same decision q_t, lanes s > t apply  p_s += w_t G[t][s] - q_t H[t][s].
+    // A warp with two or more neurons runs two of them interleaved (two independent latency chains).  In a cluster
+    // the tile's neurons are dealt out to its CTAs (OWN = TN / CS each): before the decisions every CTA has sent
+    // its column slice's partial projections of neuron n to the CTA that owns n (DSMEM, slot = sender's rank,
+    // summed in rank order), afterwards every owner writes its q values into all CTAs' qsm.  So the serial part of
+    // a block -- which one warp used to run for all TN neurons while 8 * CS - 1 warps waited -- is spread over
+    // min(TN, 8 * CS) warps.
+    const int OWN = TN / CS, own0 = crank * OWN;
     auto recurrence = [&](int k, bool have_p) {
         const int t0 = k * kB;
         const int bvalid = min(kB, a.d - t0);
         const float* wblk = wsm + (k & 1) * kB * TN;
-        if (CS > 1) {
-            if (have_p) {
-                // every CTA hands its partial projections to the leader (slot = its rank) ...
-                const uint32_t dst = dsmem_addr(slots64 + (size_t)crank * TN * (kB + 1), 0);
-                for (int e = tid; e < TN * kB; e += kThreads) {
-                    const int n = e / kB, sft = e % kB;
-                    st_dsmem_f64(dst + (uint32_t)((n * (kB + 1) + sft) * sizeof(double)), P64[n * (kB + 1) + sft]);
+        if (CS > 1) cluster_sync_all();                       // all senders' partial projections have landed
+        const int qoff = ((lane >> 2) * TN) * 4 + (lane & 3); // + 4 * n : this lane's feature of neuron n in wsm / qsm
+        if (OWN > 2 * kWarps) {
+            // Many neurons per CTA: ONE warp with lane = neuron instead.  The neuron's 32 pending projections live
+            // in the lane's registers, shifted so that p[0] belongs to the current feature; per step the lane does
+            // its own division + alphabet map and 31 updates  p[j] <- p[j+1] + w_t G[t][t+1+j] - q_t H[t][t+1+j]
+            // (rows of G / H are zero padded).  Same arithmetic; 32 latency chains advance per instruction, which
+            // beats 4 sequential neurons per warp on 8 warps (measured, tools/resident_sweep.py).
+            if (warp == 0 && lane < OWN) {
+                const int n = own0 + lane;
+                double p[kB];
+#pragma unroll
+                for (int s = 0; s < kB; ++s) {
+                    double v = 0.0;
+                    if (have_p) {
+                        if (CS > 1) {
+                            for (int r = 0; r < CS; ++r) v += slots64[((size_t)r * OWN + lane) * (kB + 1) + s];
+                        } else {
+                            v = P64[lane * (kB + 1) + s];
+                        }
+                    }
+                    p[s] = v;
                 }
-            }
-            cluster_sync_all();
-            if (leader && have_p) {                           // ... which sums them in rank order
-                for (int e = tid; e < TN * kB; e += kThreads) {
-                    const int n = e / kB, sft = e % kB;
-                    double acc = 0.0;
-                    for (int r = 0; r < CS; ++r) acc += slots64[((size_t)r * TN + n) * (kB + 1) + sft];
-                    P64[n * (kB + 1) + sft] = acc;
+                for (int t = 0; t < bvalid; ++t) {
+                    const float wt = wblk[((t >> 2) * TN + n) * 4 + (t & 3)];
+                    const double* g = Gs + t * (2 * kB) + t;
+                    const double* h = Hs + t * (2 * kB) + t;
+                    const double dot = fma((double)wt, g[0], p[0]);
+                    const float nrm = ns[t];
+                    const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                    int lv;
+                    const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
+                                                         (uint32_t)(a.n_base + row0 + n), (uint32_t)(t0 + t));
+                    qsm[((t >> 2) * TN + n) * 4 + (t & 3)] = q;
+                    if (a.levels && row0 + n < a.n_rows) a.levels[(int64_t)(row0 + n) * a.ldl + t0 + t] = (int8_t)lv;
+                    const double wd = (double)wt, qd = -(double)q;
+#pragma unroll
+                    for (int j = 0; j < kB - 1; ++j) p[j] = fma(qd, h[1 + j], fma(wd, g[1 + j], p[j + 1]));
+                    p[kB - 1] = 0.0;
                 }
+                for (int t = bvalid; t < kB; ++t) qsm[((t >> 2) * TN + n) * 4 + (t & 3)] = 0.f;
             }
             __syncthreads();
+            for (int e = tid; e < OWN * kB; e += kThreads) {      // this CTA's q values: to global Q and to the peers
+                const int n = own0 + e / kB, t = e % kB;
+                const int at = ((t >> 2) * TN + n) * 4 + (t & 3);
+                const float q = qsm[at];
+                if (row0 + n < a.n_rows && t0 + t < a.d) a.Q[(int64_t)(row0 + n) * a.ldq + t0 + t] = q;
+                for (int r = 0; r < CS; ++r)
+                    if (r != crank) st_dsmem_f32(dsmem_addr(qsm + at, (uint32_t)r), q);
+            }
+            if (CS > 1) cluster_sync_all();
+            else __syncthreads();
+            return;
         }
-        if (leader && warp == 0 && lane < TN) {
-            const int nl = lane;
-            double p[kB];
+        const int per = OWN > kWarps ? 2 : 1;                 // neurons a warp runs at once
+        for (int nl0 = per * warp; nl0 < OWN; nl0 += per * kWarps) {
+            const int cnt = min(per, OWN - nl0);
+            double pr[2] = {0.0, 0.0};
+            float wr[2] = {0.f, 0.f}, q_mine[2] = {0.f, 0.f};
+            int lv_mine[2] = {0, 0};
 #pragma unroll
-            for (int s = 0; s < kB; ++s) p[s] = have_p ? P64[nl * (kB + 1) + s] : 0.0;
-            for (int t = 0; t < bvalid; ++t) {
-                const float wt = wblk[((t >> 2) * TN + nl) * 4 + (t & 3)];
-                const double* g = Gs + t * (2 * kB) + t;
-                const double* h = Hs + t * (2 * kB) + t;
-                const double dot = fma((double)wt, g[0], p[0]);
-                const float nrm = ns[t];
-                const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
-                int lv;
-                const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
-                                                     (uint32_t)(a.n_base + row0 + nl), (uint32_t)(t0 + t));
-                qsm[((t >> 2) * TN + nl) * 4 + (t & 3)] = q;
-                if (a.levels && row0 + nl < a.n_rows) a.levels[(int64_t)(row0 + nl) * a.ldl + t0 + t] = (int8_t)lv;
-                const double wd = (double)wt, qd = -(double)q;
+            for (int i = 0; i < 2; ++i) {
+                if (i >= cnt) break;
+                const int nl = nl0 + i;
+                if (have_p) {
+                    if (CS > 1) {
+                        for (int r = 0; r < CS; ++r) pr[i] += slots64[((size_t)r * OWN + nl) * (kB + 1) + lane];
+                    } else {
+                        pr[i] = P64[nl * (kB + 1) + lane];
+                    }
+                }
+                wr[i] = wblk[qoff + 4 * (own0 + nl)];
+            }
+            if (cnt == 2) {
+                for (int t = 0; t < bvalid; ++t) {
+                    const double gtt = Gs[t * (2 * kB) + t], gl = Gs[t * (2 * kB) + lane], hl = Hs[t * (2 * kB) + lane];
+                    const float nrm = ns[t];
 #pragma unroll
-                for (int j = 0; j < kB - 1; ++j) p[j] = fma(qd, h[1 + j], fma(wd, g[1 + j], p[j + 1]));
-                p[kB - 1] = 0.0;
+                    for (int i = 0; i < 2; ++i) {
+                        const double pt = __shfl_sync(0xffffffffu, pr[i], t);
+                        const float wt = __shfl_sync(0xffffffffu, wr[i], t);
+                        const double dot = fma((double)wt, gtt, pt);
+                        const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                        int lv;
+                        const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
+                                                             (uint32_t)(a.n_base + row0 + own0 + nl0 + i), (uint32_t)(t0 + t));
+                        if (lane == t) {
+                            q_mine[i] = q;
+                            lv_mine[i] = lv;
+                        }
+                        if (lane > t) {
+                            pr[i] = fma((double)wt, gl, pr[i]);
+                            pr[i] = fma(-(double)q, hl, pr[i]);
+                        }
+                    }
+                }
+            } else {
+                for (int t = 0; t < bvalid; ++t) {
+                    const double pt = __shfl_sync(0xffffffffu, pr[0], t);
+                    const float wt = __shfl_sync(0xffffffffu, wr[0], t);
+                    const double dot = fma((double)wt, Gs[t * (2 * kB) + t], pt);
+                    const float nrm = ns[t];
+                    const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                    int lv;
+                    const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
+                                                         (uint32_t)(a.n_base + row0 + own0 + nl0), (uint32_t)(t0 + t));
+                    if (lane == t) {
+                        q_mine[0] = q;
+                        lv_mine[0] = lv;
+                    }
+                    if (lane > t) {
+                        pr[0] = fma((double)wt, Gs[t * (2 * kB) + lane], pr[0]);
+                        pr[0] = fma(-(double)q, Hs[t * (2 * kB) + lane], pr[0]);
+                    }
+                }
             }
-            for (int t = bvalid; t < kB; ++t) qsm[((t >> 2) * TN + nl) * 4 + (t & 3)] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i >= cnt) break;
+                const int n = own0 + nl0 + i;                 // neuron within the tile; lanes >= bvalid hold q = 0
+                qsm[qoff + 4 * n] = q_mine[i];
+                for (int r = 0; r < CS; ++r)
+                    if (r != crank) st_dsmem_f32(dsmem_addr(qsm + qoff + 4 * n, (uint32_t)r), q_mine[i]);
+                if (row0 + n < a.n_rows && t0 + lane < a.d) {
+                    a.Q[(int64_t)(row0 + n) * a.ldq + t0 + lane] = q_mine[i];
+                    if (a.levels) a.levels[(int64_t)(row0 + n) * a.ldl + t0 + lane] = (int8_t)lv_mine[i];
+                }
+            }
         }
-        __syncthreads();
-        if (leader) {
-            for (int e = tid; e < TN * kB; e += kThreads) {   // coalesced copy of the block's q to global Q
-                const int nl = e / kB, t = e % kB;
-                if (row0 + nl < a.n_rows && t0 + t < a.d)
-                    a.Q[(int64_t)(row0 + nl) * a.ldq + t0 + t] = qsm[((t >> 2) * TN + nl) * 4 + (t & 3)];
-            }
-            for (int r = 1; r < CS; ++r) {                    // and q goes to the other CTAs of the cluster
-                const uint32_t dst = dsmem_addr(qsm, (uint32_t)r);
-                for (int e = tid; e < TN * kB; e += kThreads) st_dsmem_f32(dst + (uint32_t)(e * sizeof(float)), qsm[e]);
-            }
-        }
-        if (CS > 1) cluster_sync_all();
+        if (CS > 1) cluster_sync_all();                       // every CTA's qsm is complete
+        else __syncthreads();
     };
 
     stage_w(0);
@@ -1214,7 +1298,11 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     double acc = 0.0;
 #pragma unroll
                     for (int w = 0; w < kWarps; ++w) acc += (double)red[(w * TN + n) * 17 + s];
-                    P64[n * (kB + 1) + half * 16 + s] = acc;
+                    if (CS > 1)      // to the CTA that decides neuron n, slot = this CTA's rank
+                        st_dsmem_f64(dsmem_addr(slots64 + ((size_t)crank * OWN + n % OWN) * (kB + 1) + half * 16 + s,
+                                                (uint32_t)(n / OWN)), acc);
+                    else
+                        P64[n * (kB + 1) + half * 16 + s] = acc;
                 }
                 __syncthreads();
             }
@@ -1255,19 +1343,19 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 }
 
 static size_t resident_smem_host(int64_t mc, int slots, int TN, int cluster) {
+    (void)cluster;      // the cluster's hand-off slots reuse the P64 area
     return 128 + (size_t)slots * (3 * kB * kRJSHost) * sizeof(float) + (size_t)4 * kB * kB * sizeof(double) +
            (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + kB) * sizeof(float) +
-           (size_t)8 * TN * 17 * sizeof(float) + (cluster > 1 ? (size_t)cluster * TN * (kB + 1) * sizeof(double) : 0) +
-           (size_t)mc * TN * sizeof(float);
+           (size_t)8 * TN * 17 * sizeof(float) + (size_t)mc * TN * sizeof(float);
 }
 
 // mc = calibration columns held by one CTA (= m_pad / cluster)
 static size_t resident_smem_bytes(int mc, int slots, int TN, int cluster = 1) {
+    (void)cluster;
     return 128 + (size_t)slots * kRStageFloats * sizeof(float) + (size_t)2 * kB * kB * sizeof(double) +
            (size_t)2 * kB * kB * sizeof(double) /* zero padding of G, H rows */ +
            (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + kB) * sizeof(float) +
-           (size_t)kWarps * TN * 17 * sizeof(float) +
-           (cluster > 1 ? (size_t)cluster * TN * (kB + 1) * sizeof(double) : 0) + (size_t)mc * TN * sizeof(float);
+           (size_t)kWarps * TN * 17 * sizeof(float) + (size_t)mc * TN * sizeof(float);
 }
 
 // How many clusters of CS CTAs of the resident kernel the GPU runs at once (the GPCs decide: 148 SMs do not
@@ -1414,7 +1502,8 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         a.seed = seed; a.n_base = n_base; a.cluster = CS;
         a.slots = 4;
         while (a.slots > 2 && resident_smem_bytes(mc, a.slots, TN, CS) > 225 * 1024) --a.slots;
-        if (resident_smem_bytes(mc, 2, TN, CS) <= 113 * 1024) a.slots = 2;       // keep two CTAs per SM possible
+        // more CTAs than SMs: keep two CTAs per SM possible; otherwise the deeper TMA ring hides the tile latency
+        if (ceil_div(n_rows, TN) * CS > 148 && resident_smem_bytes(mc, 2, TN, CS) <= 113 * 1024) a.slots = 2;
         const size_t smem = resident_smem_bytes(mc, a.slots, TN, CS);
         typedef void (*ResidentFn)(const CUtensorMap, const CUtensorMap, const ResidentArgs);
         static const ResidentFn table[2][4] = {

@@ -82,9 +82,15 @@ class SaveInputConv2d:
         self._idx_dev = None
 
     def _draw(self, batch_size, num_blocks):
+        """Patch rows to keep: per image i, ``keep`` draws with replacement from [L*i, L*(i+1)) off numpy's GLOBAL
+        generator (reference :340-345: one ``np.random.choice(np.arange(L*i, L*(i+1)), size=keep)`` per image).
+        choice() without weights is ``randint(0, L, size)`` on the same stream, and consecutive randint calls
+        with one bound consume the stream exactly like a single larger call, so ONE (batch x keep) draw returns
+        the same indices and leaves the generator in the same state (tests/test_host_cpu.py) -- 256 numpy calls
+        and 256 aranges per layer less on the host."""
         keep = int(self.p * num_blocks + 1 if self.p != 1 else self.p * num_blocks)
-        return np.concatenate([np.random.choice(np.arange(num_blocks * i, num_blocks * (i + 1)), size=keep)
-                               for i in range(batch_size)])
+        offsets = np.arange(batch_size, dtype=np.int64) * num_blocks
+        return (np.random.randint(0, num_blocks, size=(batch_size, keep)) + offsets[:, None]).reshape(-1)
 
     def __call__(self, module, module_in, module_out):
         if len(module_in) != 1:

@@ -129,6 +129,17 @@ def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates, s
     return best, times, agree_best
 
 
+def _time_call(fn):
+    """(milliseconds of the second of two calls, its result) -- the first call warms caches and attributes."""
+    for rep in range(2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+    b.synchronize()
+    return a.elapsed_time(b), out
+
+
 def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, seed=0):
     if solver != AUTO:
         return DEFAULT_SOLVER if solver is None else solver
@@ -152,6 +163,37 @@ def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, s
 
 
 AUTO_GRAM_CANDIDATES = [_lib.SOLVER_GRAM, _lib.SOLVER_GRAM_F64]
+
+# grouped / depthwise convolutions: all groups of the layer in one batched solve (gpfq_solve_grouped_f32) instead
+# of the reference's loop over groups (step_algorithm.py:221-247)
+GROUPED = "grouped"
+
+
+def solve_grouped(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, groups, levels=None, seed=0):
+    """Neurons [n0, n1) (whole groups) of a grouped layer: W (N x d_group), X / Xq feature-major
+    ((groups * d_group) x ldx).  Writes rows n0..n1-1 of Q; returns (row_err2, row_ref2)."""
+    N, dg = W.shape
+    rows = n1 - n0
+    per = N // groups
+    if n0 % per or n1 % per:
+        raise ValueError(f"grouped solve: the neuron range [{n0}, {n1}) must cover whole groups of {per} neurons")
+    dev = W.device
+    row_err2 = torch.zeros(rows, dtype=torch.float64, device=dev)
+    row_ref2 = torch.zeros(rows, dtype=torch.float64, device=dev)
+    if rows == 0:
+        return row_err2, row_ref2
+    nbytes = lib.gpfq_grouped_workspace_bytes(rows // per, dg, m)
+    if nbytes == 0:
+        raise RuntimeError(f"libgpfq_b200: the grouped solver does not support d_group={dg}")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.gpfq_solve_grouped_f32(ptr(W), W.stride(0), ptr(Xfm), ptr(Xqfm), ldx, N, dg, m, groups, n0, n1,
+                                     ptr(delta), int(K), mode, float(lamb), int(seed), ptr(Q), Q.stride(0), ptr(levels),
+                                     ptr(row_err2), ptr(row_ref2), ptr(ws), nbytes, stream_ptr()))
+    return row_err2, row_ref2
+
+
+def grouped_eligible(groups, dg, m):
+    return groups > 1 and lib.gpfq_grouped_workspace_bytes(groups, dg, m) > 0 and m >= 2 * dg
 
 
 def gram_reduce_eligible(N, d, m_total):
@@ -334,13 +376,34 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
         err2[n0:n1], ref2[n0:n1] = e2, r2
         return (Q, err2, ref2) if return_partials else (Q,) + reduce_errors(err2, ref2, groups, None)
     n_per_group = N // groups
+    if groups > 1 and solver in (GROUPED, AUTO) and grouped_eligible(groups, d, m) and not want_adder:
+        use = solver == GROUPED
+        key = ("grouped", groups, N, d, m, mode, n0, n1)
+        if solver == AUTO:
+            if key not in _AUTO_CHOICE:          # time the batched solve against the loop over groups, once
+                t_loop, Q_loop = _time_call(lambda: quantize_layer_impl(
+                    W, X, Xq, m, step_size, boundary_idx, percentile, reg, lamb, groups, stochastic_quantization, device,
+                    neuron_range=neuron_range, solver=None, return_partials=True, delta=delta, seed=seed)[0])
+                Qb = torch.zeros((N, d), dtype=torch.float32, device=dev)
+                t_batched, _ = _time_call(lambda: solve_grouped(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb,
+                                                                 Qb, n0, n1, groups, None, seed))
+                agree = float((Qb[n0:n1] == Q_loop[n0:n1]).float().mean())
+                _AUTO_CHOICE[key] = agree >= 0.999 and t_batched < t_loop
+                AUTO_LOG.append(((f"{groups}g", N, d, m), {"groups_loop": t_loop, GROUPED: t_batched}, agree,
+                                 GROUPED if _AUTO_CHOICE[key] else "groups_loop"))
+            use = _AUTO_CHOICE[key]
+        if use:
+            e2, r2 = solve_grouped(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Q, n0, n1, groups, levels, seed)
+            err2[n0:n1], ref2[n0:n1] = e2, r2
+            return (Q, err2, ref2) if return_partials else (Q,) + reduce_errors(err2, ref2, groups, None)
+    loop_solver = None if solver == GROUPED else solver
     for g in range(groups):
         g0, g1 = max(n0, g * n_per_group), min(n1, (g + 1) * n_per_group)
         if g0 >= g1:
             continue
         Xg = Xfm[g * d:(g + 1) * d]
         Xqg = Xqfm[g * d:(g + 1) * d]
-        sv = resolve_solver(solver, Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, g0, g1, seed)
+        sv = resolve_solver(loop_solver, Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, g0, g1, seed)
         e2, Ures, r2 = solve_rows(Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, Q, g0, g1,
                                   want_err=True, want_residual=(want_adder and groups == 1), levels=levels,
                                   solver=sv, want_ref=True, seed=seed)

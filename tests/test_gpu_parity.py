@@ -353,3 +353,60 @@ def test_export_packed_network_round_trip(qb):
     with torch.no_grad():
         assert torch.equal(rebuilt(probe), qmodel(probe))
     assert sum(p.nbytes for p in packed.values()) * 6 < sum(l.weight.numel() * 4 for l in layers)
+
+
+def _grouped_problem(seed, groups, per, dg, m):
+    """W (groups*per x dg) and (m x groups*dg) layer inputs with correlated, post-ReLU columns inside each group."""
+    g = torch.Generator().manual_seed(seed)
+    W = torch.randn(groups * per, dg, generator=g) * 0.1
+    X = torch.relu(torch.randn(m, groups, dg, generator=g) + 0.5 * torch.randn(m, groups, 1, generator=g)).reshape(m, -1)
+    Xq = torch.relu(X + 0.03 * torch.randn(m, groups * dg, generator=g))
+    return W, X.contiguous(), Xq.contiguous()
+
+
+@pytest.mark.parametrize("groups,per,dg,m,reg,lam", [(24, 1, 9, 777, None, 0.0), (24, 1, 9, 777, "L1", 0.004),
+                                                      (24, 1, 25, 301, "L0", 0.004), (4, 3, 18, 1030, None, 0.0),
+                                                      (130, 2, 32, 150, None, 0.0)])
+def test_grouped_batched_solver_vs_oracle(qb, groups, per, dg, m, reg, lam):
+    """gpfq_solve_grouped_f32 (all groups of a depthwise / grouped conv in one batched solve) against the oracle's
+    loop over groups (step_algorithm.py:221-247): >= 99.9 % identical levels, group-averaged errors within 1e-3."""
+    from quantized_neural_nets_b200 import step_algorithm as sa
+    K = 8
+    W, X, Xq = _grouped_problem(21, groups, per, dg, m)
+    Qo, erro, relo, _, _ = orc.quantize_layer(W, X, Xq, m, 1.16 / K, K, 1, reg, lam, groups, False)
+    Q, err, rel, adder, rel_adder = sa.quantize_layer_impl(W.to(DEV), X.to(DEV), Xq.to(DEV), m, 1.16 / K, K, 1, reg, lam,
+                                                           groups, False, DEV, solver=sa.GROUPED)
+    assert adder is None and rel_adder is None
+    delta = orc.layer_step_size(W, 1.16 / K, K, 1, reg, lam)
+    agree = (orc.level_index(Q.cpu(), delta, reg, lam) == orc.level_index(Qo, delta, reg, lam)).float().mean().item()
+    assert agree >= 0.999, agree
+    assert abs(float(err) - float(erro)) <= 1e-3 * float(erro)
+    assert abs(float(rel) - float(relo)) <= 1e-3 * float(relo)
+    # the loop over groups with the direct solver (the default) stays available and agrees as well
+    Q2, err2, rel2, _, _ = sa.quantize_layer_impl(W.to(DEV), X.to(DEV), Xq.to(DEV), m, 1.16 / K, K, 1, reg, lam, groups,
+                                                  False, DEV)
+    assert (Q2 == Q).float().mean().item() >= 0.999 and abs(float(rel2) - float(rel)) <= 1e-3 * float(rel)
+
+
+def test_grouped_batched_solver_slices_and_auto(qb):
+    from quantized_neural_nets_b200 import step_algorithm as sa
+    K, groups, per, dg, m = 8, 96, 2, 9, 2000
+    W, X, Xq = (t.to(DEV) for t in _grouped_problem(22, groups, per, dg, m))
+    full, e_full, r_full = sa.quantize_layer_impl(W, X, Xq, m, 1.16 / K, K, 1, None, 0.0, groups, False, DEV,
+                                                  solver=sa.GROUPED, return_partials=True)
+    Q = torch.zeros_like(full)
+    for n0, n1 in ((0, 64), (64, 66), (66, 192)):      # whole groups per slice: bit-identical rows
+        part, e2, r2 = sa.quantize_layer_impl(W, X, Xq, m, 1.16 / K, K, 1, None, 0.0, groups, False, DEV,
+                                              solver=sa.GROUPED, return_partials=True, neuron_range=(n0, n1))
+        assert torch.equal(part[n0:n1], full[n0:n1]) and torch.equal(e2[n0:n1], e_full[n0:n1])
+        assert torch.equal(r2[n0:n1], r_full[n0:n1])
+        assert not part[:n0].any() and not part[n1:].any()
+    with pytest.raises(ValueError, match="whole groups"):
+        sa.quantize_layer_impl(W, X, Xq, m, 1.16 / K, K, 1, None, 0.0, groups, False, DEV, solver=sa.GROUPED,
+                               neuron_range=(1, 64))
+    # 'auto' times the batched solve against the loop over 96 groups and keeps the faster one behind the level gate
+    sa.AUTO_LOG.clear()
+    Qa, _, _, _, _ = sa.quantize_layer_impl(W, X, Xq, m, 1.16 / K, K, 1, None, 0.0, groups, False, DEV, solver=sa.AUTO)
+    (key, times, agree, chosen), = [rec for rec in sa.AUTO_LOG if rec[0][0] == "96g"]
+    assert chosen == sa.GROUPED and agree >= 0.999 and times[sa.GROUPED] < times["groups_loop"], (times, agree)
+    assert torch.equal(Qa, full)

@@ -172,3 +172,20 @@ def test_packed_format_oracle_round_trip():
         np.testing.assert_array_equal(back.ravel()[:1003].astype(np.int64) - top, lv)
     import quantized_neural_nets_b200._lib as L
     assert [L.lib.gpfq_packed_bits(K, m) for K, m in ((8, 0), (4, 1), (8, 2), (1, 0), (64, 3))] == [5, 4, 5, 2, 8]
+
+
+def test_patch_index_draw_consumes_numpy_stream_like_the_reference():
+    """SaveInputConv2d._draw makes one vectorised draw; the reference makes one np.random.choice per image
+    (quantize_neural_net.py:340-345).  Same indices, same generator state afterwards."""
+    from quantized_neural_nets_b200.quantize_neural_net import SaveInputConv2d
+    for B, L, p in ((256, 1024, 0.25), (7, 25, 0.25), (5, 49, 1), (3, 1, 0.25), (16, 3136, 0.1)):
+        keep = int(p * L + 1 if p != 1 else p * L)
+        np.random.seed(11)
+        want = np.concatenate([np.random.choice(np.arange(L * i, L * (i + 1)), size=keep) for i in range(B)])
+        tail_want = np.random.rand(3)
+        np.random.seed(11)
+        got = SaveInputConv2d(3, 1, 0, 1, 1, p)._draw(B, L)
+        tail_got = np.random.rand(3)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(tail_got, tail_want)
+        assert got.dtype == want.dtype
