@@ -127,10 +127,11 @@ int gpfq_solve_grouped_f32(const float* W, int64_t ldw, const float* X, const fl
                            double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Optional per-kernel timing for bench.py's roofline object.  Between gpfq_profile_begin() and
- * gpfq_profile_end() every sweep launch of the direct solver is bracketed by CUDA events on its
- * own stream.  gpfq_profile_end() waits for them and fills out[8] = { sweep launches, sweep ms,
- * sweep algorithmic HBM bytes, sweep fp32 instructions (5 per neuron*sample*feature), other
- * solver-kernel launches, 0, 0, 0 }.  Not for use inside a timed region. */
+ * gpfq_profile_end() every sweep_kernel launch (multi-launch structure) and every resident_kernel launch (one per
+ * layer) of the direct solver is bracketed by CUDA events on its own stream.  gpfq_profile_end() waits for them
+ * and fills out[8] = { sweep launches, sweep ms, sweep algorithmic HBM bytes, sweep fp32 instructions (5 per
+ * neuron*sample*feature), other solver-kernel launches, resident launches, resident ms, resident fp32
+ * instructions }.  Not for use inside a timed region. */
 int gpfq_profile_begin(void);
 int gpfq_profile_end(double* out_host);
 

@@ -93,8 +93,10 @@ def profile_begin():
 
 
 def profile_end():
-    """-> dict(sweep_launches, sweep_ms, sweep_bytes, sweep_fp32_instr, other_launches)"""
+    """-> dict(sweep_launches, sweep_ms, sweep_bytes, sweep_fp32_instr, other_launches, resident_launches,
+    resident_ms, resident_fp32_instr)"""
     out = (ctypes.c_double * 8)()
     check(lib.gpfq_profile_end(out))
     return dict(sweep_launches=int(out[0]), sweep_ms=out[1], sweep_bytes=out[2], sweep_fp32_instr=out[3],
-                other_launches=int(out[4]))
+                other_launches=int(out[4]), resident_launches=int(out[5]), resident_ms=out[6],
+                resident_fp32_instr=out[7])

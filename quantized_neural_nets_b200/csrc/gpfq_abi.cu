@@ -42,6 +42,7 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
 struct ProfileRec {
     cudaEvent_t a, b;
     double bytes, instr;
+    int kind;       // 0 = sweep_kernel launch, 1 = resident_kernel launch
 };
 static bool g_profile = false;
 static std::vector<ProfileRec> g_recs;
@@ -54,9 +55,9 @@ void profile_mark_begin(cudaStream_t stream) {
     cudaEventCreate(&g_pending);
     cudaEventRecord(g_pending, stream);
 }
-void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr) {
+void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr, int kind) {
     if (!g_profile || !g_pending) return;
-    ProfileRec r{g_pending, nullptr, alg_bytes, fp32_instr};
+    ProfileRec r{g_pending, nullptr, alg_bytes, fp32_instr, kind};
     cudaEventCreate(&r.b);
     cudaEventRecord(r.b, stream);
     g_recs.push_back(r);
@@ -267,24 +268,28 @@ int gpfq_profile_begin(void) {
 
 int gpfq_profile_end(double* out_host) {
     g_profile = false;
-    double ms_total = 0, bytes = 0, instr = 0;
+    double n[2] = {0, 0}, ms_total[2] = {0, 0}, bytes[2] = {0, 0}, instr[2] = {0, 0};
     for (auto& r : g_recs) {
         GPFQ_CUDA_TRY(cudaEventSynchronize(r.b));
         float ms = 0;
         GPFQ_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
-        ms_total += ms;
-        bytes += r.bytes;
-        instr += r.instr;
+        const int k = r.kind == 1;
+        n[k] += 1;
+        ms_total[k] += ms;
+        bytes[k] += r.bytes;
+        instr[k] += r.instr;
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
     if (out_host) {
-        out_host[0] = (double)g_recs.size();
-        out_host[1] = ms_total;
-        out_host[2] = bytes;
-        out_host[3] = instr;
+        out_host[0] = n[0];
+        out_host[1] = ms_total[0];
+        out_host[2] = bytes[0];
+        out_host[3] = instr[0];
         out_host[4] = g_other;
-        out_host[5] = out_host[6] = out_host[7] = 0;
+        out_host[5] = n[1];
+        out_host[6] = ms_total[1];
+        out_host[7] = instr[1];
     }
     g_recs.clear();
     return 0;

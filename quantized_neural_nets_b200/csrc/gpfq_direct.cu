@@ -1530,7 +1530,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         if (profile_on()) {
             const double nm = (double)n_rows * (double)mp;
             profile_mark_end(stream, 12.0 * kB * (double)mp * p.nblk * ceil_div(n_rows, TN) + 8.0 * n_rows * (double)d,
-                             nm * (4.0 * d + 1.0 * kB * (p.nblk - 1)));
+                             nm * (4.0 * d + 1.0 * kB * (p.nblk - 1)), 1);
         }
         GPFQ_CHECK_LAUNCH();
         if (U_out) {

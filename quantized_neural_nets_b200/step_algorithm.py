@@ -193,7 +193,7 @@ def solve_grouped(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, groups,
 
 
 def grouped_eligible(groups, dg, m):
-    return groups > 1 and lib.gpfq_grouped_workspace_bytes(groups, dg, m) > 0 and m >= 2 * dg
+    return groups > 1 and lib.gpfq_grouped_workspace_bytes(groups, dg, m) > 0
 
 
 def gram_reduce_eligible(N, d, m_total):

@@ -35,7 +35,7 @@ def run(W, X, Xq, m, env):
         e1.record()
         torch.cuda.synchronize()
         p = _lib.profile_end()
-        res = p["sweep_launches"] == 1
+        res = p["resident_launches"] > 0
         if r:
             best = min(best, e0.elapsed_time(e1))
         rel = float((e2.sum() / r2.sum()).sqrt())
