@@ -323,6 +323,17 @@ def run_cuda_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), launches, clocks, qnn, d2h
 
+    if args.profile_one_step:
+        # for `ncu --profile-from-start off`: warm up (autotuning included), then expose exactly ONE step to the
+        # profiler.  Nothing measured under a profiler is a bench value, so nothing is printed.
+        for _ in range(args.warmup):
+            one_step(dev_pool, False)
+        torch.cuda.profiler.start()
+        one_step(dev_pool, False)
+        torch.cuda.profiler.stop()
+        if world > 1:
+            dist.destroy_process_group()
+        return None
     total_ms, launches, clocks, qnn, _ = timed(dev_pool, False, ClockSampler(local) if rank == 0 else None)
     e2e_ms, _, _, qnn, d2h = timed(host_pool, True)
     other_ms = None
@@ -466,6 +477,8 @@ def main():
                     help="fresh: a new batch and two prefix forward passes per layer (the reference's schedule, the "
                          "headline); reuse: one batch for all layers, two network passes in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu launch lists)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: route everything else that native libraries may print
     # there (e.g. NCCL's version banner) to stderr, and write the JSON to the real stdout at the end.

@@ -134,7 +134,7 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
         const double multi_us = 26.0 + (double)n_rows * (double)p.mpad * (5.0 * kB) / (148.0 * 128.0 * 1.9e3 * 0.5);
         double rbest = 1e300;
         p.use_resident = 0;
-        for (int CS : {1, 2, 4, 8}) {
+        for (int CS : {1, 2, 4, 8, 16}) {      // 16 = non-portable cluster size (one cluster per GPC)
             if (force_cs && CS != force_cs) continue;
             for (int TN : {32, 16}) {
                 if (force_tn && TN != force_tn) continue;
@@ -143,7 +143,9 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
                 const size_t smem = resident_smem_host(mc, 2, TN, CS);
                 if (smem > 225 * 1024) continue;
                 const int64_t clusters = ceil_div(n_rows, TN);
-                const int64_t conc = std::max(1, std::min(resident_max_clusters(TN, CS, smem), 148 / CS));
+                const int avail = resident_max_clusters(TN, CS, smem);
+                if (avail <= 0) continue;                    // e.g. 16-CTA clusters not schedulable
+                const int64_t conc = std::max(1, std::min(avail, 148 / CS));
                 const double waves = (double)ceil_div(clusters, conc);
                 const double chain = TN / CS <= 8 ? 8.5 : 14.0;      // one neuron per warp, or several / lane = neuron
                 const double cost = waves * (chain + 1.46e-3 * (double)TN * (double)mc);
@@ -1362,10 +1364,10 @@ static size_t resident_smem_bytes(int mc, int slots, int TN, int cluster = 1) {
 // hold 18 clusters of 8).  Asked from the driver once per (TN, CS, one-or-two CTAs per SM); without a device
 // (gpfq_workspace_bytes on a CPU-only host) the values measured on B200 are used.
 static int resident_max_clusters(int TN, int CS, size_t smem) {
-    static int cache[2][4][2];       // 0 = not asked yet
-    const int ti = TN == 16, ci = CS == 1 ? 0 : CS == 2 ? 1 : CS == 4 ? 2 : 3, si = smem <= 113 * 1024;
+    static int cache[2][5][2];       // 0 = not asked yet
+    const int ti = TN == 16, ci = CS == 1 ? 0 : CS == 2 ? 1 : CS == 4 ? 2 : CS == 8 ? 3 : 4, si = smem <= 113 * 1024;
     if (cache[ti][ci][si]) return cache[ti][ci][si];
-    static const int fallback[4] = {148, 74, 33, 8};
+    static const int fallback[5] = {148, 74, 33, 15, 0};     // measured on B200; 16-CTA clusters only when asked
     int n = 0;
     const void* fn = TN == 16 ? (const void*)resident_kernel<16, GPFQ_MODE_MSQ> : (const void*)resident_kernel<32, GPFQ_MODE_MSQ>;
     cudaLaunchConfig_t cfg{};
@@ -1379,6 +1381,10 @@ static int resident_max_clusters(int TN, int CS, size_t smem) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (CS > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
     if (ensure_dynamic_smem(fn, smem) != 0 || cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) {
         (void)cudaGetLastError();
         return fallback[ci];         // not cached: a device may become available later
@@ -1513,6 +1519,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
              resident_kernel<16, GPFQ_MODE_STOCHASTIC>}};
         const ResidentFn fn = table[TN == 16][mode];
         if (int rc = ensure_dynamic_smem((const void*)fn, smem)) return rc;
+        if (CS > 8) GPFQ_CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(ceil_div(n_rows, TN) * CS));
         cfg.blockDim = dim3(kThreads);

@@ -20,23 +20,30 @@
 namespace gpfq {
 
 constexpr int kGMaxD = 32;      // features per group handled here
-constexpr int kGChunk = 128;    // calibration columns staged per step
+constexpr int kGChunk = 64;     // calibration columns staged per step
 constexpr int kGThreads = 256;
+constexpr int kGMaxCG = 8;      // column groups a CTA may split a chunk into
 
-// part[slice][group - g0][3][dg * dg]
+// part[slice][group - g0][3][dg * dg].  Thread = (pair (r, c), column group): per column it loads x_r, xq_r, x_c,
+// xq_c (staged in shared memory already widened to fp64) and feeds all three matrices, GT[r][c] += x_r xq_c,
+// H[r][c] += xq_r xq_c, A[r][c] += x_r x_c.  With few pairs (depthwise: 81) the chunk's columns are dealt out to
+// several column groups whose sums are combined at the end in a fixed order.
 __global__ void __launch_bounds__(kGThreads)
 grouped_gram_kernel(const float* __restrict__ X, const float* __restrict__ Xq, int64_t ldx, int dg, int m, int g0,
                     int slice_len, double* __restrict__ part) {
-    __shared__ float xs[kGMaxD][kGChunk + 1];
-    __shared__ float xqs[kGMaxD][kGChunk + 1];
+    __shared__ double xs[kGMaxD][kGChunk + 1];
+    __shared__ double xqs[kGMaxD][kGChunk + 1];
     const int g = g0 + blockIdx.x, slice = blockIdx.y;
     const int j_begin = slice * slice_len, j_end = min(m, j_begin + slice_len);
     const int tid = threadIdx.x;
     const int dd = dg * dg;
-    // entries of the three matrices: thread e, e + 256, ...  (at most 3 * 1024 / 256 = 12 each)
-    double acc[12];
+    const int CG = dd >= kGThreads ? 1 : min(kGMaxCG, kGThreads / dd);      // column groups
+    const int ppt = dd >= kGThreads ? (dd + kGThreads - 1) / kGThreads : 1; // pairs per thread (<= 4)
+    const int cg = dd >= kGThreads ? 0 : tid / dd;
+    const bool active = cg < CG;
+    double acc[4][3];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.0;
     const float* Xg = X + (int64_t)g * dg * ldx;
     const float* Xqg = Xq + (int64_t)g * dg * ldx;
     for (int j0 = j_begin; j0 < j_end; j0 += kGChunk) {
@@ -44,29 +51,54 @@ grouped_gram_kernel(const float* __restrict__ X, const float* __restrict__ Xq, i
         for (int e = tid; e < dg * kGChunk; e += kGThreads) {
             const int r = e / kGChunk, c = e % kGChunk;
             const bool in = c < cols;
-            xs[r][c] = in ? Xg[(int64_t)r * ldx + j0 + c] : 0.f;
-            xqs[r][c] = in ? Xqg[(int64_t)r * ldx + j0 + c] : 0.f;
+            xs[r][c] = in ? (double)Xg[(int64_t)r * ldx + j0 + c] : 0.0;
+            xqs[r][c] = in ? (double)Xqg[(int64_t)r * ldx + j0 + c] : 0.0;
         }
         __syncthreads();
+        if (active) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const int e = tid + i * kGThreads;
-            if (e < 3 * dd) {
-                const int which = e / dd, r = (e % dd) / dg, c = e % dg;
-                const float* a = which == 1 ? xqs[r] : xs[r];      // GT: x_r . xq_c   H: xq_r . xq_c   A: x_r . x_c
-                const float* b = which == 2 ? xs[c] : xqs[c];
-                double s = acc[i];
-                for (int j = 0; j < kGChunk; ++j) s = fma((double)a[j], (double)b[j], s);
-                acc[i] = s;
+            for (int i = 0; i < 4; ++i) {
+                const int pair = (dd >= kGThreads ? tid + i * kGThreads : tid - cg * dd);
+                if (i < ppt && pair < dd) {
+                    const int r = pair / dg, c = pair % dg;
+                    double gt = acc[i][0], h = acc[i][1], aa = acc[i][2];
+                    for (int j = cg; j < kGChunk; j += CG) {
+                        const double xr = xs[r][j], xqr = xqs[r][j], xc = xs[c][j], xqc = xqs[c][j];
+                        gt = fma(xr, xqc, gt);
+                        h = fma(xqr, xqc, h);
+                        aa = fma(xr, xc, aa);
+                    }
+                    acc[i][0] = gt; acc[i][1] = h; acc[i][2] = aa;
+                }
             }
         }
         __syncthreads();
     }
     double* out = part + ((int64_t)slice * gridDim.x + blockIdx.x) * 3 * dd;
+    if (CG == 1) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        const int e = tid + i * kGThreads;
-        if (e < 3 * dd) out[e] = acc[i];
+        for (int i = 0; i < 4; ++i) {
+            const int pair = tid + i * kGThreads;
+            if (i < ppt && pair < dd) {
+                out[pair] = acc[i][0];
+                out[dd + pair] = acc[i][1];
+                out[2 * dd + pair] = acc[i][2];
+            }
+        }
+        return;
+    }
+    // combine the column groups in the order 0, 1, ...; xs is free now and holds CG * dd <= 256 doubles
+    double* red = &xs[0][0];
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {      // GT, then H, then A
+        __syncthreads();
+        if (active) red[cg * dd + (tid - cg * dd)] = acc[0][which];
+        __syncthreads();
+        if (tid < dd) {
+            double sum = 0.0;
+            for (int k = 0; k < CG; ++k) sum += red[k * dd + tid];
+            out[which * dd + tid] = sum;
+        }
     }
 }
 

@@ -52,7 +52,7 @@ for (N, d, m) in shapes:
     t_multi, rel0, _, Q0 = run(W, X, Xq, m, {"GPFQ_RESIDENT": "0"})
     t_auto, _, res_auto, _ = run(W, X, Xq, m, {})
     line = [f"{N}x{d}x{m}: multi {t_multi:.3f}  auto {t_auto:.3f}{'(res)' if res_auto else ''} |"]
-    for cs in (1, 2, 4, 8):
+    for cs in (1, 2, 4, 8, 16):
         for tn in (32, 16):
             t, rel, res, Q = run(W, X, Xq, m, {"GPFQ_RESIDENT": "1", "GPFQ_RESIDENT_CLUSTER": str(cs),
                                                "GPFQ_RESIDENT_TN": str(tn)})
