@@ -282,14 +282,15 @@ def run_cuda_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(pool, read_back, profile=False, forward=None, calibration=None):
+    def one_step(pool, read_back, profile=False, forward=None, calibration=None, fuse=None):
         forward = forward or args.forward
         np.random.seed(0)
         qnn = qb.QuantizeNeuralNet(model, args.model, args.batch, BatchPool(pool), args.bits, args.bits, [],
                                    1.16, 1.16, 1, 1, args.reg, args.lamb, args.retain, False, dev, profile=profile,
                                    shard_forward=(forward == "sharded" and world > 1),
                                    solver=None if args.solver == "direct" else args.solver,
-                                   calibration=calibration or args.calibration)
+                                   calibration=calibration or args.calibration,
+                                   fuse_forward=args.fuse_forward if fuse is None else fuse)
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -305,16 +306,16 @@ def run_cuda_arm(args):
         barrier()
         return start.elapsed_time(end), qnn, d2h
 
-    def timed(pool, read_back, sampler=None, forward=None, warmup=None, calibration=None):
+    def timed(pool, read_back, sampler=None, forward=None, warmup=None, calibration=None, fuse=None):
         for _ in range(args.warmup if warmup is None else warmup):
-            one_step(pool, read_back, forward=forward, calibration=calibration)
+            one_step(pool, read_back, forward=forward, calibration=calibration, fuse=fuse)
         if sampler:
             sampler.start()
         before = _lib.launch_count()
         total = 0.0
         d2h = 0
         for _ in range(args.steps):
-            ms, qnn, d2h = one_step(pool, read_back, forward=forward, calibration=calibration)
+            ms, qnn, d2h = one_step(pool, read_back, forward=forward, calibration=calibration, fuse=fuse)
             total += ms
         launches = _lib.launch_count() - before
         clocks = sampler.stop() if sampler else None
@@ -342,6 +343,9 @@ def run_cuda_arm(args):
         other_ms, _, _, _, _ = timed(dev_pool, False, forward=other, warmup=1)
     n_layers = len(qnn.layer_log)
     rel = [float(r) for (_, _, r) in qnn.layer_log]
+    unfused_ms = None
+    if args.fuse_forward and world == 1:   # the same step through PyTorch's own BatchNorm / add / ReLU kernels, for the record
+        unfused_ms, _, _, _, _ = timed(dev_pool, False, fuse=False, warmup=1)
     reuse_ms = reuse_e2e_ms = None
     if args.calibration == "fresh":   # the O(L) single-batch schedule, for the record
         reuse_ms, _, _, _, _ = timed(dev_pool, False, calibration="reuse")
@@ -403,11 +407,17 @@ def run_cuda_arm(args):
             "rel_err_nan_layers": sum(1 for r in rel if r != r),
             "forward_mode": args.forward if world > 1 else "single GPU",
             "calibration": args.calibration,
+            "fuse_forward": args.fuse_forward,
             "solver": args.solver,
             "solver_choices": solver_choices(),
             "phase_ms_per_step": {k: round(v, 2) for k, v in phases.items()},
             "solve_ms_per_layer": [round(per_layer[i].get("solve", 0.0), 3) for i in sorted(per_layer)],
         }
+        if unfused_ms is not None:
+            out["unfused_forward"] = {"note": "fuse_forward=False: cuDNN inference batch norm + separate add / ReLU "
+                                              "kernels in the calibration forward",
+                                      "ms_per_step": unfused_ms / args.steps,
+                                      "value": units / (unfused_ms / args.steps * 1e-3)}
         if reuse_ms is not None:
             out["reuse_calibration"] = {
                 "note": "calibration='reuse': ONE batch calibrates all layers (one analog pass + one quantizing pass "
@@ -476,6 +486,9 @@ def main():
     ap.add_argument("--calibration", default="fresh", choices=["fresh", "reuse"],
                     help="fresh: a new batch and two prefix forward passes per layer (the reference's schedule, the "
                          "headline); reuse: one batch for all layers, two network passes in total")
+    ap.add_argument("--no-fuse-forward", dest="fuse_forward", action="store_false",
+                    help="run the calibration forward through PyTorch's own BatchNorm / add / ReLU kernels instead of the "
+                         "fused elementwise kernel (forward_fusion.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu launch lists)")

@@ -45,6 +45,15 @@ const char* gpfq_last_error(void);
 int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta, int32_t K,
                       int32_t mode, float lam, uint64_t seed, void* stream);
 
+/* Calibration-forward helper (the forward passes of quantize_neural_net.py:256-269 are 97 % of a step and a
+ * quarter of them is BatchNorm / add / ReLU elementwise traffic): inference BatchNorm2d, optional residual add and
+ * optional ReLU / ReLU6 of a contiguous NCHW tensor in one pass,
+ *     out = clamp(x * alpha[c] + beta[c] (+ residual), lo, hi),   planes = B * C planes of HW elements,
+ * with alpha = gamma / sqrt(running_var + eps), beta = bias - running_mean * alpha (the formulation of PyTorch's CPU
+ * batch norm), every operation rounded separately; lo = -inf / hi = +inf switch the clamps off.  residual may be NULL. */
+int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, const float* beta, float* out,
+                    int64_t planes, int32_t C, int32_t HW, float lo, float hi, void* stream);
+
 /* Packed low-bit export of a quantized layer (the reference stores fp32 values that lie on the alphabet,
  * quantize_neural_net.py:163,193; main.py:127-131 saves them as fp32).  A weight is one of the 2K+1 values
  * delta*{-K..K} (MSQ / SOFT / STOCHASTIC) or of the 2K+3 values {0, +-(lam + k*delta), k = 0..K} (HARD), so it is

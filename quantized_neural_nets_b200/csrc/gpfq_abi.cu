@@ -198,6 +198,53 @@ __global__ void unpack_levels_kernel(const uint8_t* __restrict__ in, int64_t n, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Calibration-forward helper: inference BatchNorm2d (+ residual add) (+ ReLU / ReLU6) of an NCHW tensor in ONE pass.
+// y = clamp(x * alpha[c] + beta[c] (+ residual), lo, hi) with alpha = gamma / sqrt(var + eps), beta = bias - mean * alpha
+// precomputed per channel -- the formulation of PyTorch's CPU batch norm (the reference's forward), each operation
+// rounded separately.  One warp per (image, channel) plane per iteration; float4 when the plane allows it.
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ alpha,
+              const float* __restrict__ beta, float* __restrict__ out, int64_t planes, int C, int HW, float lo, float hi) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec = (HW & 3) == 0;
+    for (int64_t pl = warp; pl < planes; pl += n_warps) {
+        const int c = (int)(pl % C);
+        const float a = alpha[c], b = beta[c];
+        const int64_t base = pl * HW;
+        if (vec) {
+            const float4* x4 = reinterpret_cast<const float4*>(x + base);
+            const float4* r4 = res ? reinterpret_cast<const float4*>(res + base) : nullptr;
+            float4* o4 = reinterpret_cast<float4*>(out + base);
+#pragma unroll 4
+            for (int i = lane; i < HW / 4; i += 32) {
+                float4 v = x4[i];
+                v.x = __fadd_rn(__fmul_rn(v.x, a), b);
+                v.y = __fadd_rn(__fmul_rn(v.y, a), b);
+                v.z = __fadd_rn(__fmul_rn(v.z, a), b);
+                v.w = __fadd_rn(__fmul_rn(v.w, a), b);
+                if (r4) {
+                    const float4 r = r4[i];
+                    v.x = __fadd_rn(v.x, r.x); v.y = __fadd_rn(v.y, r.y); v.z = __fadd_rn(v.z, r.z); v.w = __fadd_rn(v.w, r.w);
+                }
+                v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
+                v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
+                o4[i] = v;
+            }
+        } else {
+            for (int i = lane; i < HW; i += 32) {
+                float v = __fadd_rn(__fmul_rn(x[base + i], a), b);
+                if (res) v = __fadd_rn(v, res[base + i]);
+                v = v < lo ? lo : v;
+                v = v > hi ? hi : v;
+                out[base + i] = v;
+            }
+        }
+    }
+}
+
 // (rows x cols) -> (cols x ld_out); pad columns rows..ld_out-1 are zero-filled.
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
                                  float* __restrict__ out, int64_t ld_out) {
@@ -347,6 +394,20 @@ int gpfq_unpack_levels_f32(const uint8_t* packed, int64_t n, const float* delta,
     level_layout(K, mode, &offset, &nbits);
     const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(n, 8), 256), 148 * 8);
     unpack_levels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(packed, n, delta, offset, nbits, mode, lam, Q, levels);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, const float* beta, float* out,
+                    int64_t planes, int32_t C, int32_t HW, float lo, float hi, void* stream) {
+    GPFQ_REQUIRE(planes >= 0 && C >= 1 && HW >= 1 && planes % C == 0, "gpfq_bn_act_f32: bad shape");
+    GPFQ_REQUIRE(x && alpha && beta && out, "gpfq_bn_act_f32: null pointer");
+    GPFQ_REQUIRE((((uintptr_t)x | (uintptr_t)out | (uintptr_t)residual) & 15) == 0, "gpfq_bn_act_f32: tensors must be 16-byte aligned");
+    if (planes == 0) return 0;
+    // 8 warps per CTA; enough CTAs for 8 resident per SM, fewer when there are few planes
+    const int64_t want = std::min<int64_t>(ceil_div(planes, 8), 148 * 8);
+    bn_act_kernel<<<(unsigned)std::max<int64_t>(1, want), 256, 0, (cudaStream_t)stream>>>(x, residual, alpha, beta, out,
+                                                                                       planes, C, HW, lo, hi);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

@@ -174,19 +174,31 @@ struct GramPathArgs {
 
 constexpr int kPathWarps = 8;
 
-// kNB neurons per warp.  dynamic smem: w[8*kNB neurons][dpad32] | q[same] (floats) | M1 | M2 | M3 [32][33] (doubles)
+// kNB neurons per warp.  dynamic smem: w[8*kNB neurons][dpad32] | q[same] (floats) | M1..M4 [32][33] (doubles)
+//
+// Per 32-feature block, left-looking: for every earlier block one pass over four 32 x 32 tiles updates, per neuron
+// and per lane s (a feature of the current block),
+//     p_s  = <u, xq_s> = sum_t  w_t GT[t][s] - q_t H[t][s]          (the projections the decisions need)
+//     rA_s = <v, x_s>  = sum_t  w_t A[t][s]                          (v = X w so far)
+//     rG_s =             sum_t  q_t GT[s][t]                          (<u, x_s> = rA_s - rG_s)
+// and the in-block recurrence then carries the residual norms along with the decisions,
+//     ||u_t||^2 = ||u_{t-1}||^2 + 2 w_t <u_{t-1}, x_t> - 2 q_t <u_{t-1}, xq_t> + w_t^2 A_tt - 2 w_t q_t GT_tt + q_t^2 H_tt
+//     ||v_t||^2 = ||v_{t-1}||^2 + 2 w_t <v_{t-1}, x_t> + w_t^2 A_tt,
+// so there is no separate quadratic-form pass over the three d x d matrices (it used to be 3/4 of the tile traffic).
 template <int kNB>
 __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs a, int dpad32) {
     constexpr int kPathNeurons = kNB * kPathWarps;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* ws = reinterpret_cast<float*>(smem_raw);
     float* qs = ws + (size_t)kPathNeurons * dpad32;
-    double* M1 = reinterpret_cast<double*>(qs + (size_t)kPathNeurons * dpad32);
-    double* M2 = M1 + kGB * 33;
-    double* M3 = M2 + kGB * 33;
+    double* M1 = reinterpret_cast<double*>(qs + (size_t)kPathNeurons * dpad32);   // GT[tc + r][t0 + c]
+    double* M2 = M1 + kGB * 33;                                                   // H [tc + r][t0 + c]
+    double* M3 = M2 + kGB * 33;                                                   // A [tc + r][t0 + c]
+    double* M4 = M3 + kGB * 33;                                                   // GT[t0 + c][tc + r]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_base = blockIdx.x * kPathNeurons;
     const float delta = *a.delta;
+    const bool want_norms = a.row_err2 != nullptr || a.row_ref2 != nullptr;
 
     for (int e = tid; e < kPathNeurons * dpad32; e += blockDim.x) {
         const int nl = e / dpad32, t = e % dpad32;
@@ -197,44 +209,58 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
     __syncthreads();
     const float* wrow[kNB];
     float* qrow[kNB];
+    double e2[kNB], r2[kNB];
 #pragma unroll
     for (int i = 0; i < kNB; ++i) {
         wrow[i] = ws + (size_t)(warp * kNB + i) * dpad32;
         qrow[i] = qs + (size_t)(warp * kNB + i) * dpad32;
+        e2[i] = r2[i] = 0.0;
     }
 
     const int nblk = (a.d + kGB - 1) / kGB;
     for (int blk = 0; blk < nblk; ++blk) {
         const int t0 = blk * kGB;
         const int bvalid = min(kGB, a.d - t0);
-        // left-looking projections  p_i[lane] = sum_{t < t0} w_t GT[t][t0+lane] - q_t H[t][t0+lane]
-        double p[kNB];
+        double p[kNB], rA[kNB], rG[kNB];
 #pragma unroll
-        for (int i = 0; i < kNB; ++i) p[i] = 0.0;
+        for (int i = 0; i < kNB; ++i) p[i] = rA[i] = rG[i] = 0.0;
         for (int tc = 0; tc < t0; tc += kGB) {
             __syncthreads();
             for (int e = tid; e < kGB * kGB; e += blockDim.x) {
                 const int r = e >> 5, c = e & 31;
-                M1[r * 33 + c] = a.GT[(int64_t)(tc + r) * a.ldg + t0 + c];
-                M2[r * 33 + c] = a.H[(int64_t)(tc + r) * a.ldg + t0 + c];
+                const int64_t idx = (int64_t)(tc + r) * a.ldg + t0 + c;
+                M1[r * 33 + c] = a.GT[idx];
+                M2[r * 33 + c] = a.H[idx];
+                if (want_norms) {
+                    M3[r * 33 + c] = a.A[idx];
+                    M4[c * 33 + r] = a.GT[(int64_t)(t0 + r) * a.ldg + tc + c];     // coalesced read, transposed store
+                }
             }
             __syncthreads();
 #pragma unroll 4
             for (int tt = 0; tt < kGB; ++tt) {
                 const double gv = M1[tt * 33 + lane], hv = M2[tt * 33 + lane];
+                const double av = M3[tt * 33 + lane], gt = M4[tt * 33 + lane];
 #pragma unroll
                 for (int i = 0; i < kNB; ++i) {
-                    p[i] = fma((double)wrow[i][tc + tt], gv, p[i]);
-                    p[i] = fma(-(double)qrow[i][tc + tt], hv, p[i]);
+                    const double wt = (double)wrow[i][tc + tt], qt = (double)qrow[i][tc + tt];
+                    p[i] = fma(wt, gv, p[i]);
+                    p[i] = fma(-qt, hv, p[i]);
+                    if (want_norms) {
+                        rA[i] = fma(wt, av, rA[i]);
+                        rG[i] = fma(qt, gt, rG[i]);
+                    }
                 }
             }
         }
-        // diagonal block of GT / H for the in-block recurrence
+        // diagonal blocks of GT / H / A for the in-block recurrence
         __syncthreads();
         for (int e = tid; e < kGB * kGB; e += blockDim.x) {
             const int r = e >> 5, c = e & 31;
-            M1[r * 33 + c] = a.GT[(int64_t)(t0 + r) * a.ldg + t0 + c];
-            M2[r * 33 + c] = a.H[(int64_t)(t0 + r) * a.ldg + t0 + c];
+            const int64_t idx = (int64_t)(t0 + r) * a.ldg + t0 + c;
+            M1[r * 33 + c] = a.GT[idx];
+            M2[r * 33 + c] = a.H[idx];
+            if (want_norms) M3[r * 33 + c] = a.A[idx];
         }
         __syncthreads();
         float wl[kNB], qmine[kNB];
@@ -246,10 +272,11 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
             lvmine[i] = 0;
         }
         for (int t = 0; t < bvalid; ++t) {
-            const double gtt = M1[t * 33 + t], htt = M2[t * 33 + t];
+            const double gtt = M1[t * 33 + t], htt = M2[t * 33 + t], att = M3[t * 33 + t];
             const float root = sqrtf((float)htt);
             const float nrm = __fmul_rn(root, root);            // linalg.norm(.)**2, step_algorithm.py:142
             const double gl = M1[t * 33 + lane], hl = M2[t * 33 + lane];
+            const double al = M3[t * 33 + lane], gtl = M1[lane * 33 + t];      // A[t][s], GT[s][t]
 #pragma unroll
             for (int i = 0; i < kNB; ++i) {
                 const double pt = __shfl_sync(0xffffffffu, p[i], t);
@@ -263,9 +290,20 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
                     qmine[i] = q;
                     lvmine[i] = lv;
                 }
+                const double wd = (double)wt, qd = (double)q;
+                if (want_norms) {
+                    const double rAt = __shfl_sync(0xffffffffu, rA[i], t), rGt = __shfl_sync(0xffffffffu, rG[i], t);
+                    const double quad = fma(wd * wd, att, 0.0);
+                    r2[i] += fma(2.0 * wd, rAt, quad);
+                    e2[i] += fma(2.0 * wd, rAt - rGt, quad) - 2.0 * qd * pt - 2.0 * wd * qd * gtt + qd * qd * htt;
+                }
                 if (lane > t) {
-                    p[i] = fma((double)wt, gl, p[i]);
-                    p[i] = fma(-(double)q, hl, p[i]);
+                    p[i] = fma(wd, gl, p[i]);
+                    p[i] = fma(-qd, hl, p[i]);
+                    if (want_norms) {
+                        rA[i] = fma(wd, al, rA[i]);
+                        rG[i] = fma(qd, gtl, rG[i]);
+                    }
                 }
             }
         }
@@ -280,52 +318,9 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
         }
         __syncwarp();
     }
-
-    // residual norms:  ||u||^2 = sum_s w_s (A w)_s - 2 q_s (GT^T w)_s + q_s (H q)_s ,  ||Xw||^2 = sum_s w_s (A w)_s
-    if (a.row_err2 == nullptr && a.row_ref2 == nullptr) return;
-    double e2[kNB], r2[kNB];
+    if (!want_norms) return;
 #pragma unroll
-    for (int i = 0; i < kNB; ++i) e2[i] = r2[i] = 0.0;
-    for (int s0 = 0; s0 < a.d; s0 += kGB) {
-        double al[kNB], be[kNB], ga[kNB];
-#pragma unroll
-        for (int i = 0; i < kNB; ++i) al[i] = be[i] = ga[i] = 0.0;
-        for (int tc = 0; tc < a.d; tc += kGB) {
-            __syncthreads();
-            for (int e = tid; e < kGB * kGB; e += blockDim.x) {
-                const int r = e >> 5, c = e & 31;
-                const int64_t idx = (int64_t)(tc + r) * a.ldg + s0 + c;
-                M1[r * 33 + c] = a.A[idx];
-                M2[r * 33 + c] = a.GT[idx];
-                M3[r * 33 + c] = a.H[idx];
-            }
-            __syncthreads();
-#pragma unroll 4
-            for (int tt = 0; tt < kGB; ++tt) {
-                const double av = M1[tt * 33 + lane], gv = M2[tt * 33 + lane], hv = M3[tt * 33 + lane];
-#pragma unroll
-                for (int i = 0; i < kNB; ++i) {
-                    const double wt = (double)wrow[i][tc + tt], qt = (double)qrow[i][tc + tt];
-                    al[i] = fma(wt, av, al[i]);
-                    be[i] = fma(wt, gv, be[i]);
-                    ga[i] = fma(qt, hv, ga[i]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kNB; ++i) {
-            const double ws_ = (double)wrow[i][s0 + lane], qs_ = (double)qrow[i][s0 + lane];
-            r2[i] += ws_ * al[i];
-            e2[i] += ws_ * al[i] - 2.0 * qs_ * be[i] + qs_ * ga[i];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < kNB; ++i) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            e2[i] += __shfl_xor_sync(0xffffffffu, e2[i], o);
-            r2[i] += __shfl_xor_sync(0xffffffffu, r2[i], o);
-        }
+    for (int i = 0; i < kNB; ++i) {     // every lane carries the same running sums
         const int n = n_base + warp * kNB + i;
         if (lane == 0 && n < a.n_rows) {
             if (a.row_err2) a.row_err2[n] = fmax(e2[i], 0.0);
@@ -363,7 +358,7 @@ int gram_path(const float* W, int64_t ldw, int d, int n_rows, const double* GT, 
     a.n_rows = n_rows; a.d = d; a.mode = mode; a.Kf = (float)K; a.lam = lam; a.seed = seed; a.n_base = n_base;
     const int dpad32 = (int)round_up(d, kGB);
     auto smem_for = [&](int nb) {
-        return (size_t)2 * nb * kPathWarps * dpad32 * sizeof(float) + 3 * kGB * 33 * sizeof(double);
+        return (size_t)2 * nb * kPathWarps * dpad32 * sizeof(float) + 4 * kGB * 33 * sizeof(double);
     };
     // 4 neurons per warp amortise the Gram tiles best; fall back to 2 / 1 when the w,q rows of the CTA's
     // neurons would not fit in shared memory (large d) or when there are too few neurons to fill the GPU

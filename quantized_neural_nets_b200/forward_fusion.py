@@ -1,0 +1,136 @@
+"""Elementwise fusion of the calibration forward (keyword ``fuse_forward=True`` of QuantizeNeuralNet).
+
+The reference obtains every layer's inputs by running both networks from the image up to the layer
+(quantize_neural_net.py:256-269); with the solver on the GPU those forward passes are 97 % of a step, and an ncu
+launch list of one ResNet-50 step (profiles/r01_launch_shares_bench_step.txt) puts 23 % of it into cuDNN's inference
+batch norm (13.6 %), the ReLU clamps (5.3 %) and the residual adds (4.2 %) -- three to seven trips through HBM per
+activation where one suffices.  ``fuse_inference_forward`` traces a network with torch.fx and replaces
+
+    BatchNorm2d -> ReLU / ReLU6                     BatchNorm2d -> (+ residual) -> ReLU / ReLU6            BatchNorm2d
+
+by one launch of ``gpfq_bn_act_f32`` each.  The traced module calls the SAME Conv2d / Linear module objects, so the
+input-capture hooks fire as before and weights written into the quantized copy are seen by the next pass.  Only
+eval-mode BatchNorm2d with running statistics on contiguous fp32 CUDA NCHW tensors takes the fused kernel; anything
+else falls through to the module's own forward.  The arithmetic is fp32 throughout: ``x * alpha + beta`` with
+``alpha = gamma / sqrt(var + eps)`` and ``beta = bias - mean * alpha`` (how PyTorch's CPU batch norm, i.e. the
+reference's forward, evaluates it), every operation rounded separately."""
+import math
+import operator
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ._lib import lib, check, ptr, stream_ptr
+
+_INF = math.inf
+
+
+class FusedBNAct(nn.Module):
+    """Inference BatchNorm2d (+ residual) (+ clamp to [lo, hi]) in one pass; ``bn`` is the wrapped module (not copied)."""
+
+    def __init__(self, bn, lo=-_INF, hi=_INF):
+        super().__init__()
+        self.bn = bn
+        self.lo, self.hi = float(lo), float(hi)
+        self._coeff = None      # (alpha, beta, version tag)
+
+    def _coefficients(self):
+        bn = self.bn
+        tag = (bn.running_mean._version, bn.running_var._version, bn.running_mean.data_ptr(), bn.eps,
+               None if bn.weight is None else (bn.weight._version, bn.weight.data_ptr()),
+               None if bn.bias is None else (bn.bias._version, bn.bias.data_ptr()))
+        if self._coeff is None or self._coeff[2] != tag:
+            invstd = 1.0 / torch.sqrt(bn.running_var + bn.eps)
+            alpha = invstd if bn.weight is None else invstd * bn.weight.data
+            beta = -bn.running_mean * alpha if bn.bias is None else bn.bias.data - bn.running_mean * alpha
+            self._coeff = (alpha.float().contiguous(), beta.float().contiguous(), tag)
+        return self._coeff[0], self._coeff[1]
+
+    def forward(self, x, residual=None):
+        bn = self.bn
+        fused = (not bn.training and bn.track_running_stats and bn.running_mean is not None and x.is_cuda
+                 and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.numel() > 0
+                 and (residual is None or (residual.shape == x.shape and residual.dtype == x.dtype
+                                           and residual.is_cuda and residual.is_contiguous())))
+        if not fused:
+            y = bn(x)
+            if residual is not None:
+                y = y + residual
+            return y if (self.lo == -_INF and self.hi == _INF) else torch.clamp(y, min=self.lo, max=self.hi)
+        alpha, beta = self._coefficients()
+        B, C, H, W = x.shape
+        out = torch.empty_like(x)
+        check(lib.gpfq_bn_act_f32(ptr(x), ptr(residual), ptr(alpha), ptr(beta), ptr(out), B * C, C, H * W, self.lo, self.hi,
+                                  stream_ptr()))
+        return out
+
+
+def _activation_bounds(node, modules):
+    """(lo, hi) if ``node`` is a ReLU / ReLU6 (module or functional), else None."""
+    if node.op == 'call_module':
+        mod = modules.get(node.target)
+        if type(mod) is nn.ReLU:
+            return 0.0, _INF
+        if type(mod) is nn.ReLU6:
+            return 0.0, 6.0
+    elif node.op == 'call_function':
+        if node.target in (F.relu, torch.relu, torch.relu_) and len(node.args) >= 1:
+            return 0.0, _INF
+        if node.target is F.relu6:
+            return 0.0, 6.0
+    return None
+
+
+def _single_user(node):
+    users = list(node.users)
+    return users[0] if len(users) == 1 else None
+
+
+def fuse_inference_forward(network):
+    """-> (callable running ``network``'s forward with fused BatchNorm / add / ReLU, number of fused sites).
+    The callable shares every submodule with ``network``.  Raises whatever torch.fx raises if the network cannot
+    be traced (data-dependent control flow); the caller then keeps the plain module."""
+    from torch import fx
+    gm = fx.symbolic_trace(network)
+    modules = dict(gm.named_modules())
+    graph = gm.graph
+    sites = 0
+    for node in list(graph.nodes):
+        if node.op != 'call_module' or type(modules.get(node.target)) is not nn.BatchNorm2d:
+            continue
+        if len(node.args) != 1 or node.kwargs:
+            continue
+        bn = modules[node.target]
+        user = _single_user(node)
+        last, residual, bounds = node, None, None
+        if user is not None:
+            act = _activation_bounds(user, modules)
+            if act is not None and user.args[0] is node:
+                last, bounds = user, act                                   # BN -> ReLU
+            elif (user.op == 'call_function' and user.target in (operator.add, operator.iadd, torch.add)
+                  and len(user.args) == 2 and not user.kwargs and node in user.args
+                  and all(isinstance(a, fx.Node) for a in user.args)):
+                after = _single_user(user)
+                act = _activation_bounds(after, modules) if after is not None else None
+                if act is not None and after.args[0] is user:
+                    last, bounds = after, act                              # BN -> + residual -> ReLU
+                    residual = user.args[1] if user.args[0] is node else user.args[0]
+        name = f"_gpfq_fused_bn_{sites}"
+        lo, hi = bounds if bounds is not None else (-_INF, _INF)
+        gm.add_submodule(name, FusedBNAct(bn, lo, hi))
+        with graph.inserting_after(last):
+            args = (node.args[0],) if residual is None else (node.args[0], residual)
+            new = graph.call_module(name, args)
+        last.replace_all_uses_with(new)
+        # erase the replaced chain from its end backwards
+        chain = [last]
+        while chain[-1] is not node:
+            prev = [a for a in chain[-1].args if isinstance(a, fx.Node) and (a is node or node in a.args)]
+            chain.append(prev[0])
+        for dead in chain:
+            graph.erase_node(dead)
+        sites += 1
+    graph.lint()
+    gm.recompile()
+    return gm, sites

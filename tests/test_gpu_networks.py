@@ -140,3 +140,84 @@ def test_reuse_calibration_equals_reference_schedule_on_a_repeated_batch(name):
         assert i == j and float(e) == float(e2) and float(r) == float(r2)
     with torch.no_grad():
         assert torch.equal(fresh.quantized_network(images.to(DEV)), reuse.quantized_network(images.to(DEV)))
+
+
+@pytest.mark.parametrize("shape,lo,hi,with_res", [((3, 5, 7, 7), 0.0, float("inf"), False), ((2, 8, 12, 12), 0.0, 6.0, False),
+                                                  ((2, 8, 12, 12), 0.0, float("inf"), True),
+                                                  ((4, 3, 6, 10), -float("inf"), float("inf"), False),
+                                                  ((1, 16, 9, 9), 0.0, float("inf"), True)])
+def test_fused_bn_act_kernel_is_exact(shape, lo, hi, with_res):
+    """gpfq_bn_act_f32 against the same expression in separately rounded torch ops (x * alpha + beta (+ r), clamp)."""
+    from quantized_neural_nets_b200.forward_fusion import FusedBNAct
+    g = torch.Generator().manual_seed(3)
+    C = shape[1]
+    bn = torch.nn.BatchNorm2d(C).eval()
+    bn.running_mean = torch.randn(C, generator=g)
+    bn.running_var = torch.rand(C, generator=g) + 0.3
+    bn.weight.data = torch.randn(C, generator=g)
+    bn.bias.data = torch.randn(C, generator=g)
+    bn = bn.to(DEV)
+    x = torch.randn(shape, generator=g).to(DEV)
+    x[0, 0, 0, 0] = float("nan")
+    res = torch.randn(shape, generator=g).to(DEV) if with_res else None
+    got = FusedBNAct(bn, lo, hi)(x, res)
+    alpha = (1.0 / torch.sqrt(bn.running_var + bn.eps)) * bn.weight.data
+    beta = bn.bias.data - bn.running_mean * alpha
+    want = x * alpha[None, :, None, None] + beta[None, :, None, None]
+    if with_res:
+        want = want + res
+    want = torch.clamp(want, min=lo, max=hi)
+    assert torch.equal(torch.nan_to_num(got, nan=123.0), torch.nan_to_num(want, nan=123.0))
+    assert torch.isnan(got[0, 0, 0, 0])
+    # and it is PyTorch's own batch norm up to rounding
+    ref = bn(x) if res is None else bn(x) + res
+    ref = torch.clamp(ref, min=lo, max=hi)
+    assert torch.allclose(torch.nan_to_num(got), torch.nan_to_num(ref), rtol=1e-5, atol=1e-6)
+
+
+def test_fused_forward_matches_plain_forward_and_keeps_hooks():
+    from quantized_neural_nets_b200.forward_fusion import fuse_inference_forward
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    model = torchvision.models.resnet18(weights=None).eval().to(DEV)
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+    fused, sites = fuse_inference_forward(model)
+    assert sites == 20
+    x = torch.randn(8, 3, 224, 224, device=DEV)
+    seen = []
+    handle = model.layer3[0].conv1.register_forward_hook(lambda m, i, o: seen.append(i[0].shape))
+    with torch.no_grad():
+        a, b = model(x), fused(x)
+    handle.remove()
+    assert len(seen) == 2 and (a - b).norm() <= 1e-5 * a.norm()
+    model.fc.weight.data.zero_()                       # the fused callable shares the modules' parameters
+    with torch.no_grad():
+        assert torch.equal(fused(x), model.fc.bias.data.expand(8, -1))
+
+
+def test_quantize_network_with_fused_forward():
+    """fuse_forward=True changes how the calibration activations are computed (one elementwise pass instead of
+    cuDNN batch norm + add + ReLU), not what is computed: the quantized network agrees with the unfused run up to
+    rare tie flips."""
+    import copy
+    import golden_cases as gc
+    torch.backends.cudnn.allow_tf32 = False
+    results = []
+    for fuse in (False, True):
+        model = copy.deepcopy(gc.bn_cnn(0)).to(DEV)
+        np.random.seed(5)
+        import quantized_neural_nets_b200 as qb
+        qnn = qb.QuantizeNeuralNet(model, "bn", 6, gc.image_batches(4, 6, 8, 51), 4, 4, [], 1.16, 1.16, 1, 1, None, 0.1,
+                                   0.5, False, DEV, fuse_forward=fuse)
+        assert bool(qnn._fused) == fuse
+        results.append(qnn.quantize_network())
+    for la, lb in zip(results[0].modules(), results[1].modules()):
+        if isinstance(la, (torch.nn.Conv2d, torch.nn.Linear)):
+            assert (la.weight.data == lb.weight.data).float().mean().item() >= 0.99
+    probe = gc.image_batches(1, 5, 8, 52)[0][0].to(DEV)
+    with torch.no_grad():
+        a, b = results[0](probe), results[1](probe)
+    assert (a - b).norm() <= 2e-2 * a.norm()
