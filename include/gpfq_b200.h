@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GPFQ_ABI_VERSION 4
+#define GPFQ_ABI_VERSION 5
 
 /* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0'),
  * :7-35 (STOCHASTIC, SGPFQ: stochastic rounding to the two neighbouring grid points, then clipping; the
@@ -138,9 +138,10 @@ int gpfq_solve_grouped_f32(const float* W, int64_t ldw, const float* X, const fl
 /* Optional per-kernel timing for bench.py's roofline object.  Between gpfq_profile_begin() and
  * gpfq_profile_end() every sweep_kernel launch (multi-launch structure) and every resident_kernel launch (one per
  * layer) of the direct solver is bracketed by CUDA events on its own stream.  gpfq_profile_end() waits for them
- * and fills out[8] = { sweep launches, sweep ms, sweep algorithmic HBM bytes, sweep fp32 instructions (5 per
+ * and fills out[12] = { sweep launches, sweep ms, sweep algorithmic HBM bytes, sweep fp32 instructions (5 per
  * neuron*sample*feature), other solver-kernel launches, resident launches, resident ms, resident fp32
- * instructions }.  Not for use inside a timed region. */
+ * instructions, bn_act launches, bn_act ms, bn_act algorithmic HBM bytes (read x (+ residual), write out), 0 }.
+ * Not for use inside a timed region. */
 int gpfq_profile_begin(void);
 int gpfq_profile_end(double* out_host);
 

@@ -95,9 +95,9 @@ def profile_begin():
 
 def profile_end():
     """-> dict(sweep_launches, sweep_ms, sweep_bytes, sweep_fp32_instr, other_launches, resident_launches,
-    resident_ms, resident_fp32_instr)"""
-    out = (ctypes.c_double * 8)()
+    resident_ms, resident_fp32_instr, bn_act_launches, bn_act_ms, bn_act_bytes)"""
+    out = (ctypes.c_double * 12)()
     check(lib.gpfq_profile_end(out))
     return dict(sweep_launches=int(out[0]), sweep_ms=out[1], sweep_bytes=out[2], sweep_fp32_instr=out[3],
                 other_launches=int(out[4]), resident_launches=int(out[5]), resident_ms=out[6],
-                resident_fp32_instr=out[7])
+                resident_fp32_instr=out[7], bn_act_launches=int(out[8]), bn_act_ms=out[9], bn_act_bytes=out[10])

@@ -42,7 +42,7 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
 struct ProfileRec {
     cudaEvent_t a, b;
     double bytes, instr;
-    int kind;       // 0 = sweep_kernel launch, 1 = resident_kernel launch
+    int kind;       // 0 = sweep_kernel launch, 1 = resident_kernel launch, 2 = bn_act_kernel launch
 };
 static bool g_profile = false;
 static std::vector<ProfileRec> g_recs;
@@ -315,12 +315,12 @@ int gpfq_profile_begin(void) {
 
 int gpfq_profile_end(double* out_host) {
     g_profile = false;
-    double n[2] = {0, 0}, ms_total[2] = {0, 0}, bytes[2] = {0, 0}, instr[2] = {0, 0};
+    double n[3] = {0, 0, 0}, ms_total[3] = {0, 0, 0}, bytes[3] = {0, 0, 0}, instr[3] = {0, 0, 0};
     for (auto& r : g_recs) {
         GPFQ_CUDA_TRY(cudaEventSynchronize(r.b));
         float ms = 0;
         GPFQ_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
-        const int k = r.kind == 1;
+        const int k = r.kind >= 0 && r.kind <= 2 ? r.kind : 0;
         n[k] += 1;
         ms_total[k] += ms;
         bytes[k] += r.bytes;
@@ -337,6 +337,10 @@ int gpfq_profile_end(double* out_host) {
         out_host[5] = n[1];
         out_host[6] = ms_total[1];
         out_host[7] = instr[1];
+        out_host[8] = n[2];
+        out_host[9] = ms_total[2];
+        out_host[10] = bytes[2];
+        out_host[11] = 0;
     }
     g_recs.clear();
     return 0;
@@ -406,8 +410,10 @@ int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, c
     if (planes == 0) return 0;
     // 8 warps per CTA; enough CTAs for 8 resident per SM, fewer when there are few planes
     const int64_t want = std::min<int64_t>(ceil_div(planes, 8), 148 * 8);
+    profile_mark_begin((cudaStream_t)stream);
     bn_act_kernel<<<(unsigned)std::max<int64_t>(1, want), 256, 0, (cudaStream_t)stream>>>(x, residual, alpha, beta, out,
                                                                                        planes, C, HW, lo, hi);
+    if (profile_on()) profile_mark_end((cudaStream_t)stream, (residual ? 12.0 : 8.0) * (double)planes * HW, 0.0, 2);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }
