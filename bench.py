@@ -35,7 +35,7 @@ NCU_SWEEP_TRAFFIC = {"dram_bytes_per_launch": 185.2e6, "algorithmic_bytes_same_l
                      "source": "profiles/r01_sweep_kernel_ncu_full_summary.txt"}
 
 # the same for one bn_act_kernel launch (filled from profiles/r01_bn_act_kernel_ncu_full_summary.txt)
-NCU_BN_ACT_TRAFFIC = {"dram_bytes_per_launch": None, "algorithmic_bytes_same_launch": 616.6e6,
+NCU_BN_ACT_TRAFFIC = {"dram_bytes_per_launch": 2440.1e6, "algorithmic_bytes_same_launch": 2466.3e6,
                       "launch": "BatchNorm + residual + ReLU of a (256, 256, 56, 56) activation",
                       "source": "profiles/r01_bn_act_kernel_ncu_full_summary.txt"}
 
