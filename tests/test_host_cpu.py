@@ -189,3 +189,42 @@ def test_patch_index_draw_consumes_numpy_stream_like_the_reference():
         np.testing.assert_array_equal(got, want)
         np.testing.assert_array_equal(tail_got, tail_want)
         assert got.dtype == want.dtype
+
+
+def test_forward_fusion_pass_structure():
+    """The torch.fx pass behind fuse_forward=True (forward_fusion.py): every BatchNorm2d becomes one fused site with
+    the right activation bounds and residual wiring, the traced module shares the network's Conv2d / Linear
+    objects (so the capture hooks still fire), and on CPU tensors the sites fall through to the modules' own
+    forward, i.e. the function is unchanged."""
+    import torchvision
+    from quantized_neural_nets_b200.forward_fusion import fuse_inference_forward, FusedBNAct
+    inf = float("inf")
+    expect = {"resnet18": {(0.0, inf): 17, (-inf, inf): 3}, "mobilenet_v2": {(0.0, 6.0): 35, (-inf, inf): 17}}
+    for name, kinds in expect.items():
+        torch.manual_seed(0)
+        model = getattr(torchvision.models, name)(weights=None).eval()
+        for mod in model.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+        fused, sites = fuse_inference_forward(model)
+        got = {}
+        for mod in fused.modules():
+            if isinstance(mod, FusedBNAct):
+                got[(mod.lo, mod.hi)] = got.get((mod.lo, mod.hi), 0) + 1
+        assert got == kinds and sites == sum(kinds.values()), (name, got)
+        convs = [m for m in model.modules() if isinstance(m, (nn.Conv2d, nn.Linear))]
+        assert all(a is b for a, b in zip(convs, [m for m in fused.modules() if isinstance(m, (nn.Conv2d, nn.Linear))]))
+        seen = []
+        handle = convs[5].register_forward_hook(lambda m, i, o: seen.append(1))
+        x = torch.randn(2, 3, 64, 64)
+        with torch.no_grad():
+            assert torch.equal(model(x), fused(x))
+        handle.remove()
+        assert len(seen) == 2
+    # residual wiring: BN -> add(identity) -> ReLU collapses into one site that takes the identity as 2nd input
+    block = torchvision.models.resnet18(weights=None).eval().layer1[0]
+    fused, sites = fuse_inference_forward(block)
+    calls = [n for n in fused.graph.nodes if n.op == "call_module" and "_gpfq_fused_bn_" in str(n.target)]
+    assert sites == 2 and [len(n.args) for n in calls] == [1, 2]
+    assert not any(n.op == "call_function" for n in fused.graph.nodes)          # the add is gone
