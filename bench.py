@@ -295,7 +295,8 @@ def run_cuda_arm(args):
                                    shard_forward=(forward == "sharded" and world > 1),
                                    solver=None if args.solver == "direct" else args.solver,
                                    calibration=calibration or args.calibration,
-                                   fuse_forward=args.fuse_forward if fuse is None else fuse)
+                                   fuse_forward=args.fuse_forward if fuse is None else fuse,
+                                   pointwise_gemm=args.pointwise_gemm if fuse is None else fuse)
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -418,6 +419,7 @@ def run_cuda_arm(args):
             "forward_mode": args.forward if world > 1 else "single GPU",
             "calibration": args.calibration,
             "fuse_forward": args.fuse_forward,
+            "pointwise_gemm": args.pointwise_gemm,
             "solver": args.solver,
             "solver_choices": solver_choices(),
             "phase_ms_per_step": {k: round(v, 2) for k, v in phases.items()},
@@ -439,8 +441,9 @@ def run_cuda_arm(args):
         else:
             out["roofline"] = out["direct_kernel_roofline"]
         if unfused_ms is not None:
-            out["unfused_forward"] = {"note": "fuse_forward=False: cuDNN inference batch norm + separate add / ReLU "
-                                              "kernels in the calibration forward",
+            out["unfused_forward"] = {"note": "fuse_forward=False, pointwise_gemm=False: cuDNN inference batch norm, "
+                                              "separate add / ReLU kernels and cuDNN 1x1 convolutions in the "
+                                              "calibration forward",
                                       "ms_per_step": unfused_ms / args.steps,
                                       "value": units / (unfused_ms / args.steps * 1e-3)}
         if reuse_ms is not None:
@@ -514,6 +517,9 @@ def main():
     ap.add_argument("--no-fuse-forward", dest="fuse_forward", action="store_false",
                     help="run the calibration forward through PyTorch's own BatchNorm / add / ReLU kernels instead of the "
                          "fused elementwise kernel (forward_fusion.py)")
+    ap.add_argument("--no-pointwise-gemm", dest="pointwise_gemm", action="store_false",
+                    help="keep cuDNN for the stride-1 1x1 convolutions of the calibration forward instead of one "
+                         "strided-batched cuBLAS SGEMM each (gpfq_conv1x1_f32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu launch lists)")

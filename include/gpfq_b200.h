@@ -54,6 +54,13 @@ int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta,
 int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, const float* beta, float* out,
                     int64_t planes, int32_t C, int32_t HW, float lo, float hi, void* stream);
 
+/* Calibration-forward helper: a stride-1 1x1 convolution (no bias, groups = 1) of a contiguous NCHW tensor,
+ * out[b] (N x HW) = W (N x C) @ x[b] (C x HW), as ONE cublasSgemmStridedBatched with a zero batch stride for W
+ * (fp32 SIMT SGEMM, default math mode: no TF32).  The library-GEMM form of what F.conv2d does for these layers inside the
+ * reference's forward passes (quantize_neural_net.py:256-269). */
+int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
+                     void* stream);
+
 /* Packed low-bit export of a quantized layer (the reference stores fp32 values that lie on the alphabet,
  * quantize_neural_net.py:163,193; main.py:127-131 saves them as fp32).  A weight is one of the 2K+1 values
  * delta*{-K..K} (MSQ / SOFT / STOCHASTIC) or of the 2K+3 values {0, +-(lam + k*delta), k = 0..K} (HARD), so it is

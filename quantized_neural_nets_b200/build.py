@@ -10,6 +10,9 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgpfq_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
+# cuBLAS for the one plain library GEMM of the calibration forward (csrc/gpfq_conv1x1.cu); at run time the SONAME
+# resolves to the libcublas that torch has already loaded, the toolkit's copy is the fallback
+LINK_FLAGS = ["-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 
 def sources():
@@ -28,7 +31,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources() + LINK_FLAGS
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

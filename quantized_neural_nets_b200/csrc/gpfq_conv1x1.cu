@@ -1,0 +1,50 @@
+// Stride-1 1x1 convolution of an NCHW tensor as ONE strided-batched library SGEMM (calibration-forward helper).
+//
+// out[b] (N x HW) = W (N x C) @ x[b] (C x HW) for every image b.  PyTorch reaches cuBLAS for this product only through
+// torch.bmm, which first materialises the batch-broadcast weight (256 copies of W; measured 17 ms of copy kernels per
+// ResNet-50 forward); cublasSgemmStridedBatched takes the weight with a batch stride of ZERO.  Plain fp32 SIMT SGEMM
+// (no TF32): cuBLAS is used here as a library GEMM, nothing else.
+#include <cublas_v2.h>
+
+#include <map>
+#include <mutex>
+
+#include "gpfq_common.cuh"
+
+namespace gpfq {
+
+static cublasHandle_t handle_for_current_device() {
+    static std::mutex mu;
+    static std::map<int, cublasHandle_t> handles;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = handles.find(dev);
+    if (it != handles.end()) return it->second;
+    cublasHandle_t h = nullptr;
+    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return nullptr;
+    // CUBLAS_DEFAULT_MATH: fp32 SGEMM keeps fp32 operands (TF32 needs CUBLAS_TF32_TENSOR_OP_MATH, never set here)
+    handles[dev] = h;
+    return h;
+}
+
+}  // namespace gpfq
+
+using namespace gpfq;
+
+extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
+                                void* stream) {
+    GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && HW >= 1, "gpfq_conv1x1_f32: bad shape");
+    GPFQ_REQUIRE(x && W && out, "gpfq_conv1x1_f32: null pointer");
+    if (B == 0) return 0;
+    cublasHandle_t h = handle_for_current_device();
+    GPFQ_REQUIRE(h != nullptr, "gpfq_conv1x1_f32: cublasCreate failed");
+    GPFQ_REQUIRE(cublasSetStream(h, (cudaStream_t)stream) == CUBLAS_STATUS_SUCCESS, "gpfq_conv1x1_f32: cublasSetStream failed");
+    // row-major out[b] (N x HW) = W (N x C) x[b] (C x HW)  <=>  column-major out[b]^T (HW x N) = x[b]^T (HW x C) W^T (C x N)
+    const float one = 1.f, zero = 0.f;
+    const cublasStatus_t st = cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, HW, N, C, &one, x, HW, (long long)C * HW,
+                                                        W, C, 0LL, &zero, out, HW, (long long)N * HW, B);
+    GPFQ_REQUIRE(st == CUBLAS_STATUS_SUCCESS, "gpfq_conv1x1_f32: cublasSgemmStridedBatched failed with status %d", (int)st);
+    count_launch();
+    return 0;
+}

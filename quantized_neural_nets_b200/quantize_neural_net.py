@@ -139,7 +139,7 @@ class QuantizeNeuralNet:
                  mlp_percentile, cnn_percentile,
                  reg, lamb, retain_rate, stochastic_quantization, device,
                  *, process_group=None, solver=None, verbose=False, profile=False, shard_forward=False,
-                 overlap_solve=False, gram_reduce=True, calibration='fresh', fuse_forward=False):
+                 overlap_solve=False, gram_reduce=True, calibration='fresh', fuse_forward=False, pointwise_gemm=False):
         self.network_name = network_name
         self.analog_network = network_to_quantize          # not copied, as in the reference (:82)
         self.batch_size = batch_size
@@ -196,6 +196,11 @@ class QuantizeNeuralNet:
         # arithmetic as PyTorch's CPU batch norm, a quarter less HBM traffic per pass.  The fused callables share all
         # Conv2d / Linear modules with the networks, so hooks and weight updates behave as before.
         self.fuse_forward = fuse_forward
+        # Opt-in experiment, measured as a LOSS in r01 (forward_fusion.pointwise_convs_as_gemm): stride-1 1x1
+        # convolutions as torch.matmul.  In isolation cuBLAS beats cuDNN on every ResNet-50 shape (20 vs 27 ms per
+        # forward), but torch.bmm materialises the batch-broadcast weight (17 ms of copies per forward), so the
+        # full forward is 59.9 ms against 53.2 ms; needs a strided-batched GEMM with a zero weight stride.
+        self.pointwise_gemm = pointwise_gemm
         self._fused = {}
         if fuse_forward:
             from .forward_fusion import fuse_inference_forward
@@ -256,6 +261,13 @@ class QuantizeNeuralNet:
             print(f'Total number of layers to quantize {len(layers_to_quantize)}')
         deltas = self._layer_deltas(layers_to_quantize)
         self.layer_deltas = deltas             # {layer index: alphabet step}; read by export.export_packed
+        if self.pointwise_gemm:                # 1x1 convolutions of the calibration passes as batched SGEMMs
+            from .forward_fusion import pointwise_convs_as_gemm
+            with pointwise_convs_as_gemm(self.analog_network, self.quantized_network):
+                return self._quantize_layers(layers_to_quantize, deltas)
+        return self._quantize_layers(layers_to_quantize, deltas)
+
+    def _quantize_layers(self, layers_to_quantize, deltas):
         if self.calibration == 'reuse':
             self._quantize_network_reuse(layers_to_quantize, deltas)
             return self.quantized_network

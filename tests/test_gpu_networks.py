@@ -221,3 +221,24 @@ def test_quantize_network_with_fused_forward():
     with torch.no_grad():
         a, b = results[0](probe), results[1](probe)
     assert (a - b).norm() <= 2e-2 * a.norm()
+
+
+def test_pointwise_convs_as_gemm_match_cudnn_and_keep_hooks():
+    from quantized_neural_nets_b200.forward_fusion import pointwise_convs_as_gemm
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    model = torchvision.models.resnet50(weights=None).eval().to(DEV)
+    x = torch.randn(8, 3, 224, 224, device=DEV)
+    conv = torch.nn.Conv2d(96, 40, 1, bias=True).to(DEV)
+    y = torch.randn(5, 96, 9, 13, device=DEV)
+    with torch.no_grad():
+        want, want_b = model(x), conv(y)
+    seen = []
+    handle = model.layer2[1].conv3.register_forward_hook(lambda m, i, o: seen.append(tuple(o.shape)))
+    with pointwise_convs_as_gemm(model, conv) as n, torch.no_grad():
+        assert n == 34
+        got, got_b = model(x), conv(y)
+    handle.remove()
+    assert seen == [(8, 512, 28, 28)]
+    assert (got - want).norm() <= 1e-6 * want.norm() and torch.allclose(got_b, want_b, rtol=1e-5, atol=1e-6)

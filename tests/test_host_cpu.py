@@ -228,3 +228,19 @@ def test_forward_fusion_pass_structure():
     calls = [n for n in fused.graph.nodes if n.op == "call_module" and "_gpfq_fused_bn_" in str(n.target)]
     assert sites == 2 and [len(n.args) for n in calls] == [1, 2]
     assert not any(n.op == "call_function" for n in fused.graph.nodes)          # the add is gone
+
+
+def test_pointwise_convs_as_gemm_patches_and_restores():
+    import torchvision
+    from quantized_neural_nets_b200.forward_fusion import pointwise_convs_as_gemm
+    torch.manual_seed(0)
+    model = torchvision.models.resnet50(weights=None).eval()
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        want = model(x)
+    with pointwise_convs_as_gemm(model) as n:
+        assert n == 33                                   # 16 bottlenecks x (conv1, conv3) + layer1.0.downsample; stride-2 / 3x3 / 7x7 untouched
+        assert sum('forward' in m.__dict__ for m in model.modules()) == 33
+        with torch.no_grad():
+            assert torch.equal(model(x), want)           # CPU tensors take Conv2d.forward
+    assert not any('forward' in m.__dict__ for m in model.modules())
