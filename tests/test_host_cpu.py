@@ -244,3 +244,26 @@ def test_pointwise_convs_as_gemm_patches_and_restores():
         with torch.no_grad():
             assert torch.equal(model(x), want)           # CPU tensors take Conv2d.forward
     assert not any('forward' in m.__dict__ for m in model.modules())
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """The JSON line bench.py printed on the B200 for the final r01 tree (profiles/) carries every key of the bench
+    contract: metric / value / e2e / gpu_launches / clocks / roofline / cpu_baseline."""
+    import json
+    j = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1_final4.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in j, key
+    assert j["n_gpus"] == 1 and j["dtype"] == "f32" and j["higher_is_better"] is True and j["vs_baseline"] is None
+    assert "workload" in j["config"] and "model" not in j["config"]
+    assert abs(j["value"] - j["units_per_step"] / (j["ms_per_step"] * 1e-3)) < 1e-6 * j["value"]
+    e2e = j["e2e"]
+    assert e2e["unit"] == j["unit"] and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    assert e2e["value"] != j["value"]
+    assert j["gpu_launches"] > 0
+    assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    roof = j["roofline"]
+    assert roof["bound"] in ("hbm", "tensor") and roof["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and roof["traffic"] is not None
+    cpu = j["cpu_baseline"]
+    assert cpu["kind"] in ("reference", "port") and cpu["cores"] >= 1 and cpu["value"] > 0 and cpu["sample"]
