@@ -51,7 +51,8 @@ def build_model(name):
 
 
 def layer_shapes(model, batch, retain, image=224):
-    """(N, d, m, groups) of every quantizable layer, walked in the reference's layer order."""
+    """(N, d, m, groups) of every quantizable layer, walked in the reference's layer order (CUDA arm only: it
+    imports the product package)."""
     from quantized_neural_nets_b200.utils import extract_layers
     layers = []
     extract_layers(model, layers)
@@ -132,112 +133,37 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-CPU_CLASSES = [  # (N, d, m) -- one ResNet-50 layer shape per calibration-row class
-    (256, 64, 200960), (512, 128, 50432), (64, 576, 23296), (1024, 256, 12800), (128, 1152, 6656),
-    (2048, 512, 3328), (256, 2304, 1792), (512, 4608, 768), (1000, 2048, 256),
-]
-
-
-def cpu_reference_sample(shapes, seconds_per_class=1.5):
-    """Times the oracle's greedy loop (a torch-CPU restatement issuing the reference's own ATen ops,
-    step_algorithm.py:140-148) for the first k features of one layer per calibration-row class
-    (k sized so that each class takes about ``seconds_per_class``) and extrapolates to the whole
-    network: the loop's cost per feature is constant within a layer.
-    Returns (extrapolated units/s, seconds spent, extrapolated seconds for the network)."""
-    from oracle import gpfq_oracle as orc
-    g = torch.Generator().manual_seed(3)
-    rates = {}
-    spent = 0.0
-    for (N, d, m) in CPU_CLASSES:
-        W = torch.randn(N, d, generator=g) * 0.05
-        X = torch.relu(torch.randn(m, d, generator=g))
-        delta = orc.layer_step_size(W, 1.16 / 8, 8, 1, None, 0.1)
-
-        def run(k):
-            Q = torch.zeros_like(W)
-            U = torch.zeros(N, m)
-            t0 = time.perf_counter()
-            orc.greedy_path(W, Q, U, X, X, orc.msq, delta, 8, 0.0, steps=k)
-            return time.perf_counter() - t0
-
-        run(1)                                  # touch pages / warm caches
-        k0 = 2
-        dt0 = run(k0)
-        k = int(min(d, max(k0, seconds_per_class / (dt0 / k0))))
-        dt = run(k)
-        spent += dt0 + dt
-        rates[m] = N * m * k / dt
-    ms = sorted(rates)
-    total_units = 0.0
-    total_time = 0.0
-    for (N, d, m, groups) in shapes:
-        nearest = min(ms, key=lambda c: abs(np.log(c / m)))
-        units = float(N) * d * m
-        total_units += units
-        total_time += units / rates[nearest]
-    return total_units / total_time, spent, total_time
-
-
-def cpu_forward_sample(model_name, batch, image=224):
-    """The reference re-runs the analog and the quantized network from the image up to layer i for every layer i
-    (quantize_neural_net.py:256-269).  Times ONE full fp32 forward of the model on the host cores at the bench's
-    batch size and scales it by sum_i(conv/linear flops before layer i) / (flops of the whole network), twice
-    (two networks).  Returns (extrapolated seconds per quantize_network(), seconds spent, full-forward seconds,
-    full-forward equivalents per network)."""
-    from quantized_neural_nets_b200.utils import extract_layers
-    model = build_model(model_name)
-    layers = []
-    extract_layers(model, layers)
-    flops = {}
-
-    def hook(mod, args, out):
-        flops[mod] = 2.0 * out[0].numel() * mod.weight[0].numel()
-
-    handles = [l.register_forward_hook(hook) for l in layers]
-    x = torch.randn(batch, 3, image, image, generator=torch.Generator().manual_seed(4))
-    with torch.no_grad():
-        model(x[:2])
-        for h in handles:
-            h.remove()
-        t0 = time.perf_counter()
-        model(x)
-        full = time.perf_counter() - t0
-    total = sum(flops[l] for l in layers)
-    before, equiv = 0.0, 0.0
-    for l in layers:
-        equiv += before / total
-        before += flops[l]
-    return 2.0 * equiv * full, full, full, equiv
-
-
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """``--impl reference``: the reference's own CPU implementation of the path on the box's host cores (the
+    UNMODIFIED reference from oracle/_ref when oracle/make_ref.py has vendored it, else the oracle port), every step
+    a bounded sample of the workload (oracle/cpu_baseline.py).  Rank 0 alone works; nothing of the product is
+    imported."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    model = build_model(args.model)
-    shapes = layer_shapes(model, args.batch, args.retain)
-    cores = torch.get_num_threads()
-    for _ in range(args.warmup):
-        cpu_reference_sample(shapes, seconds_per_class=0.3)
+    os.environ.setdefault("TQDM_DISABLE", "1")
+    from oracle import cpu_baseline as cb
+    cores = cb.host_threads()
+    _, _, extract_layers, kind = cb.reference_modules()
+    shapes = cb.layer_shapes(cb.build_model(args.model), args.batch, args.retain, extract_layers)
     units = float(sum(N * d * m for (N, d, m, g) in shapes))
-    vals, times = [], []
-    for _ in range(args.steps):
-        v, spent, solver_s = cpu_reference_sample(shapes)
-        fwd_s, fwd_spent, full, equiv = cpu_forward_sample(args.model, args.batch)
-        vals.append(units / (solver_s + fwd_s))
-        times.append(spent + fwd_spent)
-    value = sum(vals) / len(vals)
-    sample = (f"oracle port of the reference on {cores} host threads (torch CPU, the reference's own ATen ops): greedy loop "
-              f"timed on the first k features of 9 layer shapes (one per calibration-row class) and extrapolated by "
-              f"N*d*m over the {len(shapes)} layers ({solver_s:.0f} s), plus its calibration forward passes: one full "
-              f"fp32 forward at bs={args.batch} ({full:.1f} s) x 2 networks x {equiv:.1f} full-forward equivalents "
-              f"of prefix passes ({fwd_s:.0f} s)")
+    for _ in range(args.warmup):       # cheap warm-up samples: short classes, an 8-image forward scaled to the batch
+        cb.sample_step(args.model, args.batch, args.retain, args.bits, shapes, seconds_per_class=0.05, forward_batch=8)
+    steps = [cb.sample_step(args.model, args.batch, args.retain, args.bits, shapes, seconds_per_class=args.cpu_class_seconds)
+             for _ in range(args.steps)]
+    seconds = sum(s["seconds"] for s in steps) / len(steps)
+    value = units / seconds
+    validation = cb.validate(batch=args.batch, retain=args.retain) if args.validate_cpu else None
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": cb.describe(steps[-1], cores, len(shapes), args.batch),
+            "sampling_ms_per_step": 1e3 * sum(s["spent"] for s in steps) / len(steps)}
+    if validation is not None:
+        base["validation"] = validation
     print(json.dumps({
-        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * seconds, "ms_per_step_note": "implied by value (extrapolated from the bounded sample), "
+        "not the sampling time", "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args), "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -458,19 +384,24 @@ def run_cuda_arm(args):
             out["other_forward_mode"] = {"mode": other, "ms_per_step": other_ms / args.steps,
                                          "value": units / (other_ms / args.steps * 1e-3)}
         if world == 1 and not args.no_cpu_baseline:
-            v, spent, extrap = cpu_reference_sample(shapes)
-            fwd_s, fwd_spent, full, equiv = cpu_forward_sample(args.model, args.batch)
-            out["cpu_baseline"] = {
-                "value": units / (extrap + fwd_s), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                "solver_only_value": v,
-                "sample": f"oracle port of the reference (torch CPU, same ATen ops): greedy loop on the first k features "
-                          f"of 9 layer shapes, {spent:.1f} s of CPU work, extrapolated by N*d*m to the {len(shapes)} "
-                          f"layers ({extrap:.0f} s), plus the reference's per-layer prefix forward passes: one full fp32 "
-                          f"forward at bs={args.batch} timed ({full:.1f} s) x 2 networks x {equiv:.1f} full-forward "
-                          f"equivalents ({fwd_s:.0f} s)"}
+            out["cpu_baseline"] = cpu_baseline_leg(args, shapes, units)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    return out
+
+
+def cpu_baseline_leg(args, shapes, units):
+    """``cpu_baseline`` of the CUDA arm's line (rank 0, N = 1): one bounded sample of the reference on the host cores
+    (oracle/cpu_baseline.py) and, unless --no-validate-cpu, the measured-vs-extrapolated check against one complete
+    real reference run (AlexNet)."""
+    from oracle import cpu_baseline as cb
+    cores = cb.host_threads()
+    step = cb.sample_step(args.model, args.batch, args.retain, args.bits, shapes, seconds_per_class=args.cpu_class_seconds)
+    out = {"value": units / step["seconds"], "unit": UNIT, "cores": cores, "kind": step["kind"],
+           "solver_only_value": units / step["solver_s"], "sample": cb.describe(step, cores, len(shapes), args.batch)}
+    if args.validate_cpu:
+        out["validation"] = cb.validate(batch=args.batch, retain=args.retain)
     return out
 
 
@@ -521,6 +452,11 @@ def main():
                     help="keep cuDNN for the stride-1 1x1 convolutions of the calibration forward instead of one "
                          "strided-batched cuBLAS SGEMM each (gpfq_conv1x1_f32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-validate-cpu", dest="validate_cpu", action="store_false",
+                    help="skip the one complete real-reference run (AlexNet, about a minute of host time) that checks the "
+                         "CPU arm's sampled-and-extrapolated figure")
+    ap.add_argument("--cpu-class-seconds", type=float, default=0.3,
+                    help="CPU arm: seconds of greedy-loop sampling per layer-shape class and step")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="warm up, then run ONE step between cudaProfilerStart/Stop and exit (for ncu launch lists)")
     args = ap.parse_args()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GPFQ_ABI_VERSION 5
+#define GPFQ_ABI_VERSION 6
 
 /* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0'),
  * :7-35 (STOCHASTIC, SGPFQ: stochastic rounding to the two neighbouring grid points, then clipping; the
@@ -64,12 +64,12 @@ int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int3
 /* Packed low-bit export of a quantized layer (the reference stores fp32 values that lie on the alphabet,
  * quantize_neural_net.py:163,193; main.py:127-131 saves them as fp32).  A weight is one of the 2K+1 values
  * delta*{-K..K} (MSQ / SOFT / STOCHASTIC) or of the 2K+3 values {0, +-(lam + k*delta), k = 0..K} (HARD), so it is
- * stored as a code of gpfq_packed_bits(K, mode) = ceil(log2(count)) bits; 8 consecutive codes occupy that many
- * bytes, little-endian, so `packed` holds ceil(n/8) * bits bytes.
+ * stored as a code of gpfq_packed_bits(K, mode) = ceil(log2(count)) bits (at most 16: K <= 32766; 0 = unsupported K);
+ * 8 consecutive codes occupy that many bytes, little-endian, so `packed` holds ceil(n/8) * bits bytes.
  *   gpfq_pack_levels_f32: Q (n fp32 alphabet values) -> packed; *n_off_alphabet (device) receives the number of
  *     entries that are NOT exactly on the alphabet (they are stored as level 0); 0 means the export is lossless.
  *   gpfq_unpack_levels_f32: packed -> Q (fp32, bit-identical to what the solver wrote, up to the sign of zero)
- *     and / or int8 signed level indices (either may be NULL). */
+ *     and / or int8 signed level indices (either may be NULL; `levels` needs K <= 127, 126 for HARD). */
 int32_t gpfq_packed_bits(int32_t K, int32_t mode);
 int gpfq_pack_levels_f32(const float* Q, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
                          uint8_t* packed, uint32_t* n_off_alphabet, void* stream);
@@ -113,7 +113,8 @@ int gpfq_gram_path_f32(const float* W, int64_t ldw, int32_t N, int32_t d, int32_
 /* The greedy path-following solve: replaces StepAlgorithm._quantization
  * (step_algorithm.py:107-148) plus the residual norms of _quantize_layer (:216-219) for
  * neurons [n0, n1) of W.
- *   W (N x d, ldw), X / Xq feature-major (d x ldx), *delta on device, K = 2^(bits-1); seed is used by
+ *   W (N x d, ldw), X / Xq feature-major (d x ldx), *delta on device, K = 2^(bits-1) in [1, 32768] (the reference
+ *   has no bound, quantize_neural_net.py:87-88; only the int8 `levels` output needs K <= 127, 126 for HARD); seed is used by
  *   GPFQ_MODE_STOCHASTIC only (same seed => same Q whatever the neuron range or solver structure).
  *   Q (N x d, ldq): rows n0..n1-1 written (fp32 alphabet values, as the reference stores them).
  *   levels: optional int8 (N x d, ld = d) signed level indices, rows n0..n1-1 (may be NULL).

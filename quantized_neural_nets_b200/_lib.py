@@ -78,8 +78,36 @@ def require_cuda(*tensors):
             raise TypeError(f"expected a CUDA float32 tensor, got {t.device} {t.dtype}")
 
 
-def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch(fn, *args):
+    """Call one stream-ordered entry point of the library.  Tensor arguments are passed as device pointers (None as
+    NULL); the device they live on -- all of them must share it -- is made current for the call, and that device's
+    current stream is appended as the trailing ``stream`` argument.  The C side (cudaFuncSetAttribute, occupancy
+    queries, tensor maps, launches) works on the CURRENT device, so without this a tensor on cuda:1 in a process
+    whose current device is cuda:0 would be launched on the wrong GPU; the reference takes a ``device`` argument and
+    works on any device without set_device."""
+    device = None
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise TypeError(f"libgpfq_b200: expected CUDA tensors, got one on {a.device}")
+            if device is None:
+                device = a.device
+            elif a.device != device:
+                raise ValueError(f"libgpfq_b200: tensors on different devices ({device} and {a.device}) in one call")
+            conv.append(ctypes.c_void_p(a.data_ptr()))
+        elif a is None:
+            conv.append(ctypes.c_void_p(0))
+        else:
+            conv.append(a)
+    if device is None:
+        raise ValueError("libgpfq_b200: a launch needs at least one tensor argument")
+    with torch.cuda.device(device):
+        check(fn(*conv, stream_ptr(device)))
 
 
 def ptr(t):

@@ -157,7 +157,7 @@ __global__ void pack_levels_kernel(const float* __restrict__ q, int64_t n, const
     const float delta = *delta_p;
     const int64_t groups = (n + 7) / 8;
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long word = 0;
+        unsigned __int128 word = 0;                              // 8 codes of up to 16 bits
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t e = g * 8 + i;
@@ -172,7 +172,7 @@ __global__ void pack_levels_kernel(const float* __restrict__ q, int64_t n, const
                     code = offset;
                 }
             }
-            word |= (unsigned long long)code << (i * nbits);
+            word |= (unsigned __int128)(unsigned)code << (i * nbits);
         }
         for (int b = 0; b < nbits; ++b) out[g * nbits + b] = (uint8_t)(word >> (8 * b));
     }
@@ -185,8 +185,8 @@ __global__ void unpack_levels_kernel(const uint8_t* __restrict__ in, int64_t n, 
     const int64_t groups = (n + 7) / 8;
     const unsigned mask = (1u << nbits) - 1u;
     for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long word = 0;
-        for (int b = 0; b < nbits; ++b) word |= (unsigned long long)in[g * nbits + b] << (8 * b);
+        unsigned __int128 word = 0;
+        for (int b = 0; b < nbits; ++b) word |= (unsigned __int128)in[g * nbits + b] << (8 * b);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t e = g * 8 + i;
@@ -358,6 +358,9 @@ int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta,
     return 0;
 }
 
+// codes are at most 16 bits wide: levels -top..top with top = K (+1 for the L0 alphabet) <= 32767
+constexpr int kMaxPackK = 32766;
+
 static int level_layout(int32_t K, int32_t mode, int* offset, int* nbits) {
     const int top = (mode == GPFQ_MODE_HARD) ? K + 1 : K;       // levels are -top .. top
     int b = 1;
@@ -368,7 +371,7 @@ static int level_layout(int32_t K, int32_t mode, int* offset, int* nbits) {
 }
 
 int32_t gpfq_packed_bits(int32_t K, int32_t mode) {
-    if (K < 1 || K > 126 || mode < 0 || mode > 3) return 0;
+    if (K < 1 || K > kMaxPackK || mode < 0 || mode > 3) return 0;
     int offset, nbits;
     level_layout(K, mode, &offset, &nbits);
     return nbits;
@@ -376,7 +379,7 @@ int32_t gpfq_packed_bits(int32_t K, int32_t mode) {
 
 int gpfq_pack_levels_f32(const float* Q, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
                          uint8_t* packed, uint32_t* n_off_alphabet, void* stream) {
-    GPFQ_REQUIRE(n >= 0 && K >= 1 && K <= 126 && mode >= 0 && mode <= 3, "gpfq_pack_levels_f32: bad size/K/mode");
+    GPFQ_REQUIRE(n >= 0 && K >= 1 && K <= kMaxPackK && mode >= 0 && mode <= 3, "gpfq_pack_levels_f32: bad size/K/mode");
     GPFQ_REQUIRE(n_off_alphabet != nullptr, "gpfq_pack_levels_f32: n_off_alphabet is required");
     GPFQ_CUDA_TRY(cudaMemsetAsync(n_off_alphabet, 0, sizeof(uint32_t), (cudaStream_t)stream));
     if (n == 0) return 0;
@@ -391,7 +394,9 @@ int gpfq_pack_levels_f32(const float* Q, int64_t n, const float* delta, int32_t 
 
 int gpfq_unpack_levels_f32(const uint8_t* packed, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
                            float* Q, int8_t* levels, void* stream) {
-    GPFQ_REQUIRE(n >= 0 && K >= 1 && K <= 126 && mode >= 0 && mode <= 3, "gpfq_unpack_levels_f32: bad size/K/mode");
+    GPFQ_REQUIRE(n >= 0 && K >= 1 && K <= kMaxPackK && mode >= 0 && mode <= 3, "gpfq_unpack_levels_f32: bad size/K/mode");
+    GPFQ_REQUIRE(levels == nullptr || K + (mode == GPFQ_MODE_HARD ? 1 : 0) <= 127,
+                 "gpfq_unpack_levels_f32: int8 level indices need K <= 127 (126 for the L0 alphabet); got K=%d", K);
     GPFQ_REQUIRE(Q != nullptr || levels != nullptr, "gpfq_unpack_levels_f32: no output requested");
     if (n == 0) return 0;
     int offset, nbits;

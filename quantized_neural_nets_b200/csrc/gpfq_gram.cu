@@ -20,7 +20,9 @@
 namespace gpfq {
 
 constexpr int kGB = 32;   // features per recurrence block (= warp size)
-constexpr int kGramMaxD = 3328;   // w,q rows of 8 neurons (1 per warp) must fit in shared memory
+// w,q rows of 8 neurons (1 per warp) plus the four 32 x 33 fp64 tiles must fit in 227 KB of shared memory:
+// 64 * round_up(d, 32) + 33792 <= 232448  <=>  d <= 3104
+constexpr int kGramMaxD = 3104;
 
 int gram_tc_form(const float* X, const float* Xq, int64_t ldx, int d, int m, double* GT, double* H, double* A,
                  int64_t ldg, void* scratch, size_t scratch_bytes, cudaStream_t stream);

@@ -21,6 +21,10 @@ int gram_matrices(int solver, const float* X, const float* Xq, int64_t ldx, int 
 
 using namespace gpfq;
 
+// K = 2^(bits-1) (quantize_neural_net.py:87-88); the reference has no bound.  The kernels carry K as an fp32 value
+// and the level as an int, so any K that fp32 counts exactly works; 2^15 (16-bit alphabets) is what is tested.
+constexpr int kMaxK = 32768;
+
 extern "C" {
 
 size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m) {
@@ -44,7 +48,9 @@ int gpfq_gram_path_f32(const float* W, int64_t ldw, int32_t N, int32_t d, int32_
                        uint64_t seed, float* Q, int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2,
                        void* stream) {
     GPFQ_REQUIRE(N >= 0 && d > 0 && 0 <= n0 && n0 <= n1 && n1 <= N, "gpfq_gram_path_f32: bad shape or neuron range");
-    GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_STOCHASTIC && K >= 1 && K <= 127, "gpfq_gram_path_f32: bad mode or K");
+    GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_STOCHASTIC && K >= 1 && K <= kMaxK, "gpfq_gram_path_f32: bad mode or K");
+    GPFQ_REQUIRE(levels == nullptr || K + (mode == GPFQ_MODE_HARD ? 1 : 0) <= 127,
+                 "gpfq_gram_path_f32: the int8 `levels` output needs K <= 127 (126 for the L0 alphabet); got K=%d", K);
     GPFQ_REQUIRE(ldw >= d && ldq >= d && ldg >= (d + 31) / 32 * 32, "gpfq_gram_path_f32: leading dimension too small");
     if (n0 == n1) return 0;
     GPFQ_REQUIRE(W && GT && H && A && delta && Q, "gpfq_gram_path_f32: null pointer");
@@ -60,7 +66,9 @@ int gpfq_solve_f32(int32_t solver, const float* W, int64_t ldw, const float* X, 
     GPFQ_REQUIRE(N >= 0 && d >= 0 && m >= 0, "gpfq_solve_f32: negative dimension");
     GPFQ_REQUIRE(0 <= n0 && n0 <= n1 && n1 <= N, "gpfq_solve_f32: bad neuron range [%d, %d) of %d", n0, n1, N);
     GPFQ_REQUIRE(mode >= GPFQ_MODE_MSQ && mode <= GPFQ_MODE_STOCHASTIC, "gpfq_solve_f32: bad mode %d", mode);
-    GPFQ_REQUIRE(K >= 1 && K <= 127, "gpfq_solve_f32: boundary index K=%d outside [1,127]", K);
+    GPFQ_REQUIRE(K >= 1 && K <= kMaxK, "gpfq_solve_f32: boundary index K=%d outside [1,%d]", K, kMaxK);
+    GPFQ_REQUIRE(levels == nullptr || K + (mode == GPFQ_MODE_HARD ? 1 : 0) <= 127,
+                 "gpfq_solve_f32: the int8 `levels` output needs K <= 127 (126 for the L0 alphabet); got K=%d", K);
     GPFQ_REQUIRE(ldw >= d && ldq >= d, "gpfq_solve_f32: ldw/ldq smaller than d");
     GPFQ_REQUIRE(ldx >= m && (ldx % 4) == 0, "gpfq_solve_f32: ldx must be >= m and a multiple of 4");
     GPFQ_REQUIRE(U_out == nullptr || ldu >= m, "gpfq_solve_f32: ldu smaller than m");

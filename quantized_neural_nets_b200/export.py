@@ -10,7 +10,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import lib, check, ptr, stream_ptr, require_cuda
+from ._lib import lib, launch, require_cuda
 from .step_algorithm import mode_of
 
 
@@ -50,8 +50,7 @@ def pack_layer(Q, delta, boundary_idx, reg=None, lamb=0.0, stochastic_quantizati
     delta_dev = torch.as_tensor(delta, dtype=torch.float32).reshape(()).to(Q.device)
     codes = torch.empty(((n + 7) // 8) * bits, dtype=torch.uint8, device=Q.device)
     bad = torch.zeros(1, dtype=torch.int32, device=Q.device)
-    check(lib.gpfq_pack_levels_f32(ptr(Qc), n, ptr(delta_dev), int(boundary_idx), mode, lam, ptr(codes), ptr(bad),
-                                   stream_ptr()))
+    launch(lib.gpfq_pack_levels_f32, Qc, n, delta_dev, int(boundary_idx), mode, lam, codes, bad)
     n_bad = int(bad.item())
     if n_bad:
         raise ValueError(f"{n_bad} of {n} weights are not on the alphabet (delta={float(delta_dev):.6g}, "
@@ -68,8 +67,8 @@ def unpack_layer(packed, want_levels=False):
     n = packed.numel
     Q = torch.empty(packed.shape, dtype=torch.float32, device=dev)
     levels = torch.empty(packed.shape, dtype=torch.int8, device=dev) if want_levels else None
-    check(lib.gpfq_unpack_levels_f32(ptr(packed.codes), n, ptr(packed.delta.to(dev)), packed.boundary_idx, mode,
-                                     packed.lamb, ptr(Q), ptr(levels), stream_ptr()))
+    launch(lib.gpfq_unpack_levels_f32, packed.codes, n, packed.delta.to(dev), packed.boundary_idx, mode, packed.lamb, Q,
+           levels)
     return (Q, levels) if want_levels else Q
 
 

@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ._lib import lib, check, ptr, stream_ptr
+from ._lib import lib, launch
 
 _INF = math.inf
 
@@ -62,8 +62,7 @@ class FusedBNAct(nn.Module):
         alpha, beta = self._coefficients()
         B, C, H, W = x.shape
         out = torch.empty_like(x)
-        check(lib.gpfq_bn_act_f32(ptr(x), ptr(residual), ptr(alpha), ptr(beta), ptr(out), B * C, C, H * W, self.lo, self.hi,
-                                  stream_ptr()))
+        launch(lib.gpfq_bn_act_f32, x, residual, alpha, beta, out, B * C, C, H * W, self.lo, self.hi)
         return out
 
 
@@ -158,7 +157,7 @@ def _pointwise_forward(mod, x):
         return nn.Conv2d.forward(mod, x)
     B, C, H, W = x.shape
     out = torch.empty((B, mod.out_channels, H, W), dtype=torch.float32, device=x.device)
-    check(lib.gpfq_conv1x1_f32(ptr(x), ptr(mod.weight), ptr(out), B, C, mod.out_channels, H * W, stream_ptr()))
+    launch(lib.gpfq_conv1x1_f32, x, mod.weight, out, B, C, mod.out_channels, H * W)
     return out
 
 

@@ -18,14 +18,19 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import lib, check, ptr, stream_ptr, require_cuda
+from ._lib import lib, launch, require_cuda
 from .sharding import neuron_slice, gather_layer, gather_inputs, world_and_rank
+from . import step_algorithm as _sa
 from .step_algorithm import (quantize_layer_impl, reduce_errors, row_radius, delta_from_radii,
                              gram_reduce_eligible, feature_major)
 from .utils import InterruptException, extract_layers
 
 LINEAR_MODULE_TYPE = nn.Linear
 CONV2D_MODULE_TYPE = nn.Conv2d
+
+# {(id(analog layer), world size, total calibration rows): bool} -- verdict of the per-layer parity gate of the
+# Gram-reduce mode of the sharded calibration forward (QuantizeNeuralNet._gate_gram_reduce)
+_GRAM_REDUCE_GATE = {}
 
 
 def _default_group():
@@ -123,8 +128,7 @@ class SaveInputConv2d:
         ld = (m + 3) // 4 * 4
         feats = C * kh * kw
         out = torch.empty((feats, ld), dtype=torch.float32, device=x.device)
-        check(lib.gpfq_im2col_gather_f32(ptr(x), B, C, H, W, kh, kw, dh, dw, ph, pw, 0, C,
-                                         ptr(self._idx_dev), m, ptr(out), ld, stream_ptr()))
+        launch(lib.gpfq_im2col_gather_f32, x, B, C, H, W, kh, kw, dh, dw, ph, pw, 0, C, self._idx_dev, m, out, ld)
         return out[:, :m].t()
 
 
@@ -183,6 +187,7 @@ class QuantizeNeuralNet:
         # and the Gram formation is divided by the world size).
         self.gram_reduce = gram_reduce
         self._rows_split = False
+        self._gate_pending = None
         # 'fresh' (reference behaviour, :234): a new loader batch and two forward passes from the image for EVERY
         # layer, O(L^2) layer evaluations.  'reuse' (SURVEY.md section 8f rank 1): ONE batch calibrates all layers --
         # one pass of the analog network records every layer's input, then one pass of the quantized network
@@ -373,12 +378,23 @@ class QuantizeNeuralNet:
                 t.record_stream(side)              # keep their memory alive until the side stream is done
         with torch.cuda.stream(stream):
             with self._Phase(self, layer_idx, 'solve'):
-                Q, err2, ref2 = quantize_layer_impl(W, X, Xq, m, step, K, pct, self.reg, self.lamb, groups,
-                                                    self.stochastic_quantization, self.device,
-                                                    neuron_range=(n0, n1), solver=self.solver, return_partials=True,
-                                                    delta=delta,
-                                                    rows_split_over=((self.process_group or _default_group())
-                                                                     if self._rows_split else None))
+                common = dict(neuron_range=(n0, n1), return_partials=True, delta=delta)
+                if self._gate_pending is not None:
+                    # first sight of a layer the sharded forward wants to solve from all-reduced Gram matrices: X / Xq
+                    # are the all-gathered inputs; solve with the DIRECT solver (the result that is kept), solve again
+                    # from the all-reduced Gram matrices of the local rows, and keep the Gram-reduce mode for this layer
+                    # only if every rank reproduces >= 99.9 % of the direct levels (one MIN all-reduce: the decision
+                    # must be identical on all ranks because it selects which collectives later steps issue)
+                    Q, err2, ref2 = quantize_layer_impl(W, X, Xq, m, step, K, pct, self.reg, self.lamb, groups,
+                                                        self.stochastic_quantization, self.device,
+                                                        solver=_lib.SOLVER_DIRECT, **common)
+                    self._gate_gram_reduce(layer, W, Q, n0, n1, step, K, pct, groups, delta)
+                else:
+                    Q, err2, ref2 = quantize_layer_impl(W, X, Xq, m, step, K, pct, self.reg, self.lamb, groups,
+                                                        self.stochastic_quantization, self.device, solver=self.solver,
+                                                        rows_split_over=((self.process_group or _default_group())
+                                                                         if self._rows_split else None),
+                                                        layer_key=id(layer), **common)
             done = torch.cuda.Event()
             done.record(stream)
         return layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side
@@ -511,6 +527,7 @@ class QuantizeNeuralNet:
         """With a sharded calibration forward X / X~ hold this rank's calibration rows: either all-gather them,
         or leave them split and let the solve all-reduce the layer's Gram matrices instead."""
         self._rows_split = False
+        self._gate_pending = None
         if sharded:
             layer = self.analog_network_layers[layer_idx]
             world, _ = world_and_rank(self.process_group)
@@ -519,8 +536,29 @@ class QuantizeNeuralNet:
             m_total = X.shape[0] * world
             if self.gram_reduce and getattr(layer, 'groups', 1) == 1 and gram_reduce_eligible(N, d, m_total) \
                     and not self.stochastic_quantization:
-                self._rows_split = True          # the solve exchanges Gram matrices instead (see _launch_solve)
-                return X, Xq
+                verdict = _GRAM_REDUCE_GATE.get((id(layer), world, m_total))
+                if verdict is True:
+                    self._rows_split = True      # the solve exchanges Gram matrices instead (see _launch_solve)
+                    return X, Xq
+                if verdict is None:              # not yet verified on this layer: see _launch_solve
+                    self._gate_pending = (X, Xq, (id(layer), world, m_total))
             with self._Phase(self, layer_idx, 'gather_inputs'):
                 return gather_inputs(X, Xq, self.process_group)
         return X, Xq
+
+    def _gate_gram_reduce(self, layer, W, Q_direct, n0, n1, step, K, pct, groups, delta):
+        """Per-LAYER parity gate of the Gram-reduce mode (run once per layer, during warm-up)."""
+        import torch.distributed as dist
+        X_local, Xq_local, key = self._gate_pending
+        self._gate_pending = None
+        group = self.process_group or _default_group()
+        Qg, _, _ = quantize_layer_impl(W, X_local, Xq_local, X_local.shape[0], step, K, pct, self.reg, self.lamb, groups,
+                                       self.stochastic_quantization, self.device, neuron_range=(n0, n1),
+                                       return_partials=True, delta=delta, rows_split_over=group)
+        same = (Qg[n0:n1] == Q_direct[n0:n1]).float().mean() if n1 > n0 else torch.ones((), device=self.device)
+        agree = same.reshape(1).clone()
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=group)
+        agree = float(agree.item())
+        _GRAM_REDUCE_GATE[key] = agree >= _sa.GATE
+        _sa.AUTO_LOG.append((("gram_reduce", W.shape[0], W.shape[1], key[2]), {}, agree,
+                             "gram_reduce" if _GRAM_REDUCE_GATE[key] else "gather_inputs"))

@@ -21,13 +21,22 @@ def rows_per_rank(N, world):
 
 
 def neuron_slice(N, groups=1, group=None, world=None, rank=None):
-    """Contiguous [n0, n1) of the N output neurons owned by this rank (empty for trailing ranks
-    when N < world).  Slices may cut through conv groups; the solver intersects them per group."""
+    """Contiguous [n0, n1) of the N output neurons owned by this rank (empty for trailing ranks when there are
+    fewer units than ranks).  For a grouped convolution the unit is a whole conv group (N/groups neurons): the
+    batched grouped solver needs whole groups, and SURVEY.md section 8e partitions grouped layers that way."""
     if world is None:
         world, rank = _world(group)
-    per = rows_per_rank(N, world)
+    unit = N // groups if groups > 1 and N % groups == 0 else 1
+    units = N // unit
+    per = rows_per_rank(units, world) * unit
     n0 = min(rank * per, N)
     return n0, min(n0 + per, N)
+
+
+def slice_rows(N, groups, world):
+    """Rows per rank of ``neuron_slice`` (the all-gather's per-rank buffer height)."""
+    unit = N // groups if groups > 1 and N % groups == 0 else 1
+    return rows_per_rank(N // unit, world) * unit
 
 
 def pack_slice(Q, err2, ref2, n0, n1, per):
@@ -59,7 +68,7 @@ def gather_layer(Q, err2, ref2, n0, n1, groups=1, group=None):
     if world == 1:
         return Q, err2, ref2
     N, d = Q.shape
-    per = rows_per_rank(N, world)
+    per = slice_rows(N, groups, world)
     mine = pack_slice(Q, err2, ref2, n0, n1, per)
     full = torch.empty((world * per, d + 4), dtype=torch.float32, device=Q.device)
     dist.all_gather_into_tensor(full, mine, group=group)

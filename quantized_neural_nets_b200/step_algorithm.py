@@ -10,7 +10,7 @@ relative-error denominators (step_algorithm.py:217,219)."""
 import torch
 
 from . import _lib
-from ._lib import lib, check, ptr, stream_ptr, require_cuda
+from ._lib import lib, launch, require_cuda
 
 # solver used by _quantization/_quantize_layer: _lib.SOLVER_DIRECT or _lib.SOLVER_GRAM
 DEFAULT_SOLVER = _lib.SOLVER_DIRECT
@@ -35,8 +35,7 @@ def _elementwise(mode, step_size, x, boundary_idx, lamb, seed=0):
     xc = x.contiguous()
     out = torch.empty_like(xc)
     delta = _delta_tensor(step_size, x.device)
-    check(lib.gpfq_quantize_f32(ptr(xc), ptr(out), xc.numel(), ptr(delta), int(boundary_idx), mode, float(lamb),
-                                int(seed), stream_ptr()))
+    launch(lib.gpfq_quantize_f32, xc, out, xc.numel(), delta, int(boundary_idx), mode, float(lamb), int(seed))
     return out
 
 
@@ -53,7 +52,7 @@ def feature_major(X):
     ld = (m + 3) // 4 * 4
     out = torch.empty((d, ld), dtype=torch.float32, device=X.device)
     Xc = X if X.stride(1) == 1 else X.contiguous()
-    check(lib.gpfq_transpose_f32(ptr(Xc), m, d, Xc.stride(0), ptr(out), ld, stream_ptr()))
+    launch(lib.gpfq_transpose_f32, Xc, m, d, Xc.stride(0), out, ld)
     return out, ld
 
 
@@ -79,22 +78,31 @@ def solve_rows(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, want_err=T
     if nbytes == 0:
         raise RuntimeError(f"libgpfq_b200: solver {solver} does not support a (d={d}, m={m}) layer")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    check(lib.gpfq_solve_f32(solver, ptr(W), W.stride(0), ptr(Xfm), ptr(Xqfm), ldx, N, d, m, n0, n1, ptr(delta),
-                             int(K), mode, float(lamb), int(seed), ptr(Q), Q.stride(0), ptr(levels), ptr(row_err2),
-                             ptr(row_ref2), ptr(U), m, ptr(ws), nbytes, stream_ptr()))
+    launch(lib.gpfq_solve_f32, solver, W, W.stride(0), Xfm, Xqfm, ldx, N, d, m, n0, n1, delta, int(K), mode, float(lamb),
+           int(seed), Q, Q.stride(0), levels, row_err2, row_ref2, U, m, ws, nbytes)
     if want_residual and gram:      # the Gram solvers never form U; rebuild it only when somebody asks for it
         U = torch.matmul(W[n0:n1], Xfm[:, :m]) - torch.matmul(Q[n0:n1], Xqfm[:, :m])
     return row_err2, U, row_ref2
 
 
 # ---------------------------------------------------------------------------------------------
-# per-layer solver choice "from measured time" (BASELINE.json north_star): the first time a
-# (rows, d, m, mode) shape is seen with solver='auto', every eligible solver is run once on the real
-# data and timed with CUDA events; a Gram candidate is kept only if it is faster AND reproduces at
-# least 99.9 % of the direct solver's levels on that layer.  The choice is cached for the process.
+# per-layer solver choice "from measured time" (BASELINE.json north_star): the first time a LAYER is seen
+# with solver='auto' (key: the caller's ``layer_key`` -- the orchestrator passes the identity of the analog layer
+# module -- plus (rows, d, m, mode); without a layer_key the key is the shape alone), every eligible solver is
+# run once on the layer's real data and timed with CUDA events; a Gram candidate is kept only if it is faster
+# AND reproduces at least 99.9 % of the direct solver's levels ON THAT LAYER.  The choice is cached for the
+# process, so the gate is measured once per layer (during warm-up), not once per shape.
 AUTO = "auto"
+GATE = 0.999
 _AUTO_CHOICE = {}
 AUTO_LOG = []          # (key, {solver: ms}, agreement, chosen) for reports
+
+
+def min_gated_agreement():
+    """Smallest level agreement (vs the direct solver, on the layer's own data) among the layers for which a Gram
+    variant was CHOSEN; 1.0 when none was."""
+    picked = [ag for (k, tm, ag, ch) in AUTO_LOG if ch not in (_lib.SOLVER_DIRECT, "groups_loop", "gather_inputs")]
+    return min(picked) if picked else 1.0
 
 
 def gram_eligible(rows, d, m):
@@ -124,7 +132,7 @@ def _auto_pick(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, candidates, s
         if sv == _lib.SOLVER_DIRECT:
             continue
         agree = float((results[sv] == base).float().mean())
-        if agree >= 0.999 and times[sv] < times[best]:
+        if agree >= GATE and times[sv] < times[best]:
             best, agree_best = sv, agree
     return best, times, agree_best
 
@@ -140,11 +148,11 @@ def _time_call(fn):
     return a.elapsed_time(b), out
 
 
-def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, seed=0):
+def resolve_solver(solver, W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, n0, n1, seed=0, layer_key=None):
     if solver != AUTO:
         return DEFAULT_SOLVER if solver is None else solver
     rows, d = n1 - n0, W.shape[1]
-    key = (rows, d, m, mode)
+    key = (rows, d, m, mode) if layer_key is None else (rows, d, m, mode, layer_key)
     if key not in _AUTO_CHOICE:
         candidates = [_lib.SOLVER_DIRECT]
         if gram_eligible(rows, d, m):
@@ -186,9 +194,8 @@ def solve_grouped(W, Xfm, Xqfm, ldx, m, delta, K, mode, lamb, Q, n0, n1, groups,
     if nbytes == 0:
         raise RuntimeError(f"libgpfq_b200: the grouped solver does not support d_group={dg}")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    check(lib.gpfq_solve_grouped_f32(ptr(W), W.stride(0), ptr(Xfm), ptr(Xqfm), ldx, N, dg, m, groups, n0, n1,
-                                     ptr(delta), int(K), mode, float(lamb), int(seed), ptr(Q), Q.stride(0), ptr(levels),
-                                     ptr(row_err2), ptr(row_ref2), ptr(ws), nbytes, stream_ptr()))
+    launch(lib.gpfq_solve_grouped_f32, W, W.stride(0), Xfm, Xqfm, ldx, N, dg, m, groups, n0, n1, delta, int(K), mode,
+           float(lamb), int(seed), Q, Q.stride(0), levels, row_err2, row_ref2, ws, nbytes)
     return row_err2, row_ref2
 
 
@@ -203,29 +210,49 @@ def gram_reduce_eligible(N, d, m_total):
     return m_total >= 2 * d and (d <= 512 or (d <= 1024 and N >= 2 * d))
 
 
-def solve_rows_gram_reduced(W, Xfm_local, Xqfm_local, ldx, m_local, delta, K, mode, lamb, Q, n0, n1, group, seed=0):
-    """Gram solver over calibration rows that are SPLIT over the ranks of ``group``: every rank forms the Gram
-    matrices of its own rows on the tensor cores, one all-reduce (fp64, 3*d*d values) sums them, then the rank
-    runs the recurrence for its neuron slice.  Returns (row_err2, row_ref2) for neurons [n0, n1)."""
-    import torch.distributed as dist
-    N, d = W.shape
-    dev = W.device
+def local_gram_matrices(Xfm_local, Xqfm_local, ldx, d, m_local):
+    """(3, ldg, ldg) fp64: GT = X Xq^T, H = Xq Xq^T, A = X X^T of THIS rank's calibration rows, formed on the tensor
+    cores (gpfq_gram_f32, split-TF32)."""
     ldg = (d + 63) // 64 * 64
-    grams = torch.empty((3, ldg, ldg), dtype=torch.float64, device=dev)
+    grams = torch.empty((3, ldg, ldg), dtype=torch.float64, device=Xfm_local.device)
     nbytes = lib.gpfq_workspace_bytes(_lib.SOLVER_GRAM, 1, d, m_local)
     if nbytes == 0:
         raise RuntimeError(f"libgpfq_b200: the Gram solver does not support d={d}")
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    check(lib.gpfq_gram_f32(_lib.SOLVER_GRAM, ptr(Xfm_local), ptr(Xqfm_local), ldx, d, m_local, ptr(grams[0]),
-                            ptr(grams[1]), ptr(grams[2]), ptr(ws), nbytes, stream_ptr()))
-    dist.all_reduce(grams, group=group)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=Xfm_local.device)
+    launch(lib.gpfq_gram_f32, _lib.SOLVER_GRAM, Xfm_local, Xqfm_local, ldx, d, m_local, grams[0], grams[1], grams[2], ws,
+           nbytes)
+    return grams
+
+
+def solve_rows_from_grams(W, grams, delta, K, mode, lamb, Q, n0, n1, seed=0, levels=None):
+    """The Gram-form recurrence for neurons [n0, n1) from GIVEN (3, ldg, ldg) Gram matrices (gpfq_gram_path_f32).
+    Returns (row_err2, row_ref2)."""
+    N, d = W.shape
     rows = n1 - n0
-    e2 = torch.zeros(rows, dtype=torch.float64, device=dev)
-    r2 = torch.zeros(rows, dtype=torch.float64, device=dev)
-    check(lib.gpfq_gram_path_f32(ptr(W), W.stride(0), N, d, n0, n1, ptr(grams[0]), ptr(grams[1]), ptr(grams[2]), ldg,
-                                 ptr(delta), int(K), mode, float(lamb), int(seed), ptr(Q), Q.stride(0), None, ptr(e2),
-                                 ptr(r2), stream_ptr()))
+    e2 = torch.zeros(rows, dtype=torch.float64, device=W.device)
+    r2 = torch.zeros(rows, dtype=torch.float64, device=W.device)
+    if rows > 0:
+        launch(lib.gpfq_gram_path_f32, W, W.stride(0), N, d, n0, n1, grams[0], grams[1], grams[2], grams.shape[2], delta,
+               int(K), mode, float(lamb), int(seed), Q, Q.stride(0), levels, e2, r2)
     return e2, r2
+
+
+def all_reduce_sum(group):
+    """The reducer of a real multi-GPU run: one in-place fp64 all-reduce over ``group``."""
+    def reduce(grams):
+        import torch.distributed as dist
+        dist.all_reduce(grams, group=group)
+        return grams
+    return reduce
+
+
+def solve_rows_gram_reduced(W, Xfm_local, Xqfm_local, ldx, m_local, delta, K, mode, lamb, Q, n0, n1, reduce, seed=0):
+    """Gram solver over calibration rows that are SPLIT over ranks: every rank forms the Gram matrices of its own
+    rows on the tensor cores, ``reduce`` (a callable: local (3, ldg, ldg) fp64 tensor -> the sum over all ranks; in a
+    real run ``all_reduce_sum(group)``, in the single-GPU parity test a serial sum over emulated shards) adds them
+    up, then the rank runs the recurrence for its neuron slice.  Returns (row_err2, row_ref2) for neurons [n0, n1)."""
+    grams = reduce(local_gram_matrices(Xfm_local, Xqfm_local, ldx, W.shape[1], m_local))
+    return solve_rows_from_grams(W, grams, delta, K, mode, lamb, Q, n0, n1, seed)
 
 
 class StepAlgorithm:
@@ -277,6 +304,10 @@ class StepAlgorithm:
                                 want_err=False, want_residual=True, seed=seed)
         if Qc is not Q:
             Q.copy_(Qc)
+        # the reference accumulates into the U it is handed, which is always zeros (step_algorithm.py:196); the CUDA
+        # solver starts from a zero residual, so any other U is rejected instead of being silently overwritten
+        if bool(U.any()):
+            raise NotImplementedError("_quantization expects the zero-initialised U of the reference's call sites")
         U.copy_(Ures)
 
     # ------------------------------------------------------------------ one layer
@@ -337,7 +368,8 @@ def mode_of(reg, stochastic_quantization):
 
 def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, lamb, groups,
                         stochastic_quantization, device, want_adder=False, neuron_range=None, levels=None,
-                        solver=None, return_partials=False, delta=None, seed=None, rows_split_over=None):
+                        solver=None, return_partials=False, delta=None, seed=None, rows_split_over=None,
+                        layer_key=None):
     """Shared body of ``StepAlgorithm._quantize_layer`` and of the sharded orchestrator.
 
     neuron_range=(n0, n1) restricts the solve to a contiguous slice of output neurons (rows
@@ -371,8 +403,8 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
         # X / Xq hold only this rank's calibration rows (m of them); the ranks of the group exchange Gram matrices
         if groups != 1 or want_adder:
             raise ValueError("rows_split_over supports ungrouped layers without the adder output")
-        e2, r2 = solve_rows_gram_reduced(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Q, n0, n1,
-                                         rows_split_over, seed)
+        reducer = rows_split_over if callable(rows_split_over) else all_reduce_sum(rows_split_over)
+        e2, r2 = solve_rows_gram_reduced(Wc, Xfm, Xqfm, ldx, m, delta, boundary_idx, mode, lamb, Q, n0, n1, reducer, seed)
         err2[n0:n1], ref2[n0:n1] = e2, r2
         return (Q, err2, ref2) if return_partials else (Q,) + reduce_errors(err2, ref2, groups, None)
     n_per_group = N // groups
@@ -403,7 +435,8 @@ def quantize_layer_impl(W, X, Xq, m, step_size, boundary_idx, percentile, reg, l
             continue
         Xg = Xfm[g * d:(g + 1) * d]
         Xqg = Xqfm[g * d:(g + 1) * d]
-        sv = resolve_solver(loop_solver, Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, g0, g1, seed)
+        sv = resolve_solver(loop_solver, Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, g0, g1, seed,
+                            layer_key if groups == 1 else None)
         e2, Ures, r2 = solve_rows(Wc, Xg, Xqg, ldx, m, delta, boundary_idx, mode, lamb, Q, g0, g1,
                                   want_err=True, want_residual=(want_adder and groups == 1), levels=levels,
                                   solver=sv, want_ref=True, seed=seed)

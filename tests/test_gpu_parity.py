@@ -223,7 +223,7 @@ def test_auto_solver_picks_from_measured_time(qb):
 
 def test_gram_matrices_tcgen05_accuracy(qb):
     """The tensor-core Gram kernel (TMA + tcgen05.mma kind::tf32 x3 + TMEM ping-pong) against float64."""
-    from quantized_neural_nets_b200._lib import lib, check, ptr, stream_ptr
+    from quantized_neural_nets_b200._lib import lib, launch
     d, m = 200, 5000      # not multiples of the 128 x 128 x 32 tile
     g = torch.Generator(device=DEV).manual_seed(0)
     ld = (m + 3) // 4 * 4
@@ -234,8 +234,7 @@ def test_gram_matrices_tcgen05_accuracy(qb):
         nbytes = lib.gpfq_workspace_bytes(solver, 1, d, m)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
         out = [torch.zeros((ldg, ldg), dtype=torch.float64, device=DEV) for _ in range(3)]
-        check(lib.gpfq_gram_f32(solver, ptr(X), ptr(Xq), ld, d, m, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(ws), nbytes,
-                                stream_ptr()))
+        launch(lib.gpfq_gram_f32, solver, X, Xq, ld, d, m, out[0], out[1], out[2], ws, nbytes)   # straight through the C ABI
         Xd, Xqd = X[:, :m].double(), Xq[:, :m].double()
         for got, want in zip(out, (Xd @ Xqd.T, Xqd @ Xqd.T, Xd @ Xd.T)):
             rel = ((got[:d, :d] - want).norm() / want.norm()).item()

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(dll, name), f"{name} declared in gpfq_b200.h but not exported"
     assert declared == set(L.SIGNATURES), "ctypes binding and header disagree"
-    assert L.lib.gpfq_abi_version() == 5
+    assert L.lib.gpfq_abi_version() == 6
 
 
 def test_workspace_and_argument_validation_without_gpu():
@@ -81,6 +81,21 @@ def test_neuron_slices_partition():
             for r in range(world):
                 n0, n1 = neuron_slice(N, 1, world=world, rank=r)
                 assert 0 <= n0 <= n1 <= N
+                cover += list(range(n0, n1))
+            assert cover == list(range(N))
+
+
+def test_neuron_slices_of_grouped_layers_cover_whole_groups():
+    """Grouped convolutions are partitioned by whole conv groups (the batched grouped solver
+    rejects ranges that cut a group)."""
+    from quantized_neural_nets_b200.sharding import neuron_slice, slice_rows
+    for N, groups in ((96, 3), (960, 960), (64, 4), (30, 5), (24, 2)):
+        per_group = N // groups
+        for world in (1, 2, 3, 4, 8):
+            cover = []
+            for r in range(world):
+                n0, n1 = neuron_slice(N, groups, world=world, rank=r)
+                assert n0 % per_group == 0 and n1 % per_group == 0 and n1 - n0 <= slice_rows(N, groups, world)
                 cover += list(range(n0, n1))
             assert cover == list(range(N))
 

@@ -4,7 +4,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from quantized_neural_nets_b200 import _lib
-from quantized_neural_nets_b200._lib import lib, check, ptr, stream_ptr
+from quantized_neural_nets_b200._lib import lib, launch
 
 d, m = int(sys.argv[1]), int(sys.argv[2])
 solvers = [int(s) for s in sys.argv[3:]] or [2, 1]
@@ -22,7 +22,7 @@ for sv in solvers:
     out = [torch.full((ldg, ldg), float("nan"), dtype=torch.float64, device=dev) for _ in range(3)]
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        check(lib.gpfq_gram_f32(sv, ptr(X), ptr(Xq), ld, d, m, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(ws), nbytes, stream_ptr()))
+        launch(lib.gpfq_gram_f32, sv, X, Xq, ld, d, m, out[0], out[1], out[2], ws, nbytes)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     flops = 2.0 * d * d * m * 3
     line = f"solver {sv} d={d} m={m}: {dt*1e3:.3f} ms ({flops/dt/1e12:.1f} algorithmic TFLOP/s, workspace {nbytes/1e6:.0f} MB)"
