@@ -54,12 +54,24 @@ int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta,
 int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, const float* beta, float* out,
                     int64_t planes, int32_t C, int32_t HW, float lo, float hi, void* stream);
 
-/* Calibration-forward helper: a stride-1 1x1 convolution (no bias, groups = 1) of a contiguous NCHW tensor,
- * out[b] (N x HW) = W (N x C) @ x[b] (C x HW), as ONE cublasSgemmStridedBatched with a zero batch stride for W
- * (fp32 SIMT SGEMM, default math mode: no TF32).  The library-GEMM form of what F.conv2d does for these layers inside the
- * reference's forward passes (quantize_neural_net.py:256-269). */
+/* Calibration-forward helpers: the stride-1 1x1 convolutions (no bias, groups = 1) of a contiguous NCHW tensor, which
+ * are the bulk of the forward passes of quantize_neural_net.py:256-269 for the bottleneck networks.
+ *   gpfq_conv1x1_bn_act_f32:  out[b] (N x HW) = clamp((W (N x C) @ x[b] (C x HW)) * alpha[n] + beta[n] (+ residual[b]), lo, hi)
+ *     -- the convolution, the inference BatchNorm2d that follows it, the optional residual add and the optional
+ *     ReLU / ReLU6 in ONE kernel: tcgen05 tensor cores in split-TF32 (three MMAs per product, a fresh TMEM accumulator
+ *     per 32 channels summed in fp32 registers with round-to-nearest: fp32-SGEMM accuracy, no TF32 rounding of the result),
+ *     epilogue arithmetic as gpfq_bn_act_f32.  alpha / beta may both be NULL (no affine map), residual may be NULL,
+ *     lo = -inf / hi = +inf switch the clamps off.  Needs HW % 4 == 0 (gpfq_conv1x1_fused_supported) and a workspace
+ *     of gpfq_conv1x1_workspace_bytes(N, C) bytes, 256-byte aligned (the TF32 planes of W).
+ *   gpfq_conv1x1_f32: the plain convolution; the same kernel when the shape allows it and a workspace is given, else ONE
+ *     cublasSgemmStridedBatched with a zero batch stride for W (fp32 SIMT SGEMM, default math mode: no TF32). */
+size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C);
+int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW);
+int gpfq_conv1x1_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha, const float* beta,
+                            float* out, int32_t B, int32_t C, int32_t N, int32_t HW, float lo, float hi, void* workspace,
+                            size_t workspace_bytes, void* stream);
 int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
-                     void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Packed low-bit export of a quantized layer (the reference stores fp32 values that lie on the alphabet,
  * quantize_neural_net.py:163,193; main.py:127-131 saves them as fp32).  A weight is one of the 2K+1 values

@@ -1,10 +1,13 @@
-// Stride-1 1x1 convolution of an NCHW tensor as ONE strided-batched library SGEMM (calibration-forward helper).
+// C ABI of the stride-1 1x1 convolution (calibration-forward helper): the tcgen05 split-TF32 kernel of
+// gpfq_conv1x1_tc.cu wherever it applies (HW % 4 == 0), and for the remaining shapes (the 7 x 7 planes of ResNet's last
+// stage) ONE strided-batched library SGEMM:
 //
 // out[b] (N x HW) = W (N x C) @ x[b] (C x HW) for every image b.  PyTorch reaches cuBLAS for this product only through
 // torch.bmm, which first materialises the batch-broadcast weight (256 copies of W; measured 17 ms of copy kernels per
 // ResNet-50 forward); cublasSgemmStridedBatched takes the weight with a batch stride of ZERO.  Plain fp32 SIMT SGEMM
 // (no TF32): cuBLAS is used here as a library GEMM, nothing else.
 #include <cublas_v2.h>
+#include <math.h>
 
 #include <map>
 #include <mutex>
@@ -30,13 +33,18 @@ static cublasHandle_t handle_for_current_device() {
 
 }  // namespace gpfq
 
+namespace gpfq {
+size_t conv1x1_tc_workspace_bytes(int N, int C);
+bool conv1x1_tc_supported(int C, int N, int HW);
+int conv1x1_tc(const float* x, const float* W, float* out, const float* residual, const float* alpha, const float* beta,
+               float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream);
+}  // namespace gpfq
+
 using namespace gpfq;
 
-extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
-                                void* stream) {
-    GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && HW >= 1, "gpfq_conv1x1_f32: bad shape");
-    GPFQ_REQUIRE(x && W && out, "gpfq_conv1x1_f32: null pointer");
-    if (B == 0) return 0;
+static int conv1x1_cublas(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
+                          void* stream) {
     cublasHandle_t h = handle_for_current_device();
     GPFQ_REQUIRE(h != nullptr, "gpfq_conv1x1_f32: cublasCreate failed");
     GPFQ_REQUIRE(cublasSetStream(h, (cudaStream_t)stream) == CUBLAS_STATUS_SUCCESS, "gpfq_conv1x1_f32: cublasSetStream failed");
@@ -47,4 +55,38 @@ extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int3
     GPFQ_REQUIRE(st == CUBLAS_STATUS_SUCCESS, "gpfq_conv1x1_f32: cublasSgemmStridedBatched failed with status %d", (int)st);
     count_launch();
     return 0;
+}
+
+extern "C" size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C) {
+    if (N < 1 || C < 1) return 0;
+    return conv1x1_tc_workspace_bytes(N, C);
+}
+
+extern "C" int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW) {
+    return conv1x1_tc_supported(C, N, HW) ? 1 : 0;
+}
+
+extern "C" int gpfq_conv1x1_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha,
+                                       const float* beta, float* out, int32_t B, int32_t C, int32_t N, int32_t HW, float lo,
+                                       float hi, void* workspace, size_t workspace_bytes, void* stream) {
+    GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && HW >= 1, "gpfq_conv1x1_bn_act_f32: bad shape");
+    GPFQ_REQUIRE(x && W && out && workspace, "gpfq_conv1x1_bn_act_f32: null pointer");
+    GPFQ_REQUIRE((alpha == nullptr) == (beta == nullptr), "gpfq_conv1x1_bn_act_f32: alpha and beta go together");
+    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW),
+                 "gpfq_conv1x1_bn_act_f32: HW = %d is not a multiple of 4 (ask gpfq_conv1x1_fused_supported first)", HW);
+    if (B == 0) return 0;
+    return conv1x1_tc(x, W, out, residual, alpha, beta, lo, hi, B, C, N, HW, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && HW >= 1, "gpfq_conv1x1_f32: bad shape");
+    GPFQ_REQUIRE(x && W && out, "gpfq_conv1x1_f32: null pointer");
+    if (B == 0) return 0;
+    static const bool force_cublas = getenv("GPFQ_CONV1X1_CUBLAS") && atoi(getenv("GPFQ_CONV1X1_CUBLAS")) == 1;
+    if (!force_cublas && workspace != nullptr && conv1x1_tc_supported(C, N, HW))
+        return conv1x1_tc(x, W, out, nullptr, nullptr, nullptr, -INFINITY, INFINITY, B, C, N, HW, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+    return conv1x1_cublas(x, W, out, B, C, N, HW, stream);       // 7 x 7 planes (HW % 4 != 0): plain library SGEMM
 }

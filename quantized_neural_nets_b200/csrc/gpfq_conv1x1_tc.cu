@@ -1,0 +1,431 @@
+// Stride-1 1x1 convolution of an NCHW activation on the 5th-generation tensor cores, fused with the inference
+// BatchNorm (+ residual add) (+ ReLU / ReLU6) that follows it in the calibration forward:
+//
+//     out[b] (N x HW) = clamp( (W (N x C) @ x[b] (C x HW)) * alpha[n] + beta[n] (+ residual[b]), lo, hi )
+//
+// These layers are the bulk of the forward passes the reference prescribes (quantize_neural_net.py:256-269 re-runs both
+// networks from the image for every layer; with the solver on the GPU that is 97 % of a step).  fp32 accuracy is kept
+// by the split-TF32 scheme of gram_tc_kernel: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), three MMAs per
+// product (lo*hi, hi*lo, hi*hi), and -- because the tensor core accumulates fp32 with truncation -- a FRESH TMEM
+// accumulator per 32-channel k-block that the epilogue warps add up in registers with round-to-nearest.
+//
+// Structure (one persistent CTA per SM, 320 threads, tiles of 128 output channels x 128 pixels of one image):
+//   warp 0      TMA producer: per k-block the weight planes w_hi / w_lo (boxes [128][32], SWIZZLE_128B, K-major) and the
+//               RAW fp32 activation (four boxes [32 channels][32 pixels], SWIZZLE_128B_ATOM_32B: the B operand is
+//               MN-major -- the pixel index is the contiguous one in NCHW), 3-stage ring that runs on across tiles;
+//   warps 6-9   split: turn the raw activation tile into its TF32 hi plane in place and the lo plane next to it (an
+//               elementwise map, so the swizzled layout is untouched), fence.proxy.async, release the MMA warp --
+//               the activation is read from HBM exactly once;
+//   warp 1      single-thread tcgen05.mma issue, 12 MMAs (M = N = 128, K = 8, kind::tf32) per k-block into one of FOUR
+//               128-column TMEM accumulators (all 512 columns): the MMAs run up to four k-blocks ahead of the drain;
+//   warps 2-5   drain each finished accumulator (tcgen05.ld 32x32b) into 128 fp32 registers per thread (thread = output
+//               channel, register = pixel) and, after the tile's last k-block, apply alpha / beta / residual / clamp and
+//               store the row segment.  While they store, the MMA warp is already working on the next tile.
+//
+// The MN-major recipe (validated on B200 in round 1, experimental/conv1x1_tf32x3.cu): for 32-bit operands the only
+// MN-major shared-memory layout UMMA accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1), written by TMA with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; LBO = bytes between 32-pixel chunks (one box, 4096), SBO = 512 (a swizzle
+// atom is 4 channel rows of 128 bytes), +1024 bytes per K = 8 step, instruction-descriptor bit 16 (B is MN-major).
+//
+// Shapes: HW % 4 == 0 (TMA global strides are multiples of 16 bytes); any C (the channel tail of a k-block is zero-filled
+// by TMA on both operands) and any N.  Other shapes return GPFQ_CONV_UNSUPPORTED and the caller uses another path.
+#include <algorithm>
+
+#include "gpfq_common.cuh"
+
+namespace gpfq {
+
+namespace {
+
+constexpr int kTM = 128;            // output channels per tile (UMMA M)
+constexpr int kTN = 128;            // pixels per tile (UMMA N)
+constexpr int kBK = 32;             // channels per k-block
+constexpr int kPx = 32;             // pixels per activation box = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kAccs = 4;            // TMEM accumulators of kTN columns
+constexpr int kATile = kTM * kBK;   // floats per weight plane tile (16 KB)
+constexpr int kBTile = kBK * kTN;   // floats per activation plane tile (16 KB) = 4 boxes [32 ch][32 px]
+constexpr int kStageFloats = 2 * kATile + 2 * kBTile;      // w_hi | w_lo | x_hi (raw on arrival) | x_lo
+constexpr int kThreads = 320;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageFloats * sizeof(float) + 256;
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major tile (weights): rows of 128 bytes, SWIZZLE_128B, 8-row atoms 1024 bytes apart (SBO); LBO unused.
+__device__ __forceinline__ uint64_t desc_k_major(const void* tile) {
+    const uint32_t addr = smem_u32(tile);
+    uint64_t desc = 0;
+    desc |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    desc |= (uint64_t)1 << 16;
+    desc |= (uint64_t)(1024 >> 4) << 32;
+    desc |= (uint64_t)1 << 46;
+    desc |= (uint64_t)2 << 61;
+    return desc;
+}
+// MN-major tile (activation): [32-pixel chunk][channel row][32 pixels = 128 bytes], SWIZZLE_128B_BASE32B (layout type 1),
+// LBO = bytes between pixel chunks (one TMA box of kBK rows = 4096), SBO = bytes between 4-row swizzle atoms (512).
+__device__ __forceinline__ uint64_t desc_mn_major(const void* tile) {
+    const uint32_t addr = smem_u32(tile);
+    uint64_t desc = 0;
+    desc |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    desc |= (uint64_t)((kBK * kPx * 4) >> 4) << 16;
+    desc |= (uint64_t)(512 >> 4) << 32;
+    desc |= (uint64_t)1 << 46;
+    desc |= (uint64_t)1 << 61;
+    return desc;
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// D = F32, A = B = TF32, A K-major, B MN-major (bit 16), N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(kTN >> 3) << 17) |
+                            ((uint32_t)(kTM >> 4) << 24);
+
+struct ConvArgs {
+    float* out;              // (B, N, HW)
+    const float* residual;   // (B, N, HW) or null
+    const float* alpha;      // (N) or null (then no affine map)
+    const float* beta;       // (N)
+    float lo, hi;
+    int C, N, HW, B;
+    int n_tiles, p_tiles, total_tiles;
+};
+
+// hi = rna_tf32(w), lo = rna_tf32(w - hi) of the (N x C) weight, rows padded with zeros to Cp columns
+__global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, int Cp, float* __restrict__ hi,
+                                    float* __restrict__ lo) {
+    const int64_t n = (int64_t)N * Cp;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / Cp;
+        const int c = (int)(e % Cp);
+        const float v = c < C ? W[r * C + c] : 0.f;
+        const float h = to_tf32(v);
+        hi[e] = h;
+        lo[e] = to_tf32(v - h);
+    }
+}
+
+// tmWh / tmWl: (N x Cp) planes, box [128][32], SWIZZLE_128B.  tmX: RAW activation as (HW, C, B), box (32, 32, 1),
+// SWIZZLE_128B_ATOM_32B; channels beyond C and pixels beyond HW arrive as zeros.
+__global__ void __launch_bounds__(kThreads, 1)
+conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                  const __grid_constant__ CUtensorMap tmX, const ConvArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageFloats * sizeof(float));
+    uint64_t* split = full + kStages;
+    uint64_t* empty = split + kStages;
+    uint64_t* acc_full = empty + kStages;
+    uint64_t* acc_empty = acc_full + kAccs;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccs);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = (a.C + kBK - 1) / kBK;
+    const int my_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 4);           // one arrival per split warp
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < kAccs; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);       // one arrival per drain warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kAccs * kTN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile index -> (image, pixel tile, channel tile): channel tiles of one activation tile are adjacent in the
+    // schedule, so CTAs that run side by side share the activation tile through L2
+    auto tile_coords = [&](int i, int& img, int& p0, int& n0) {
+        const int t = (int)blockIdx.x + i * (int)gridDim.x;
+        const int nt = t % a.n_tiles;
+        const int rest = t / a.n_tiles;
+        n0 = nt * kTM;
+        p0 = (rest % a.p_tiles) * kTN;
+        img = rest / a.p_tiles;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                int img, p0, n0;
+                tile_coords(i, img, p0, n0);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
+                    float* st = tiles + (size_t)s * kStageFloats;
+                    mbar_expect_tx(&full[s], (uint32_t)((2 * kATile + kBTile) * sizeof(float)));
+                    const int c0 = kb * kBK;
+                    tma_load_2d(st, &tmWh, c0, n0, &full[s]);
+                    tma_load_2d(st + kATile, &tmWl, c0, n0, &full[s]);
+#pragma unroll
+                    for (int j = 0; j < kTN / kPx; ++j)
+                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx, c0, img, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const int total = my_tiles * nkb;
+            for (int it = 0; it < total; ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (uint32_t)((it / kStages) & 1);
+                const int b = it % kAccs;
+                mbar_wait(&acc_empty[b], (uint32_t)(((it / kAccs) & 1) ^ 1));
+                mbar_wait(&full[s], ph);       // weight planes (TMA)
+                mbar_wait(&split[s], ph);      // activation planes (split warps)
+                tc_fence_after();
+                const float* st = tiles + (size_t)s * kStageFloats;
+                const uint64_t d_wh = desc_k_major(st), d_wl = desc_k_major(st + kATile);
+                const uint64_t d_xh = desc_mn_major(st + 2 * kATile);
+                const uint64_t d_xl = desc_mn_major(st + 2 * kATile + kBTile);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(b * kTN);
+#pragma unroll
+                for (int k8 = 0; k8 < kBK / 8; ++k8) {
+                    const uint64_t adv_a = (uint64_t)((k8 * 8 * sizeof(float)) >> 4);     // 32 bytes along K
+                    const uint64_t adv_b = (uint64_t)((k8 * 1024) >> 4);                  // 8 channel rows
+                    umma_tf32(d_tmem, d_wl + adv_a, d_xh + adv_b, kIdesc, k8 > 0);
+                    umma_tf32(d_tmem, d_wh + adv_a, d_xl + adv_b, kIdesc, 1);
+                    umma_tf32(d_tmem, d_wh + adv_a, d_xh + adv_b, kIdesc, 1);
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&acc_full[b]);
+            }
+        }
+    } else if (warp >= 6) {
+        // split warps: raw fp32 (written by TMA) -> hi in place, lo next to it
+        const int t = threadIdx.x - 6 * 32;        // 0 .. 127
+        const int total = my_tiles * nkb;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % kStages;
+            mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+            float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats + 2 * kATile);
+            float4* lo = hi + kBTile / 4;
+#pragma unroll
+            for (int i = 0; i < kBTile / 4 / 128; ++i) {
+                const float4 v = hi[t + 128 * i];
+                float4 h, l;
+                h.x = to_tf32(v.x); l.x = to_tf32(v.x - h.x);
+                h.y = to_tf32(v.y); l.y = to_tf32(v.y - h.y);
+                h.z = to_tf32(v.z); l.z = to_tf32(v.z - h.z);
+                h.w = to_tf32(v.w); l.w = to_tf32(v.w - h.w);
+                hi[t + 128 * i] = h;
+                lo[t + 128 * i] = l;
+            }
+            fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[s]);
+        }
+    } else {
+        const int quad = warp & 3;                 // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
+        const int row = quad * 32 + lane;          // output channel within the tile
+        const bool vec_ok = true;                  // HW % 4 == 0 on this path
+        (void)vec_ok;
+        int it = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            int img, p0, n0;
+            tile_coords(i, img, p0, n0);
+            float run[kTN];
+#pragma unroll
+            for (int c = 0; c < kTN; ++c) run[c] = 0.f;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int b = it % kAccs;
+                mbar_wait(&acc_full[b], (uint32_t)((it / kAccs) & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < kTN; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + c0), v);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) run[c0 + e] = __fadd_rn(run[c0 + e], v[e]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[b]);
+            }
+            const int n = n0 + row;
+            if (n < a.N) {
+                const bool affine = a.alpha != nullptr;
+                const float al = affine ? a.alpha[n] : 1.f, be = affine ? a.beta[n] : 0.f;
+                const size_t base = ((size_t)img * a.N + n) * a.HW + p0;
+                float* dst = a.out + base;
+                const float* res = a.residual ? a.residual + base : nullptr;
+                const float lo = a.lo, hi = a.hi;
+#pragma unroll
+                for (int c = 0; c < kTN; c += 4) {
+                    if (p0 + c < a.HW) {           // HW % 4 == 0: a float4 is entirely inside or outside the row
+                        float4 v = make_float4(run[c], run[c + 1], run[c + 2], run[c + 3]);
+                        if (affine) {
+                            v.x = __fadd_rn(__fmul_rn(v.x, al), be);
+                            v.y = __fadd_rn(__fmul_rn(v.y, al), be);
+                            v.z = __fadd_rn(__fmul_rn(v.z, al), be);
+                            v.w = __fadd_rn(__fmul_rn(v.w, al), be);
+                        }
+                        if (res) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(res + c));
+                            v.x = __fadd_rn(v.x, r.x); v.y = __fadd_rn(v.y, r.y);
+                            v.z = __fadd_rn(v.z, r.z); v.w = __fadd_rn(v.w, r.w);
+                        }
+                        v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
+                        v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
+                        *reinterpret_cast<float4*>(dst + c) = v;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kAccs * kTN);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// fp32 tensor map of `rank` dimensions; dims / box are innermost first, strides (bytes) for dimensions 1..rank-1
+int make_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+             const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+    EncodeTiledFn fn = encode_fn();
+    GPFQ_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available (driver too old?)");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GPFQ_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
+    return 0;
+}
+
+int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v;
+    }();
+    return n;
+}
+
+}  // namespace
+
+size_t conv1x1_tc_workspace_bytes(int N, int C) { return (size_t)2 * N * round_up(C, kBK) * sizeof(float) + 256; }
+
+bool conv1x1_tc_supported(int C, int N, int HW) { return C >= 1 && N >= 1 && HW >= 4 && HW % 4 == 0; }
+
+int conv1x1_tc(const float* x, const float* W, float* out, const float* residual, const float* alpha, const float* beta,
+               float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream) {
+    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW), "conv1x1_tc: unsupported shape");
+    GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C), "conv1x1_tc: workspace too small");
+    GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                     ((uintptr_t)residual & 15) == 0,
+                 "conv1x1_tc: workspace must be 256-byte aligned, tensors 16-byte aligned");
+    const int Cp = (int)round_up(C, kBK);
+    float* w_hi = (float*)workspace;
+    float* w_lo = w_hi + (size_t)N * Cp;
+    const int64_t n_w = (int64_t)N * Cp;
+    split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
+    GPFQ_CHECK_LAUNCH();
+
+    CUtensorMap tmWh, tmWl, tmX;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cp, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)Cp * sizeof(float)};
+        cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTM};
+        if (int rc = make_map(&tmWh, w_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        if (int rc = make_map(&tmWl, w_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)C * HW * sizeof(float)};
+        cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kBK, 1};
+        if (int rc = make_map(&tmX, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    }
+    ConvArgs a{};
+    a.out = out; a.residual = residual; a.alpha = alpha; a.beta = beta; a.lo = lo; a.hi = hi;
+    a.C = C; a.N = N; a.HW = HW; a.B = B;
+    a.n_tiles = (int)ceil_div(N, kTM);
+    a.p_tiles = (int)ceil_div(HW, kTN);
+    const int64_t total = (int64_t)a.n_tiles * a.p_tiles * B;
+    GPFQ_REQUIRE(total < (1ll << 31), "conv1x1_tc: too many tiles");
+    a.total_tiles = (int)total;
+    if (int rc = ensure_dynamic_smem((const void*)conv1x1_tc_kernel, kSmemBytes)) return rc;
+    const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
+    profile_mark_begin(stream);
+    conv1x1_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, a);
+    if (profile_on())
+        profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
+                         2.0 * B * (double)HW * C * N, 3);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace gpfq

@@ -66,6 +66,51 @@ class FusedBNAct(nn.Module):
         return out
 
 
+def _is_pointwise(mod):
+    return (type(mod) is nn.Conv2d and mod.kernel_size == (1, 1) and mod.stride == (1, 1) and mod.padding == (0, 0)
+            and mod.dilation == (1, 1) and mod.groups == 1 and mod.padding_mode == 'zeros')
+
+
+def _conv_workspace(conv, device):
+    return torch.empty(lib.gpfq_conv1x1_workspace_bytes(conv.out_channels, conv.in_channels), dtype=torch.uint8, device=device)
+
+
+class FusedConv1x1BNAct(nn.Module):
+    """Stride-1 1x1 Conv2d -> inference BatchNorm2d (-> + residual) (-> clamp to [lo, hi]) as ONE tensor-core kernel
+    (gpfq_conv1x1_bn_act_f32: tcgen05 split-TF32 GEMM whose epilogue applies the batch norm, the residual add and the
+    activation, so the convolution's output never makes a round trip through HBM).  ``conv`` and ``bn`` are the wrapped
+    modules (not copied).  Whenever the convolution carries a hook (the layer whose input is being captured, or a
+    user's own hook), or the shape / dtype / layout is not the kernel's, the modules run as they are: ``conv(x)`` (so
+    its hooks fire exactly as in the plain network) followed by the fused elementwise pass."""
+
+    def __init__(self, conv, bn, lo=-_INF, hi=_INF):
+        super().__init__()
+        self.conv = conv
+        self.tail = FusedBNAct(bn, lo, hi)
+
+    def forward(self, x, residual=None):
+        conv, bn = self.conv, self.tail.bn
+        hooked = bool(conv._forward_hooks or conv._forward_pre_hooks)
+        patched = 'forward' in conv.__dict__ and getattr(conv.forward, '__func__', None) is not _pointwise_forward
+        fused = not hooked and not patched
+        fused = (fused and conv.bias is None and not bn.training and bn.track_running_stats and bn.running_mean is not None
+                 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.shape[0] > 0
+                 and conv.weight.is_contiguous() and conv.weight.dtype == torch.float32
+                 and (residual is None or (residual.dtype == x.dtype and residual.is_cuda and residual.is_contiguous()
+                                           and residual.shape == (x.shape[0], conv.out_channels) + x.shape[2:]))
+                 and lib.gpfq_conv1x1_fused_supported(x.shape[1], conv.out_channels, x.shape[2] * x.shape[3]))
+        if not fused:
+            return self.tail(conv(x), residual)
+        alpha, beta = self.tail._coefficients()
+        B, C, H, W = x.shape
+        N = conv.out_channels
+        out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
+        ws = _conv_workspace(conv, x.device)
+        launch(lib.gpfq_conv1x1_bn_act_f32, x, conv.weight, residual, alpha, beta, out, B, C, N, H * W, self.tail.lo,
+               self.tail.hi, ws, ws.numel())
+        return out
+
+
 def _activation_bounds(node, modules):
     """(lo, hi) if ``node`` is a ReLU / ReLU6 (module or functional), else None."""
     if node.op == 'call_module':
@@ -87,8 +132,10 @@ def _single_user(node):
     return users[0] if len(users) == 1 else None
 
 
-def fuse_inference_forward(network):
-    """-> (callable running ``network``'s forward with fused BatchNorm / add / ReLU, number of fused sites).
+def fuse_inference_forward(network, fuse_pointwise=True):
+    """-> (callable running ``network``'s forward with fused BatchNorm / add / ReLU, number of fused sites); with
+    ``fuse_pointwise`` a stride-1 1x1 convolution that feeds only the batch norm is folded into the same site
+    (FusedConv1x1BNAct; ``.fused_conv_sites`` of the returned module counts them).
     The callable shares every submodule with ``network``.  Raises whatever torch.fx raises if the network cannot
     be traced (data-dependent control flow); the caller then keeps the plain module."""
     from torch import fx
@@ -96,6 +143,7 @@ def fuse_inference_forward(network):
     modules = dict(gm.named_modules())
     graph = gm.graph
     sites = 0
+    conv_sites = 0
     for node in list(graph.nodes):
         if node.op != 'call_module' or type(modules.get(node.target)) is not nn.BatchNorm2d:
             continue
@@ -118,9 +166,20 @@ def fuse_inference_forward(network):
                     residual = user.args[1] if user.args[0] is node else user.args[0]
         name = f"_gpfq_fused_bn_{sites}"
         lo, hi = bounds if bounds is not None else (-_INF, _INF)
-        gm.add_submodule(name, FusedBNAct(bn, lo, hi))
+        # a stride-1 1x1 convolution feeding only this batch norm joins the fused site: conv + BN (+ add) (+ ReLU) in
+        # one tensor-core kernel
+        src = node.args[0]
+        conv_node = None
+        if (fuse_pointwise and isinstance(src, fx.Node) and src.op == 'call_module' and _is_pointwise(modules.get(src.target))
+                and modules[src.target].bias is None and len(src.users) == 1 and len(src.args) == 1 and not src.kwargs):
+            conv_node = src
+            gm.add_submodule(name, FusedConv1x1BNAct(modules[src.target], bn, lo, hi))
+            src = conv_node.args[0]
+            conv_sites += 1
+        else:
+            gm.add_submodule(name, FusedBNAct(bn, lo, hi))
         with graph.inserting_after(last):
-            args = (node.args[0],) if residual is None else (node.args[0], residual)
+            args = (src,) if residual is None else (src, residual)
             new = graph.call_module(name, args)
         last.replace_all_uses_with(new)
         # erase the replaced chain from its end backwards
@@ -130,9 +189,12 @@ def fuse_inference_forward(network):
             chain.append(prev[0])
         for dead in chain:
             graph.erase_node(dead)
+        if conv_node is not None:
+            graph.erase_node(conv_node)
         sites += 1
     graph.lint()
     gm.recompile()
+    gm.fused_conv_sites = conv_sites
     return gm, sites
 
 
@@ -146,18 +208,14 @@ def fuse_inference_forward(network):
 # gpfq_conv1x1_f32 = one cublasSgemmStridedBatched with a ZERO batch stride for W.
 # The Conv2d MODULES stay in place -- only their ``forward`` is overridden, on the instance, for the duration of
 # quantize_network() -- so forward hooks, pre-hooks and weight updates behave as before.
-def _is_pointwise(mod):
-    return (type(mod) is nn.Conv2d and mod.kernel_size == (1, 1) and mod.stride == (1, 1) and mod.padding == (0, 0)
-            and mod.dilation == (1, 1) and mod.groups == 1 and mod.padding_mode == 'zeros')
-
-
 def _pointwise_forward(mod, x):
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and mod.bias is None
             and mod.weight.is_contiguous()):
         return nn.Conv2d.forward(mod, x)
     B, C, H, W = x.shape
     out = torch.empty((B, mod.out_channels, H, W), dtype=torch.float32, device=x.device)
-    launch(lib.gpfq_conv1x1_f32, x, mod.weight, out, B, C, mod.out_channels, H * W)
+    ws = _conv_workspace(mod, x.device)
+    launch(lib.gpfq_conv1x1_f32, x, mod.weight, out, B, C, mod.out_channels, H * W, ws, ws.numel())
     return out
 
 
