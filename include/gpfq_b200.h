@@ -54,22 +54,30 @@ int gpfq_quantize_f32(const float* x, float* out, int64_t n, const float* delta,
 int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, const float* beta, float* out,
                     int64_t planes, int32_t C, int32_t HW, float lo, float hi, void* stream);
 
-/* Calibration-forward helpers: the stride-1 1x1 convolutions (no bias, groups = 1) of a contiguous NCHW tensor, which
- * are the bulk of the forward passes of quantize_neural_net.py:256-269 for the bottleneck networks.
+/* Calibration-forward helpers: convolutions (no bias, groups = 1) of a contiguous NCHW tensor on the tensor cores.  The
+ * forward passes of quantize_neural_net.py:256-269 are 97 % of a step once the solver runs on the GPU.
  *   gpfq_conv1x1_bn_act_f32:  out[b] (N x HW) = clamp((W (N x C) @ x[b] (C x HW)) * alpha[n] + beta[n] (+ residual[b]), lo, hi)
- *     -- the convolution, the inference BatchNorm2d that follows it, the optional residual add and the optional
- *     ReLU / ReLU6 in ONE kernel: tcgen05 tensor cores in split-TF32 (three MMAs per product, a fresh TMEM accumulator
- *     per 32 channels summed in fp32 registers with round-to-nearest: fp32-SGEMM accuracy, no TF32 rounding of the result),
- *     epilogue arithmetic as gpfq_bn_act_f32.  alpha / beta may both be NULL (no affine map), residual may be NULL,
- *     lo = -inf / hi = +inf switch the clamps off.  Needs HW % 4 == 0 (gpfq_conv1x1_fused_supported) and a workspace
- *     of gpfq_conv1x1_workspace_bytes(N, C) bytes, 256-byte aligned (the TF32 planes of W).
- *   gpfq_conv1x1_f32: the plain convolution; the same kernel when the shape allows it and a workspace is given, else ONE
- *     cublasSgemmStridedBatched with a zero batch stride for W (fp32 SIMT SGEMM, default math mode: no TF32). */
+ *     -- a 1x1 convolution, the inference BatchNorm2d that follows it, the optional residual add and the optional
+ *     ReLU / ReLU6 in ONE kernel: tcgen05 tensor cores in split-TF32 (three MMAs per product, four when C <= 128; a
+ *     fresh TMEM accumulator per 32 channels summed in fp32 registers with round-to-nearest: fp32-SGEMM accuracy, no
+ *     TF32 rounding of the result), epilogue arithmetic as gpfq_bn_act_f32.  x is (B, C, x_ld) with x_ld >= HW the
+ *     pixel pitch in floats, a multiple of 4 (TMA strides); out / residual are contiguous (B, N, HW), any HW.
+ *     alpha / beta may both be NULL (no affine map), residual may be NULL, lo = -inf / hi = +inf switch the clamps
+ *     off.  Workspace: gpfq_conv1x1_workspace_bytes(N, C) bytes, 256-byte aligned (the TF32 planes of W).
+ *   gpfq_conv_patches_f32: the patch matrix of a convolution with its own stride / padding / dilation,
+ *     out (B, C*kh*kw, ld) with ld >= Ho*Wo (pad columns zeroed), row order (c, ki, kj) = weight.view(N, -1); feeding
+ *     it to gpfq_conv1x1_bn_act_f32 (x_ld = ld, C = C*kh*kw, HW = Ho*Wo) evaluates ANY convolution on the tensor
+ *     cores; a 1x1 kernel with stride 2 is a strided gather, with stride 1 a copy that pads the row pitch to a
+ *     multiple of 4 (7 x 7 planes).
+ *   gpfq_conv1x1_f32: the plain stride-1 1x1 convolution; the same kernel when HW % 4 == 0 and a workspace is given, else
+ *     ONE cublasSgemmStridedBatched with a zero batch stride for W (fp32 SIMT SGEMM, default math mode: no TF32). */
 size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C);
-int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW);
-int gpfq_conv1x1_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha, const float* beta,
-                            float* out, int32_t B, int32_t C, int32_t N, int32_t HW, float lo, float hi, void* workspace,
-                            size_t workspace_bytes, void* stream);
+int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW, int64_t x_ld);
+int gpfq_conv1x1_bn_act_f32(const float* x, int64_t x_ld, const float* W, const float* residual, const float* alpha,
+                            const float* beta, float* out, int32_t B, int32_t C, int32_t N, int32_t HW, float lo, float hi,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int gpfq_conv_patches_f32(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw, int32_t sh,
+                          int32_t sw, int32_t ph, int32_t pw, int32_t dh, int32_t dw, float* out, int64_t ld, void* stream);
 int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
                      void* workspace, size_t workspace_bytes, void* stream);
 

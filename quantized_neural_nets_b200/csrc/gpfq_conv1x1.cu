@@ -9,6 +9,7 @@
 #include <cublas_v2.h>
 #include <math.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -35,10 +36,37 @@ static cublasHandle_t handle_for_current_device() {
 
 namespace gpfq {
 size_t conv1x1_tc_workspace_bytes(int N, int C);
-bool conv1x1_tc_supported(int C, int N, int HW);
-int conv1x1_tc(const float* x, const float* W, float* out, const float* residual, const float* alpha, const float* beta,
-               float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
+bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld);
+int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
+               const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
                cudaStream_t stream);
+
+// Patch matrix of a convolution with ITS OWN stride (not the stride = kernel unfold of the calibration capture):
+// out[b][(c, ki, kj)][yo * Wo + xo] = in[b][c][yo * sh - ph + ki * dh][xo * sw - pw + kj * dw] (0 outside the image),
+// rows of ld >= Ho * Wo floats (columns Ho*Wo..ld-1 are zeroed).  With it every convolution is a 1x1 convolution over
+// C * kh * kw channels; a 1x1 kernel with stride 2 is a plain strided gather, stride 1 a copy that pads the row pitch.
+__global__ void __launch_bounds__(256)
+conv_patches_kernel(const float* __restrict__ in, int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
+                    int dw, int Ho, int Wo, float* __restrict__ out, int64_t ld, int64_t rows_total) {
+    // one warp-row of 256 threads walks the pixels of one (image, channel, ki, kj) row; grid.y strides over the rows
+    const int HWo = Ho * Wo;
+    for (int64_t row = blockIdx.y; row < rows_total; row += gridDim.y) {
+        const int kj = (int)(row % kw);
+        const int ki = (int)((row / kw) % kh);
+        const int64_t bc = row / ((int64_t)kw * kh);          // b * C + c
+        const float* src = in + bc * (int64_t)H * W;
+        float* dst = out + row * ld;
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < ld; p += gridDim.x * blockDim.x) {
+            float v = 0.f;
+            if (p < HWo) {
+                const int yo = p / Wo, xo = p - yo * Wo;
+                const int y = yo * sh - ph + ki * dh, x = xo * sw - pw + kj * dw;
+                if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(src + (int64_t)y * W + x);
+            }
+            dst[p] = v;
+        }
+    }
+}
 }  // namespace gpfq
 
 using namespace gpfq;
@@ -62,20 +90,39 @@ extern "C" size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C) {
     return conv1x1_tc_workspace_bytes(N, C);
 }
 
-extern "C" int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW) {
-    return conv1x1_tc_supported(C, N, HW) ? 1 : 0;
+extern "C" int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW, int64_t x_ld) {
+    return conv1x1_tc_supported(C, N, HW, x_ld) ? 1 : 0;
 }
 
-extern "C" int gpfq_conv1x1_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha,
-                                       const float* beta, float* out, int32_t B, int32_t C, int32_t N, int32_t HW, float lo,
-                                       float hi, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int gpfq_conv_patches_f32(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                                     int32_t sh, int32_t sw, int32_t ph, int32_t pw, int32_t dh, int32_t dw, float* out,
+                                     int64_t ld, void* stream) {
+    GPFQ_REQUIRE(B >= 0 && C >= 1 && H >= 1 && W >= 1 && kh >= 1 && kw >= 1 && sh >= 1 && sw >= 1 && dh >= 1 && dw >= 1 &&
+                     ph >= 0 && pw >= 0, "gpfq_conv_patches_f32: bad geometry");
+    const int Ho = (H + 2 * ph - dh * (kh - 1) - 1) / sh + 1, Wo = (W + 2 * pw - dw * (kw - 1) - 1) / sw + 1;
+    GPFQ_REQUIRE(Ho >= 1 && Wo >= 1 && ld >= (int64_t)Ho * Wo, "gpfq_conv_patches_f32: empty output or ld too small");
+    GPFQ_REQUIRE(in && out, "gpfq_conv_patches_f32: null pointer");
+    if (B == 0) return 0;
+    const int64_t rows = (int64_t)B * C * kh * kw;
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(ld, 256), 64), (unsigned)std::min<int64_t>(rows, 65535));
+    conv_patches_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, out, ld,
+                                                                rows);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int gpfq_conv1x1_bn_act_f32(const float* x, int64_t x_ld, const float* W, const float* residual,
+                                       const float* alpha, const float* beta, float* out, int32_t B, int32_t C, int32_t N,
+                                       int32_t HW, float lo, float hi, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
     GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && HW >= 1, "gpfq_conv1x1_bn_act_f32: bad shape");
     GPFQ_REQUIRE(x && W && out && workspace, "gpfq_conv1x1_bn_act_f32: null pointer");
     GPFQ_REQUIRE((alpha == nullptr) == (beta == nullptr), "gpfq_conv1x1_bn_act_f32: alpha and beta go together");
-    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW),
-                 "gpfq_conv1x1_bn_act_f32: HW = %d is not a multiple of 4 (ask gpfq_conv1x1_fused_supported first)", HW);
+    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW, x_ld),
+                 "gpfq_conv1x1_bn_act_f32: the pixel pitch x_ld = %lld must be >= HW and a multiple of 4 (pad it with "
+                 "gpfq_conv_patches_f32; ask gpfq_conv1x1_fused_supported first)", (long long)x_ld);
     if (B == 0) return 0;
-    return conv1x1_tc(x, W, out, residual, alpha, beta, lo, hi, B, C, N, HW, workspace, workspace_bytes,
+    return conv1x1_tc(x, x_ld, W, out, residual, alpha, beta, lo, hi, B, C, N, HW, workspace, workspace_bytes,
                       (cudaStream_t)stream);
 }
 
@@ -85,8 +132,8 @@ extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int3
     GPFQ_REQUIRE(x && W && out, "gpfq_conv1x1_f32: null pointer");
     if (B == 0) return 0;
     static const bool force_cublas = getenv("GPFQ_CONV1X1_CUBLAS") && atoi(getenv("GPFQ_CONV1X1_CUBLAS")) == 1;
-    if (!force_cublas && workspace != nullptr && conv1x1_tc_supported(C, N, HW))
-        return conv1x1_tc(x, W, out, nullptr, nullptr, nullptr, -INFINITY, INFINITY, B, C, N, HW, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+    if (!force_cublas && workspace != nullptr && conv1x1_tc_supported(C, N, HW, HW))
+        return conv1x1_tc(x, HW, W, out, nullptr, nullptr, nullptr, -INFINITY, INFINITY, B, C, N, HW, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
     return conv1x1_cublas(x, W, out, B, C, N, HW, stream);       // 7 x 7 planes (HW % 4 != 0): plain library SGEMM
 }

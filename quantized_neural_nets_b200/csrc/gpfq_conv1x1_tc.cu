@@ -47,7 +47,9 @@ constexpr int kATile = kTM * kBK;   // floats per weight plane tile (16 KB)
 constexpr int kBTile = kBK * kTN;   // floats per activation plane tile (16 KB) = 4 boxes [32 ch][32 px]
 constexpr int kStageFloats = 2 * kATile + 2 * kBTile;      // w_hi | w_lo | x_hi (raw on arrival) | x_lo
 constexpr int kThreads = 320;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageFloats * sizeof(float) + 256;
+constexpr int kStgStride = 36;      // floats per staged row: 32 pixels + 4 of padding (conflict-free float4 rows)
+constexpr int kStgFloats = 4 * 32 * kStgStride;            // one 32 x 32 transposition buffer per drain warp
+constexpr size_t kSmemBytes = (size_t)(kStages * kStageFloats + kStgFloats) * sizeof(float) + 256;
 
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
@@ -138,6 +140,7 @@ struct ConvArgs {
     float lo, hi;
     int C, N, HW, B;
     int n_tiles, p_tiles, total_tiles;
+    int four_terms;          // also issue lo*lo (short reductions: the dropped term is not averaged away)
 };
 
 // hi = rna_tf32(w), lo = rna_tf32(w - hi) of the (N x C) weight, rows padded with zeros to Cp columns
@@ -161,7 +164,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                   const __grid_constant__ CUtensorMap tmX, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageFloats * sizeof(float));
+    float* staging = tiles + (size_t)kStages * kStageFloats;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)(kStages * kStageFloats + kStgFloats) * sizeof(float));
     uint64_t* split = full + kStages;
     uint64_t* empty = split + kStages;
     uint64_t* acc_full = empty + kStages;
@@ -241,7 +245,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 for (int k8 = 0; k8 < kBK / 8; ++k8) {
                     const uint64_t adv_a = (uint64_t)((k8 * 8 * sizeof(float)) >> 4);     // 32 bytes along K
                     const uint64_t adv_b = (uint64_t)((k8 * 1024) >> 4);                  // 8 channel rows
-                    umma_tf32(d_tmem, d_wl + adv_a, d_xh + adv_b, kIdesc, k8 > 0);
+                    if (a.four_terms) umma_tf32(d_tmem, d_wl + adv_a, d_xl + adv_b, kIdesc, k8 > 0);
+                    umma_tf32(d_tmem, d_wl + adv_a, d_xh + adv_b, kIdesc, (k8 > 0) | a.four_terms);
                     umma_tf32(d_tmem, d_wh + adv_a, d_xl + adv_b, kIdesc, 1);
                     umma_tf32(d_tmem, d_wh + adv_a, d_xh + adv_b, kIdesc, 1);
                 }
@@ -276,8 +281,6 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
     } else {
         const int quad = warp & 3;                 // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
         const int row = quad * 32 + lane;          // output channel within the tile
-        const bool vec_ok = true;                  // HW % 4 == 0 on this path
-        (void)vec_ok;
         int it = 0;
         for (int i = 0; i < my_tiles; ++i) {
             int img, p0, n0;
@@ -300,34 +303,65 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[b]);
             }
-            const int n = n0 + row;
-            if (n < a.N) {
-                const bool affine = a.alpha != nullptr;
-                const float al = affine ? a.alpha[n] : 1.f, be = affine ? a.beta[n] : 0.f;
-                const size_t base = ((size_t)img * a.N + n) * a.HW + p0;
-                float* dst = a.out + base;
-                const float* res = a.residual ? a.residual + base : nullptr;
-                const float lo = a.lo, hi = a.hi;
+            // Epilogue.  run[] holds one output channel per thread; 32 x 32 blocks go through a per-warp shared-memory
+            // transposition so that every global access of the warp covers whole 128-byte row segments (4 rows x 32
+            // pixels per float4 instruction) instead of 32 different rows.
+            const bool affine = a.alpha != nullptr;
+            const int n_mine = n0 + row;
+            const float al_mine = (affine && n_mine < a.N) ? a.alpha[n_mine] : 1.f;
+            const float be_mine = (affine && n_mine < a.N) ? a.beta[n_mine] : 0.f;
+            float* stg = staging + (warp - 2) * 32 * kStgStride;
+            const float lo = a.lo, hi = a.hi;
+            const bool vec = (a.HW & 3) == 0;
 #pragma unroll
-                for (int c = 0; c < kTN; c += 4) {
-                    if (p0 + c < a.HW) {           // HW % 4 == 0: a float4 is entirely inside or outside the row
-                        float4 v = make_float4(run[c], run[c + 1], run[c + 2], run[c + 3]);
-                        if (affine) {
-                            v.x = __fadd_rn(__fmul_rn(v.x, al), be);
-                            v.y = __fadd_rn(__fmul_rn(v.y, al), be);
-                            v.z = __fadd_rn(__fmul_rn(v.z, al), be);
-                            v.w = __fadd_rn(__fmul_rn(v.w, al), be);
+            for (int c0 = 0; c0 < kTN; c0 += 32) {
+                if (p0 + c0 >= a.HW) break;        // uniform over the warp
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * j) =
+                        make_float4(run[c0 + 4 * j], run[c0 + 4 * j + 1], run[c0 + 4 * j + 2], run[c0 + 4 * j + 3]);
+                __syncwarp();
+                if (vec) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int r = 4 * k + (lane >> 3), cq = lane & 7;
+                        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgStride + 4 * cq);
+                        const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
+                        const int n = n0 + quad * 32 + r, p = p0 + c0 + 4 * cq;
+                        if (n < a.N && p < a.HW) {     // HW % 4 == 0: a float4 is entirely inside or outside the row
+                            const size_t off = ((size_t)img * a.N + n) * a.HW + p;
+                            if (affine) {
+                                v.x = __fadd_rn(__fmul_rn(v.x, al), be);
+                                v.y = __fadd_rn(__fmul_rn(v.y, al), be);
+                                v.z = __fadd_rn(__fmul_rn(v.z, al), be);
+                                v.w = __fadd_rn(__fmul_rn(v.w, al), be);
+                            }
+                            if (a.residual) {
+                                const float4 rr = __ldg(reinterpret_cast<const float4*>(a.residual + off));
+                                v.x = __fadd_rn(v.x, rr.x); v.y = __fadd_rn(v.y, rr.y);
+                                v.z = __fadd_rn(v.z, rr.z); v.w = __fadd_rn(v.w, rr.w);
+                            }
+                            v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
+                            v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
+                            *reinterpret_cast<float4*>(a.out + off) = v;
                         }
-                        if (res) {
-                            const float4 r = __ldg(reinterpret_cast<const float4*>(res + c));
-                            v.x = __fadd_rn(v.x, r.x); v.y = __fadd_rn(v.y, r.y);
-                            v.z = __fadd_rn(v.z, r.z); v.w = __fadd_rn(v.w, r.w);
+                    }
+                } else {
+                    for (int r = 0; r < 32; ++r) {     // lane = pixel: one 128-byte row segment per instruction
+                        float v = stg[r * kStgStride + lane];
+                        const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
+                        const int n = n0 + quad * 32 + r, p = p0 + c0 + lane;
+                        if (n < a.N && p < a.HW) {
+                            const size_t off = ((size_t)img * a.N + n) * a.HW + p;
+                            if (affine) v = __fadd_rn(__fmul_rn(v, al), be);
+                            if (a.residual) v = __fadd_rn(v, __ldg(a.residual + off));
+                            v = v < lo ? lo : v;
+                            v = v > hi ? hi : v;
+                            a.out[off] = v;
                         }
-                        v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
-                        v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
-                        *reinterpret_cast<float4*>(dst + c) = v;
                     }
                 }
+                __syncwarp();
             }
         }
     }
@@ -378,16 +412,18 @@ int sm_count() {
 
 size_t conv1x1_tc_workspace_bytes(int N, int C) { return (size_t)2 * N * round_up(C, kBK) * sizeof(float) + 256; }
 
-bool conv1x1_tc_supported(int C, int N, int HW) { return C >= 1 && N >= 1 && HW >= 4 && HW % 4 == 0; }
+// x is read through TMA: its pixel pitch x_ld (floats between consecutive channels) must be a multiple of 4
+bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld) { return C >= 1 && N >= 1 && HW >= 1 && x_ld >= HW && x_ld % 4 == 0; }
 
-int conv1x1_tc(const float* x, const float* W, float* out, const float* residual, const float* alpha, const float* beta,
-               float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
+int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
+               const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
                cudaStream_t stream) {
-    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW), "conv1x1_tc: unsupported shape");
+    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW, x_ld), "conv1x1_tc: unsupported shape");
     GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C), "conv1x1_tc: workspace too small");
     GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
                      ((uintptr_t)residual & 15) == 0,
                  "conv1x1_tc: workspace must be 256-byte aligned, tensors 16-byte aligned");
+    GPFQ_REQUIRE((const void*)x != (const void*)out && (const void*)residual != (const void*)out, "conv1x1_tc: out must not alias an input");
     const int Cp = (int)round_up(C, kBK);
     float* w_hi = (float*)workspace;
     float* w_lo = w_hi + (size_t)N * Cp;
@@ -405,7 +441,7 @@ int conv1x1_tc(const float* x, const float* W, float* out, const float* residual
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
-        cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)C * HW * sizeof(float)};
+        cuuint64_t strides[2] = {(cuuint64_t)x_ld * sizeof(float), (cuuint64_t)C * x_ld * sizeof(float)};
         cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kBK, 1};
         if (int rc = make_map(&tmX, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
     }
@@ -417,6 +453,7 @@ int conv1x1_tc(const float* x, const float* W, float* out, const float* residual
     const int64_t total = (int64_t)a.n_tiles * a.p_tiles * B;
     GPFQ_REQUIRE(total < (1ll << 31), "conv1x1_tc: too many tiles");
     a.total_tiles = (int)total;
+    a.four_terms = C <= 128 ? 1 : 0;
     if (int rc = ensure_dynamic_smem((const void*)conv1x1_tc_kernel, kSmemBytes)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
     profile_mark_begin(stream);

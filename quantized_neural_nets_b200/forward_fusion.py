@@ -72,41 +72,70 @@ def _is_pointwise(mod):
 
 
 def _conv_workspace(conv, device):
-    return torch.empty(lib.gpfq_conv1x1_workspace_bytes(conv.out_channels, conv.in_channels), dtype=torch.uint8, device=device)
+    k = conv.in_channels // conv.groups * conv.kernel_size[0] * conv.kernel_size[1]
+    return torch.empty(lib.gpfq_conv1x1_workspace_bytes(conv.out_channels, k), dtype=torch.uint8, device=device)
 
 
-class FusedConv1x1BNAct(nn.Module):
-    """Stride-1 1x1 Conv2d -> inference BatchNorm2d (-> + residual) (-> clamp to [lo, hi]) as ONE tensor-core kernel
+def _tc_route(conv):
+    """How a Conv2d reaches the tensor-core kernel: 'direct' (stride-1 1x1: the activation is the B operand as it is),
+    'patches' (gpfq_conv_patches_f32 writes the patch matrix first: 1x1 with a stride -- a strided gather -- and k x k
+    kernels with stride >= 2, which cuDNN's fp32 kernels run at 25-35 TFLOP/s: ResNet's stem, its three stride-2 3x3
+    layers and its three stride-2 shortcuts), or None (grouped / depthwise, and stride-1 k x k layers, where cuDNN's
+    Winograd kernels beat a 9x larger patch matrix)."""
+    if type(conv) is not nn.Conv2d or conv.groups != 1 or conv.padding_mode != 'zeros' or isinstance(conv.padding, str):
+        return None
+    if conv.kernel_size == (1, 1):
+        return 'direct' if conv.stride == (1, 1) and conv.padding == (0, 0) else 'patches'
+    return 'patches' if max(conv.stride) >= 2 else None
+
+
+class FusedConvBNAct(nn.Module):
+    """Conv2d -> inference BatchNorm2d (-> + residual) (-> clamp to [lo, hi]) as ONE tensor-core kernel
     (gpfq_conv1x1_bn_act_f32: tcgen05 split-TF32 GEMM whose epilogue applies the batch norm, the residual add and the
-    activation, so the convolution's output never makes a round trip through HBM).  ``conv`` and ``bn`` are the wrapped
-    modules (not copied).  Whenever the convolution carries a hook (the layer whose input is being captured, or a
-    user's own hook), or the shape / dtype / layout is not the kernel's, the modules run as they are: ``conv(x)`` (so
-    its hooks fire exactly as in the plain network) followed by the fused elementwise pass."""
+    activation, so the convolution's output never makes a round trip through HBM); convolutions that are not stride-1
+    1x1 go through their patch matrix first (see _tc_route).  ``conv`` and ``bn`` are the wrapped modules (not copied).
+    Whenever the convolution carries a hook (the layer whose input is being captured, or a user's own hook), or the
+    dtype / layout is not the kernel's, the modules run as they are: ``conv(x)`` (so its hooks fire exactly as in the
+    plain network) followed by the fused elementwise pass."""
 
     def __init__(self, conv, bn, lo=-_INF, hi=_INF):
         super().__init__()
         self.conv = conv
         self.tail = FusedBNAct(bn, lo, hi)
+        self.route = _tc_route(conv)
 
     def forward(self, x, residual=None):
         conv, bn = self.conv, self.tail.bn
         hooked = bool(conv._forward_hooks or conv._forward_pre_hooks)
         patched = 'forward' in conv.__dict__ and getattr(conv.forward, '__func__', None) is not _pointwise_forward
-        fused = not hooked and not patched
-        fused = (fused and conv.bias is None and not bn.training and bn.track_running_stats and bn.running_mean is not None
-                 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.shape[0] > 0
-                 and conv.weight.is_contiguous() and conv.weight.dtype == torch.float32
-                 and (residual is None or (residual.dtype == x.dtype and residual.is_cuda and residual.is_contiguous()
-                                           and residual.shape == (x.shape[0], conv.out_channels) + x.shape[2:]))
-                 and lib.gpfq_conv1x1_fused_supported(x.shape[1], conv.out_channels, x.shape[2] * x.shape[3]))
+        fused = (self.route is not None and not hooked and not patched and not bn.training and bn.track_running_stats
+                 and bn.running_mean is not None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                 and x.is_contiguous() and x.shape[0] > 0 and conv.weight.is_contiguous()
+                 and conv.weight.dtype == torch.float32)
+        if fused:
+            B, C, H, W = x.shape
+            (kh, kw), (sh, sw), (ph, pw), (dh, dw) = conv.kernel_size, conv.stride, conv.padding, conv.dilation
+            Ho = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+            Wo = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+            N = conv.out_channels
+            fused = (Ho >= 1 and Wo >= 1 and C == conv.in_channels and
+                     (residual is None or (residual.dtype == x.dtype and residual.is_cuda and residual.is_contiguous()
+                                           and tuple(residual.shape) == (B, N, Ho, Wo))))
         if not fused:
             return self.tail(conv(x), residual)
         alpha, beta = self.tail._coefficients()
-        B, C, H, W = x.shape
-        N = conv.out_channels
-        out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
+        if conv.bias is not None:            # (W x + b) * alpha + beta  =  (W x) * alpha + (beta + alpha * b)
+            beta = beta + alpha * conv.bias.data
+        HW = Ho * Wo
+        if self.route == 'direct' and HW % 4 == 0:
+            xin, x_ld, Ck = x, HW, C
+        else:
+            x_ld, Ck = (HW + 3) // 4 * 4, C * kh * kw
+            xin = torch.empty((B, Ck, x_ld), dtype=torch.float32, device=x.device)
+            launch(lib.gpfq_conv_patches_f32, x, B, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, xin, x_ld)
+        out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=x.device)
         ws = _conv_workspace(conv, x.device)
-        launch(lib.gpfq_conv1x1_bn_act_f32, x, conv.weight, residual, alpha, beta, out, B, C, N, H * W, self.tail.lo,
+        launch(lib.gpfq_conv1x1_bn_act_f32, xin, x_ld, conv.weight, residual, alpha, beta, out, B, Ck, N, HW, self.tail.lo,
                self.tail.hi, ws, ws.numel())
         return out
 
@@ -134,8 +163,9 @@ def _single_user(node):
 
 def fuse_inference_forward(network, fuse_pointwise=True):
     """-> (callable running ``network``'s forward with fused BatchNorm / add / ReLU, number of fused sites); with
-    ``fuse_pointwise`` a stride-1 1x1 convolution that feeds only the batch norm is folded into the same site
-    (FusedConv1x1BNAct; ``.fused_conv_sites`` of the returned module counts them).
+    ``fuse_pointwise`` a convolution that feeds only the batch norm and that the tensor-core kernel handles (every 1x1
+    layer and every layer with stride >= 2, see _tc_route) is folded into the same site (FusedConvBNAct;
+    ``.fused_conv_sites`` of the returned module counts them).
     The callable shares every submodule with ``network``.  Raises whatever torch.fx raises if the network cannot
     be traced (data-dependent control flow); the caller then keeps the plain module."""
     from torch import fx
@@ -166,14 +196,15 @@ def fuse_inference_forward(network, fuse_pointwise=True):
                     residual = user.args[1] if user.args[0] is node else user.args[0]
         name = f"_gpfq_fused_bn_{sites}"
         lo, hi = bounds if bounds is not None else (-_INF, _INF)
-        # a stride-1 1x1 convolution feeding only this batch norm joins the fused site: conv + BN (+ add) (+ ReLU) in
-        # one tensor-core kernel
+        # a convolution the tensor-core kernel handles (_tc_route) that feeds only this batch norm joins the fused
+        # site: conv + BN (+ add) (+ ReLU) in one kernel
         src = node.args[0]
         conv_node = None
-        if (fuse_pointwise and isinstance(src, fx.Node) and src.op == 'call_module' and _is_pointwise(modules.get(src.target))
-                and modules[src.target].bias is None and len(src.users) == 1 and len(src.args) == 1 and not src.kwargs):
+        if (fuse_pointwise and isinstance(src, fx.Node) and src.op == 'call_module'
+                and _tc_route(modules.get(src.target)) is not None and len(src.users) == 1 and len(src.args) == 1
+                and not src.kwargs and modules[src.target].out_channels == bn.num_features):
             conv_node = src
-            gm.add_submodule(name, FusedConv1x1BNAct(modules[src.target], bn, lo, hi))
+            gm.add_submodule(name, FusedConvBNAct(modules[src.target], bn, lo, hi))
             src = conv_node.args[0]
             conv_sites += 1
         else:

@@ -306,23 +306,55 @@ def test_conv1x1_tensor_core_kernel(B, C, N, H, W, with_res, lo, hi):
     alpha = (torch.rand(N, generator=g) + 0.5).to(DEV)
     beta = (torch.randn(N, generator=g) * 0.1).to(DEV)
     res = torch.randn(B, N, H, W, generator=g).to(DEV) if with_res else None
-    assert lib.gpfq_conv1x1_fused_supported(C, N, H * W) == 1
+    assert lib.gpfq_conv1x1_fused_supported(C, N, H * W, H * W) == 1
     ws = torch.empty(lib.gpfq_conv1x1_workspace_bytes(N, C), dtype=torch.uint8, device=DEV)
     plain = torch.full((B, N, H, W), float("nan"), device=DEV)
-    launch(lib.gpfq_conv1x1_bn_act_f32, x, w, None, None, None, plain, B, C, N, H * W, -float("inf"), float("inf"), ws,
+    launch(lib.gpfq_conv1x1_bn_act_f32, x, H * W, w, None, None, None, plain, B, C, N, H * W, -float("inf"), float("inf"), ws,
            ws.numel())
     ref = torch.einsum("nc,bchw->bnhw", w.double(), x.double())
     mag = torch.einsum("nc,bchw->bnhw", w.double().abs(), x.double().abs())
     err = ((plain.double() - ref).abs() / (mag + 1e-30)).max().item()
     assert err <= 3e-7, err
     fused = torch.full((B, N, H, W), float("nan"), device=DEV)
-    launch(lib.gpfq_conv1x1_bn_act_f32, x, w, res, alpha, beta, fused, B, C, N, H * W, lo, hi, ws, ws.numel())
+    launch(lib.gpfq_conv1x1_bn_act_f32, x, H * W, w, res, alpha, beta, fused, B, C, N, H * W, lo, hi, ws, ws.numel())
     two_pass = torch.empty_like(plain)
     launch(lib.gpfq_bn_act_f32, plain, res, alpha, beta, two_pass, B * N, N, H * W, lo, hi)
     assert torch.equal(fused, two_pass)
     # and against cuDNN's fp32 convolution
     cud = torch.nn.functional.conv2d(x, w.view(N, C, 1, 1))
     assert (plain - cud).norm() <= 2e-6 * cud.norm()
+
+
+@pytest.mark.parametrize("C,N,H,W,k,stride,pad,bias", [(3, 64, 40, 40, 7, 2, 3, False),      # ResNet stem
+                                                      (32, 48, 28, 28, 3, 2, 1, False),    # stride-2 3x3
+                                                      (64, 96, 14, 14, 1, 2, 0, False),    # stride-2 shortcut, 7 x 7 output
+                                                      (96, 40, 7, 7, 1, 1, 0, True),       # 7 x 7 planes: padded pitch; bias
+                                                      (16, 24, 9, 11, 3, 2, 0, True)])
+def test_fused_conv_bn_act_module_any_convolution(C, N, H, W, k, stride, pad, bias):
+    """FusedConvBNAct (patch matrix + tensor-core GEMM + fused epilogue) against PyTorch's conv2d -> BatchNorm2d -> + r -> ReLU."""
+    from quantized_neural_nets_b200.forward_fusion import FusedConvBNAct
+    g = torch.Generator().manual_seed(C * 100 + N)
+    conv = torch.nn.Conv2d(C, N, k, stride=stride, padding=pad, bias=bias).to(DEV)
+    bn = torch.nn.BatchNorm2d(N).eval()
+    bn.running_mean = torch.randn(N, generator=g) * 0.1
+    bn.running_var = torch.rand(N, generator=g) + 0.5
+    bn.weight.data = torch.rand(N, generator=g) + 0.5
+    bn.bias.data = torch.randn(N, generator=g) * 0.1
+    bn = bn.to(DEV)
+    x = torch.randn(5, C, H, W, generator=g).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        y = bn(conv(x))
+        res = torch.randn(y.shape, generator=g).to(DEV)
+        want = torch.relu(y + res)
+        mod = FusedConvBNAct(conv, bn, 0.0, float("inf"))
+        assert mod.route is not None
+        from quantized_neural_nets_b200 import _lib
+        before = _lib.launch_count()
+        got = mod(x, res)
+        assert _lib.launch_count() - before >= 2        # the tensor-core path ran (weight split + GEMM (+ patches))
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
 
 
 def test_fused_resnet50_forward_with_tensor_core_convolutions():
@@ -338,7 +370,7 @@ def test_fused_resnet50_forward_with_tensor_core_convolutions():
             mod.running_mean.normal_(0, 0.1)
             mod.running_var.uniform_(0.5, 1.5)
     fused, sites = fuse_inference_forward(model)
-    assert sites == 53 and fused.fused_conv_sites == 33
+    assert sites == 53 and fused.fused_conv_sites == 40      # 33 stride-1 1x1 + 3 stride-2 1x1 + 3 stride-2 3x3 + the stem
     x = torch.randn(8, 3, 224, 224, device=DEV)
     with torch.no_grad():
         want, got = model(x), fused(x)

@@ -44,7 +44,7 @@ for (cin, cout, hw, count, with_res) in ((64, 64, 56, 1, False), (64, 256, 56, 1
     ws = torch.empty(lib.gpfq_conv1x1_workspace_bytes(cout, cin), dtype=torch.uint8, device=dev)
 
     def fused():
-        launch(lib.gpfq_conv1x1_bn_act_f32, x, w, res, alpha, beta, out, B, cin, cout, hw * hw, 0.0, float("inf"), ws, ws.numel())
+        launch(lib.gpfq_conv1x1_bn_act_f32, x, hw * hw, w, res, alpha, beta, out, B, cin, cout, hw * hw, 0.0, float("inf"), ws, ws.numel())
 
     tmp = torch.empty_like(out)
 

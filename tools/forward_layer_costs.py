@@ -35,14 +35,18 @@ records = {}     # module name -> [events]
 order = []
 
 
-def leafs(m):
-    return [(n, c) for n, c in m.named_modules() if not list(c.children()) or type(c).__name__ == "FusedBNAct"]
-
-
+fused_types = ("FusedConvBNAct", "FusedBNAct")
+owned = set()       # modules that live inside a fused site: a hook on them would make the site fall back
+for n, c in net.named_modules():
+    if type(c).__name__ == "FusedConvBNAct":
+        owned |= {id(c.conv), id(c.tail), id(c.tail.bn)}
+    elif type(c).__name__ == "FusedBNAct":
+        owned.add(id(c.bn))
+timed = [(n, c) for n, c in net.named_modules()
+         if id(c) not in owned and (type(c).__name__ in fused_types or not list(c.children()))]
+# a FusedBNAct that is the tail of a FusedConvBNAct is in `owned`; stand-alone ones are timed
 handles = []
-for n, c in leafs(net):
-    if any(n.startswith(p + ".") for p, q in leafs(net) if type(q).__name__ == "FusedBNAct" and p != n):
-        continue        # the BatchNorm wrapped inside a FusedBNAct
+for n, c in timed:
 
     def pre(mod, args, n=n):
         e = torch.cuda.Event(enable_timing=True)
@@ -84,8 +88,9 @@ for n in order:
     ms = sum(a.elapsed_time(b) for a, b in records[n]) / reps
     mod = mods[n]
     # number of quantizable layers that come strictly AFTER this module's position = how many prefix passes run it
-    if id(mod) in qset:
-        seen_q = qset[id(mod)] + 1
+    inner = getattr(mod, "conv", None)
+    if id(mod) in qset or id(inner) in qset:
+        seen_q = qset[id(mod) if id(mod) in qset else id(inner)] + 1
         mult = len(qlayers) - seen_q          # the layer's own forward is interrupted by the hook
     else:
         mult = len(qlayers) - seen_q
@@ -100,9 +105,10 @@ for r in sorted(rows, key=lambda r: -r[4])[:45]:
 by_type = {}
 for r in rows:
     key = r[1]
-    if r[1] == "Conv2d":
-        m = mods[r[0]]
-        key = f"Conv2d {m.kernel_size[0]}x{m.kernel_size[1]} s{m.stride[0]}"
+    m = mods[r[0]]
+    m = getattr(m, "conv", m)
+    if isinstance(m, torch.nn.Conv2d):
+        key = f"{r[1]} {m.kernel_size[0]}x{m.kernel_size[1]} s{m.stride[0]}"
     by_type[key] = by_type.get(key, 0.0) + r[4]
 print("\nby type:")
 for k, v in sorted(by_type.items(), key=lambda kv: -kv[1]):
