@@ -96,6 +96,22 @@ int gpfq_pack_levels_f32(const float* Q, int64_t n, const float* delta, int32_t 
 int gpfq_unpack_levels_f32(const uint8_t* packed, int64_t n, const float* delta, int32_t K, int32_t mode, float lam,
                            float* Q, int8_t* levels, void* stream);
 
+/* Multi-GPU exchange of one layer (neurons are independent, each rank solves a contiguous slice of
+ * rows and ONE all-gather per layer distributes them).  A slice travels as `per` rows of gpfq_slice_row_bytes(d) bytes:
+ *   [ d int8 signed level indices, zero padded to a multiple of 8 | ||u_n||^2 fp64 | ||X w_n||^2 fp64 ]
+ * (Q = level * delta exactly -- or sign*(lam + (|level|-1)*delta) for HARD -- so int8 levels are lossless; rows beyond the
+ * slice are zero).  gpfq_pack_slice_f32 packs rows [n0, n1) of Q (fp32 alphabet values) and of the per-neuron norms
+ * (err2 / ref2 indexed by neuron); *n_off_alphabet counts entries that are not exactly on the alphabet (0 = lossless).
+ * gpfq_unpack_slices_f32 turns the concatenation of all ranks' buffers (rank r holds neurons [r*per, (r+1)*per)) into the
+ * full Q (N x d fp32, bit-identical to what the solver wrote up to the sign of zero) and the full norms.  Needs
+ * K <= 127 (126 for HARD); wider alphabets exchange fp32 rows on the host side. */
+int64_t gpfq_slice_row_bytes(int32_t d);
+int gpfq_pack_slice_f32(const float* Q, int64_t ldq, int32_t d, int32_t n0, int32_t n1, int32_t per, const float* delta,
+                        int32_t K, int32_t mode, float lam, const double* err2, const double* ref2, uint8_t* out,
+                        uint32_t* n_off_alphabet, void* stream);
+int gpfq_unpack_slices_f32(const uint8_t* in, int32_t N, int32_t d, const float* delta, int32_t K, int32_t mode, float lam,
+                           float* Q, int64_t ldq, double* err2, double* ref2, void* stream);
+
 /* (rows x cols, ld_in) row-major  ->  (cols x ld_out) row-major, columns rows..ld_out-1 zeroed.
  * Turns the reference's (m x d) layer input (quantize_neural_net.py:291,347) into feature-major. */
 int gpfq_transpose_f32(const float* in, int64_t rows, int64_t cols, int64_t ld_in, float* out,

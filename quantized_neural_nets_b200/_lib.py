@@ -38,6 +38,10 @@ SIGNATURES = {
     "gpfq_packed_bits": (c_i32, [c_i32, c_i32]),
     "gpfq_pack_levels_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, c_ptr, c_ptr, c_ptr]),
     "gpfq_unpack_levels_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, c_ptr, c_ptr, c_ptr]),
+    "gpfq_slice_row_bytes": (c_i64, [c_i32]),
+    "gpfq_pack_slice_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_ptr, c_i32, c_i32, c_f32, c_ptr, c_ptr, c_ptr,
+                                    c_ptr, c_ptr]),
+    "gpfq_unpack_slices_f32": (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i32, c_i32, c_f32, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "gpfq_transpose_f32": (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gpfq_im2col_gather_f32": (c_i32, [c_ptr] + [c_i32] * 12 + [c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gpfq_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),

@@ -199,6 +199,59 @@ __global__ void unpack_levels_kernel(const uint8_t* __restrict__ in, int64_t n, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Multi-GPU exchange of one layer: a rank's solved neuron slice travels as ONE buffer of
+// `per` rows of  [d int8 level indices, padded to a multiple of 8 bytes | ||u_n||^2 fp64 | ||X w_n||^2 fp64]
+// (Q = level * delta exactly, so int8 levels are lossless and a quarter of the fp32 volume); one kernel packs, one
+// unpacks the concatenation of all ranks' buffers into the full fp32 Q and the full per-neuron norms.
+__global__ void __launch_bounds__(256)
+pack_slice_kernel(const float* __restrict__ Q, int64_t ldq, int d, int n0, int n1, int per, const float* __restrict__ delta_p,
+                  int mode, float lam, const double* __restrict__ err2, const double* __restrict__ ref2,
+                  uint8_t* __restrict__ out, int row_bytes, unsigned int* __restrict__ bad) {
+    const float delta = *delta_p;
+    const int lev_bytes = row_bytes - 16;
+    for (int r = blockIdx.x; r < per; r += gridDim.x) {
+        uint8_t* row = out + (int64_t)r * row_bytes;
+        const int n = n0 + r;
+        const bool live = n < n1;
+        for (int t = threadIdx.x; t < lev_bytes; t += blockDim.x) {
+            int lv = 0;
+            if (live && t < d) {
+                const float v = Q[(int64_t)n * ldq + t];
+                lv = level_of_value(v, delta, mode, lam);
+                if (lv < -127 || lv > 127 || value_of_level(lv, delta, mode, lam) != v) {
+                    atomicAdd(bad, 1u);          // off the alphabet: reported, never silently rounded
+                    lv = 0;
+                }
+            }
+            row[t] = (uint8_t)(int8_t)lv;
+        }
+        if (threadIdx.x == 0) {
+            double* tail = reinterpret_cast<double*>(row + lev_bytes);
+            tail[0] = live ? err2[n] : 0.0;
+            tail[1] = live ? ref2[n] : 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_slices_kernel(const uint8_t* __restrict__ in, int N, int d, const float* __restrict__ delta_p, int mode, float lam,
+                     float* __restrict__ Q, int64_t ldq, double* __restrict__ err2, double* __restrict__ ref2,
+                     int row_bytes) {
+    const float delta = *delta_p;
+    const int lev_bytes = row_bytes - 16;
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {      // rank r's rows are [r * per, (r + 1) * per): row n is row n
+        const uint8_t* row = in + (int64_t)n * row_bytes;
+        for (int t = threadIdx.x; t < d; t += blockDim.x)
+            Q[(int64_t)n * ldq + t] = value_of_level((int)(int8_t)row[t], delta, mode, lam);
+        if (threadIdx.x == 0) {
+            const double* tail = reinterpret_cast<const double*>(row + lev_bytes);
+            err2[n] = tail[0];
+            ref2[n] = tail[1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Calibration-forward helper: inference BatchNorm2d (+ residual add) (+ ReLU / ReLU6) of an NCHW tensor in ONE pass.
 // y = clamp(x * alpha[c] + beta[c] (+ residual), lo, hi) with alpha = gamma / sqrt(var + eps), beta = bias - mean * alpha
 // precomputed per channel -- the formulation of PyTorch's CPU batch norm (the reference's forward), each operation
@@ -403,6 +456,34 @@ int gpfq_unpack_levels_f32(const uint8_t* packed, int64_t n, const float* delta,
     level_layout(K, mode, &offset, &nbits);
     const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(n, 8), 256), 148 * 8);
     unpack_levels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(packed, n, delta, offset, nbits, mode, lam, Q, levels);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int64_t gpfq_slice_row_bytes(int32_t d) { return d < 0 ? 0 : (int64_t)((d + 7) / 8 * 8 + 16); }
+
+int gpfq_pack_slice_f32(const float* Q, int64_t ldq, int32_t d, int32_t n0, int32_t n1, int32_t per, const float* delta,
+                        int32_t K, int32_t mode, float lam, const double* err2, const double* ref2, uint8_t* out,
+                        uint32_t* n_off_alphabet, void* stream) {
+    GPFQ_REQUIRE(d >= 1 && 0 <= n0 && n0 <= n1 && n1 - n0 <= per && ldq >= d, "gpfq_pack_slice_f32: bad shape");
+    GPFQ_REQUIRE(mode >= 0 && mode <= 3 && K >= 1 && K + (mode == GPFQ_MODE_HARD ? 1 : 0) <= 127,
+                 "gpfq_pack_slice_f32: int8 levels need K <= 127 (126 for the L0 alphabet); got K=%d", K);
+    GPFQ_REQUIRE(Q && delta && err2 && ref2 && out && n_off_alphabet, "gpfq_pack_slice_f32: null pointer");
+    GPFQ_CUDA_TRY(cudaMemsetAsync(n_off_alphabet, 0, sizeof(uint32_t), (cudaStream_t)stream));
+    if (per == 0) return 0;
+    pack_slice_kernel<<<(unsigned)std::min(per, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        Q, ldq, d, n0, n1, per, delta, mode, lam, err2, ref2, out, (int)gpfq_slice_row_bytes(d), n_off_alphabet);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int gpfq_unpack_slices_f32(const uint8_t* in, int32_t N, int32_t d, const float* delta, int32_t K, int32_t mode, float lam,
+                           float* Q, int64_t ldq, double* err2, double* ref2, void* stream) {
+    GPFQ_REQUIRE(N >= 0 && d >= 1 && ldq >= d && mode >= 0 && mode <= 3 && K >= 1, "gpfq_unpack_slices_f32: bad shape");
+    GPFQ_REQUIRE(in && delta && Q && err2 && ref2, "gpfq_unpack_slices_f32: null pointer");
+    if (N == 0) return 0;
+    unpack_slices_kernel<<<(unsigned)std::min(N, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        in, N, d, delta, mode, lam, Q, ldq, err2, ref2, (int)gpfq_slice_row_bytes(d));
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

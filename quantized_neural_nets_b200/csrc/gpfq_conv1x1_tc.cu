@@ -9,16 +9,16 @@
 // product (lo*hi, hi*lo, hi*hi), and -- because the tensor core accumulates fp32 with truncation -- a FRESH TMEM
 // accumulator per 32-channel k-block that the epilogue warps add up in registers with round-to-nearest.
 //
-// Structure (one persistent CTA per SM, 320 threads, tiles of 128 output channels x 128 pixels of one image):
+// Structure (one persistent CTA per SM, 256 threads, tiles of 128 output channels x 128 pixels of one image):
 //   warp 0      TMA producer: per k-block the weight planes w_hi / w_lo (boxes [128][32], SWIZZLE_128B, K-major) and the
 //               RAW fp32 activation (four boxes [32 channels][32 pixels], SWIZZLE_128B_ATOM_32B: the B operand is
 //               MN-major -- the pixel index is the contiguous one in NCHW), 3-stage ring that runs on across tiles;
-//   warps 6-9   split: turn the raw activation tile into its TF32 hi plane in place and the lo plane next to it (an
+//   warps 2-3   split: turn the raw activation tile into its TF32 hi plane in place and the lo plane next to it (an
 //               elementwise map, so the swizzled layout is untouched), fence.proxy.async, release the MMA warp --
 //               the activation is read from HBM exactly once;
 //   warp 1      single-thread tcgen05.mma issue, 12 MMAs (M = N = 128, K = 8, kind::tf32) per k-block into one of FOUR
 //               128-column TMEM accumulators (all 512 columns): the MMAs run up to four k-blocks ahead of the drain;
-//   warps 2-5   drain each finished accumulator (tcgen05.ld 32x32b) into 128 fp32 registers per thread (thread = output
+//   warps 4-7   drain each finished accumulator (tcgen05.ld 32x32b) into 128 fp32 registers per thread (thread = output
 //               channel, register = pixel) and, after the tile's last k-block, apply alpha / beta / residual / clamp and
 //               store the row segment.  While they store, the MMA warp is already working on the next tile.
 //
@@ -46,7 +46,8 @@ constexpr int kAccs = 4;            // TMEM accumulators of kTN columns
 constexpr int kATile = kTM * kBK;   // floats per weight plane tile (16 KB)
 constexpr int kBTile = kBK * kTN;   // floats per activation plane tile (16 KB) = 4 boxes [32 ch][32 px]
 constexpr int kStageFloats = 2 * kATile + 2 * kBTile;      // w_hi | w_lo | x_hi (raw on arrival) | x_lo
-constexpr int kThreads = 320;
+constexpr int kThreads = 256;        // 8 warps, two per SM sub-partition: the register file then allows 255 per thread
+constexpr int kSplitThreads = 64;    // warps 2-3
 constexpr int kStgStride = 36;      // floats per staged row: 32 pixels + 4 of padding (conflict-free float4 rows)
 constexpr int kStgFloats = 4 * 32 * kStgStride;            // one 32 x 32 transposition buffer per drain warp
 constexpr size_t kSmemBytes = (size_t)(kStages * kStageFloats + kStgFloats) * sizeof(float) + 256;
@@ -121,6 +122,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -141,6 +146,7 @@ struct ConvArgs {
     int C, N, HW, B;
     int n_tiles, p_tiles, total_tiles;
     int four_terms;          // also issue lo*lo (short reductions: the dropped term is not averaged away)
+    int prefetch_residual;   // tmRes is valid
 };
 
 // hi = rna_tf32(w), lo = rna_tf32(w - hi) of the (N x C) weight, rows padded with zeros to Cp columns
@@ -161,7 +167,7 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, i
 // SWIZZLE_128B_ATOM_32B; channels beyond C and pixels beyond HW arrive as zeros.
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-                  const __grid_constant__ CUtensorMap tmX, const ConvArgs a) {
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     float* staging = tiles + (size_t)kStages * kStageFloats;
@@ -179,7 +185,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], 4);           // one arrival per split warp
+            mbar_init(&split[s], kSplitThreads / 32);      // one arrival per split warp
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < kAccs; ++b) {
@@ -211,6 +217,9 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             for (int i = 0; i < my_tiles; ++i) {
                 int img, p0, n0;
                 tile_coords(i, img, p0, n0);
+                // the residual tile is only needed by the epilogue, several microseconds from now: pull it into L2 with
+                // one bulk prefetch so that the epilogue's loads do not each pay an HBM round trip
+                if (a.prefetch_residual) tma_prefetch_3d(&tmRes, p0, n0, img);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
@@ -254,25 +263,25 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 umma_commit(&acc_full[b]);
             }
         }
-    } else if (warp >= 6) {
-        // split warps: raw fp32 (written by TMA) -> hi in place, lo next to it
-        const int t = threadIdx.x - 6 * 32;        // 0 .. 127
+    } else if (warp < 4) {
+        // split warps (2, 3): raw fp32 (written by TMA) -> hi in place, lo next to it
+        const int t = threadIdx.x - 2 * 32;        // 0 .. kSplitThreads-1
         const int total = my_tiles * nkb;
         for (int it = 0; it < total; ++it) {
             const int s = it % kStages;
             mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
             float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats + 2 * kATile);
             float4* lo = hi + kBTile / 4;
-#pragma unroll
-            for (int i = 0; i < kBTile / 4 / 128; ++i) {
-                const float4 v = hi[t + 128 * i];
+#pragma unroll 8
+            for (int i = 0; i < kBTile / 4 / kSplitThreads; ++i) {
+                const float4 v = hi[t + kSplitThreads * i];
                 float4 h, l;
                 h.x = to_tf32(v.x); l.x = to_tf32(v.x - h.x);
                 h.y = to_tf32(v.y); l.y = to_tf32(v.y - h.y);
                 h.z = to_tf32(v.z); l.z = to_tf32(v.z - h.z);
                 h.w = to_tf32(v.w); l.w = to_tf32(v.w - h.w);
-                hi[t + 128 * i] = h;
-                lo[t + 128 * i] = l;
+                hi[t + kSplitThreads * i] = h;
+                lo[t + kSplitThreads * i] = l;
             }
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
@@ -310,7 +319,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             const int n_mine = n0 + row;
             const float al_mine = (affine && n_mine < a.N) ? a.alpha[n_mine] : 1.f;
             const float be_mine = (affine && n_mine < a.N) ? a.beta[n_mine] : 0.f;
-            float* stg = staging + (warp - 2) * 32 * kStgStride;
+            float* stg = staging + (warp - 4) * 32 * kStgStride;
             const float lo = a.lo, hi = a.hi;
             const bool vec = (a.HW & 3) == 0;
 #pragma unroll
@@ -323,27 +332,39 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 __syncwarp();
                 if (vec) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int r = 4 * k + (lane >> 3), cq = lane & 7;
-                        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgStride + 4 * cq);
-                        const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
-                        const int n = n0 + quad * 32 + r, p = p0 + c0 + 4 * cq;
-                        if (n < a.N && p < a.HW) {     // HW % 4 == 0: a float4 is entirely inside or outside the row
-                            const size_t off = ((size_t)img * a.N + n) * a.HW + p;
-                            if (affine) {
-                                v.x = __fadd_rn(__fmul_rn(v.x, al), be);
-                                v.y = __fadd_rn(__fmul_rn(v.y, al), be);
-                                v.z = __fadd_rn(__fmul_rn(v.z, al), be);
-                                v.w = __fadd_rn(__fmul_rn(v.w, al), be);
+                    for (int half = 0; half < 2; ++half) {
+                        float4 rr[4];
+                        if (a.residual) {          // four residual loads in flight per thread (L2 hits after the prefetch)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int n = n0 + quad * 32 + 4 * (4 * half + k) + (lane >> 3), p = p0 + c0 + 4 * (lane & 7);
+                                rr[k] = (n < a.N && p < a.HW)
+                                            ? __ldg(reinterpret_cast<const float4*>(a.residual + ((size_t)img * a.N + n) * a.HW + p))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                             }
-                            if (a.residual) {
-                                const float4 rr = __ldg(reinterpret_cast<const float4*>(a.residual + off));
-                                v.x = __fadd_rn(v.x, rr.x); v.y = __fadd_rn(v.y, rr.y);
-                                v.z = __fadd_rn(v.z, rr.z); v.w = __fadd_rn(v.w, rr.w);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int r = 4 * (4 * half + k) + (lane >> 3), cq = lane & 7;
+                            float4 v = *reinterpret_cast<const float4*>(stg + r * kStgStride + 4 * cq);
+                            const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
+                            const int n = n0 + quad * 32 + r, p = p0 + c0 + 4 * cq;
+                            if (n < a.N && p < a.HW) {     // HW % 4 == 0: a float4 is entirely inside or outside the row
+                                const size_t off = ((size_t)img * a.N + n) * a.HW + p;
+                                if (affine) {
+                                    v.x = __fadd_rn(__fmul_rn(v.x, al), be);
+                                    v.y = __fadd_rn(__fmul_rn(v.y, al), be);
+                                    v.z = __fadd_rn(__fmul_rn(v.z, al), be);
+                                    v.w = __fadd_rn(__fmul_rn(v.w, al), be);
+                                }
+                                if (a.residual) {
+                                    v.x = __fadd_rn(v.x, rr[k].x); v.y = __fadd_rn(v.y, rr[k].y);
+                                    v.z = __fadd_rn(v.z, rr[k].z); v.w = __fadd_rn(v.w, rr[k].w);
+                                }
+                                v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
+                                v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
+                                *reinterpret_cast<float4*>(a.out + off) = v;
                             }
-                            v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
-                            v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
-                            *reinterpret_cast<float4*>(a.out + off) = v;
                         }
                     }
                 } else {
@@ -431,7 +452,7 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
     GPFQ_CHECK_LAUNCH();
 
-    CUtensorMap tmWh, tmWl, tmX;
+    CUtensorMap tmWh, tmWl, tmX, tmRes;
     {
         cuuint64_t dims[2] = {(cuuint64_t)Cp, (cuuint64_t)N};
         cuuint64_t strides[1] = {(cuuint64_t)Cp * sizeof(float)};
@@ -454,10 +475,19 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     GPFQ_REQUIRE(total < (1ll << 31), "conv1x1_tc: too many tiles");
     a.total_tiles = (int)total;
     a.four_terms = C <= 128 ? 1 : 0;
+    a.prefetch_residual = 0;
+    tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
+    if (residual != nullptr && HW % 4 == 0) {
+        cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)N, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)N * HW * sizeof(float)};
+        cuuint32_t box[3] = {(cuuint32_t)kTN, (cuuint32_t)kTM, 1};
+        if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        a.prefetch_residual = 1;
+    }
     if (int rc = ensure_dynamic_smem((const void*)conv1x1_tc_kernel, kSmemBytes)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
     profile_mark_begin(stream);
-    conv1x1_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, a);
+    conv1x1_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, tmRes, a);
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
                          2.0 * B * (double)HW * C * N, 3);

@@ -397,17 +397,19 @@ class QuantizeNeuralNet:
                                                         layer_key=id(layer), **common)
             done = torch.cuda.Event()
             done.record(stream)
-        return layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side
+        alphabet = (_sa._delta_tensor(delta, self.device), K, _sa.mode_of(self.reg, self.stochastic_quantization),
+                    float(self.lamb) if self.reg in ('L1', 'L0') else 0.0)
+        return layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side, alphabet
 
     def _finish_layer(self, pending):
-        layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side = pending
+        layer_idx, Q, err2, ref2, n0, n1, groups, W_shape, done, side, alphabet = pending
         main = torch.cuda.current_stream(self.device)
         if side is not None:
             main.wait_event(done)
             for t in (Q, err2, ref2):
                 t.record_stream(main)
         with self._Phase(self, layer_idx, 'gather'):
-            Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group)
+            Q, err2, ref2 = gather_layer(Q, err2, ref2, n0, n1, groups, self.process_group, alphabet)
         quantize_error, relative_quantize_error, _, _ = reduce_errors(err2, ref2, groups)
         self.quantized_network_layers[layer_idx].weight.data = Q.reshape(W_shape).float()
         self.layer_log.append((layer_idx, quantize_error, relative_quantize_error))

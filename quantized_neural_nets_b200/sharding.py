@@ -61,14 +61,35 @@ def unpack_all(full, N, d):
     return Q, err2, ref2
 
 
-def gather_layer(Q, err2, ref2, n0, n1, groups=1, group=None):
+def gather_layer(Q, err2, ref2, n0, n1, groups=1, group=None, alphabet=None):
     """All-gather the solved slices so that every rank holds the full Q (N x d) and the full
-    per-neuron squared norms.  The layer's only collective."""
+    per-neuron squared norms.  The layer's only collective.
+
+    ``alphabet`` = (delta 1-element device tensor, K, mode, lam): on CUDA the slice then travels as int8 level
+    indices plus the two fp64 norms per neuron (a quarter of the fp32 volume; Q = level * delta exactly), packed by
+    ONE kernel and unpacked by ONE kernel (gpfq_pack_slice_f32 / gpfq_unpack_slices_f32).  Without it (CPU tensors
+    of the gloo tests, alphabets beyond int8) fp32 rows are exchanged with torch ops."""
     world, _ = _world(group)
     if world == 1:
         return Q, err2, ref2
     N, d = Q.shape
     per = slice_rows(N, groups, world)
+    if alphabet is not None and Q.is_cuda:
+        from . import _lib
+        delta, K, mode, lam = alphabet
+        if K + (1 if mode == _lib.MODE_HARD else 0) <= 127:
+            rb = int(_lib.lib.gpfq_slice_row_bytes(d))
+            mine = torch.empty(per * rb, dtype=torch.uint8, device=Q.device)
+            bad = torch.empty(1, dtype=torch.int32, device=Q.device)
+            _lib.launch(_lib.lib.gpfq_pack_slice_f32, Q, Q.stride(0), d, n0, n1, per, delta, int(K), int(mode), float(lam),
+                        err2, ref2, mine, bad)
+            full = torch.empty(world * per * rb, dtype=torch.uint8, device=Q.device)
+            dist.all_gather_into_tensor(full, mine, group=group)
+            Qf = torch.empty((N, d), dtype=torch.float32, device=Q.device)
+            e2 = torch.empty(N, dtype=torch.float64, device=Q.device)
+            r2 = torch.empty(N, dtype=torch.float64, device=Q.device)
+            _lib.launch(_lib.lib.gpfq_unpack_slices_f32, full, N, d, delta, int(K), int(mode), float(lam), Qf, d, e2, r2)
+            return Qf, e2, r2
     mine = pack_slice(Q, err2, ref2, n0, n1, per)
     full = torch.empty((world * per, d + 4), dtype=torch.float32, device=Q.device)
     dist.all_gather_into_tensor(full, mine, group=group)

@@ -321,6 +321,7 @@ def test_conv1x1_tensor_core_kernel(B, C, N, H, W, with_res, lo, hi):
     launch(lib.gpfq_bn_act_f32, plain, res, alpha, beta, two_pass, B * N, N, H * W, lo, hi)
     assert torch.equal(fused, two_pass)
     # and against cuDNN's fp32 convolution
+    torch.backends.cudnn.allow_tf32 = False
     cud = torch.nn.functional.conv2d(x, w.view(N, C, 1, 1))
     assert (plain - cud).norm() <= 2e-6 * cud.norm()
 
@@ -382,3 +383,47 @@ def test_fused_resnet50_forward_with_tensor_core_convolutions():
     handle.remove()
     assert seen == [((8, 128, 28, 28), (8, 512, 28, 28))]
     assert (got2 - want).norm() <= 2e-5 * want.norm()
+
+
+@pytest.mark.parametrize("reg,lam,groups", [(None, 0.0, 1), ("L0", 0.004, 1), ("L1", 0.002, 1), (None, 0.0, 4)])
+def test_slice_exchange_kernels_round_trip(reg, lam, groups):
+    """The layer's all-gather payload (int8 levels + two fp64 norms per neuron, gpfq_pack_slice_f32) unpacked from the
+    concatenation of 1 / 2 / 3 / 8 ranks' buffers reproduces the solver's Q bit for bit and the norms exactly."""
+    from quantized_neural_nets_b200 import _lib, step_algorithm as sa
+    from quantized_neural_nets_b200.sharding import neuron_slice, slice_rows
+    lib, launch = _lib.lib, _lib.launch
+    N, d, m, K = 52, 45, 200, 8
+    W, X, Xq = gc._problem(seed=97, N=N, d=d * groups, m=m, relu=True, xq_noise=0.02)
+    W = W[:, :d].contiguous()
+    step = 1.16 / K
+    Wd, Xd, Xqd = W.to(DEV), X.to(DEV), Xq.to(DEV)
+    Q, e2, r2 = sa.quantize_layer_impl(Wd, Xd, Xqd, m, step, K, 1, reg, lam, groups, False, DEV, return_partials=True)
+    delta = sa._delta_tensor(sa.layer_delta(Wd, step, K, 1, reg, lam), DEV)
+    mode = sa.mode_of(reg, False)
+    rb = int(lib.gpfq_slice_row_bytes(d))
+    assert rb == (d + 7) // 8 * 8 + 16
+    for world in (1, 2, 3, 8):
+        per = slice_rows(N, groups, world)
+        bufs = []
+        for rank in range(world):
+            n0, n1 = neuron_slice(N, groups, world=world, rank=rank)
+            Qr = torch.zeros_like(Q)
+            Qr[n0:n1] = Q[n0:n1]                   # what a rank holds: its own rows, zeros elsewhere
+            buf = torch.full((per * rb,), 0xAB, dtype=torch.uint8, device=DEV)
+            bad = torch.ones(1, dtype=torch.int32, device=DEV)
+            launch(lib.gpfq_pack_slice_f32, Qr, Qr.stride(0), d, n0, n1, per, delta, K, mode, float(lam), e2, r2, buf, bad)
+            assert int(bad.item()) == 0
+            bufs.append(buf)
+        full = torch.cat(bufs)
+        Qf = torch.full((N, d), float("nan"), device=DEV)
+        ef = torch.zeros(N, dtype=torch.float64, device=DEV)
+        rf = torch.zeros(N, dtype=torch.float64, device=DEV)
+        launch(lib.gpfq_unpack_slices_f32, full, N, d, delta, K, mode, float(lam), Qf, d, ef, rf)
+        assert torch.equal(Qf, Q) and torch.equal(ef, e2) and torch.equal(rf, r2), world
+    # a value off the alphabet is reported, not rounded away
+    Qbad = Q.clone()
+    Qbad[3, 7] += 1e-3
+    buf = torch.zeros(N * rb, dtype=torch.uint8, device=DEV)
+    bad = torch.zeros(1, dtype=torch.int32, device=DEV)
+    launch(lib.gpfq_pack_slice_f32, Qbad, d, d, 0, N, N, delta, K, mode, float(lam), e2, r2, buf, bad)
+    assert int(bad.item()) == 1
