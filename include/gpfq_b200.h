@@ -188,6 +188,10 @@ int gpfq_solve_grouped_f32(const float* W, int64_t ldw, const float* X, const fl
  * Not for use inside a timed region. */
 int gpfq_profile_begin(void);
 int gpfq_profile_end(double* out_host);
+/* After gpfq_profile_end(): totals of one kernel kind over the profiled region, out[4] = { launches, ms, algorithmic
+ * bytes, instructions or flops }.  kind: 0 sweep_kernel, 1 resident_kernel, 2 bn_act_kernel, 3 conv1x1_tc_kernel (flops =
+ * 2*B*HW*C*N algorithmic), 4 gram_tc_kernel (flops = algorithmic 2*d*d*m per product), 5 gram_path_kernel, 6 recur_kernel. */
+int gpfq_profile_kind(int32_t kind, double* out_host);
 
 /* Number of kernels the library has launched so far on behalf of this process (bench.py's
  * gpu_launches counter). */

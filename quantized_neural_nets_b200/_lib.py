@@ -27,6 +27,7 @@ SIGNATURES = {
     "gpfq_launch_count": (c_i64, []),
     "gpfq_profile_begin": (c_i32, []),
     "gpfq_profile_end": (c_i32, [ctypes.POINTER(ctypes.c_double)]),
+    "gpfq_profile_kind": (c_i32, [c_i32, ctypes.POINTER(ctypes.c_double)]),
     "gpfq_quantize_f32": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, ctypes.c_uint64, c_ptr]),
     "gpfq_bn_act_f32": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f32, c_f32, c_ptr]),
     "gpfq_conv1x1_f32": (c_i32, [c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr, ctypes.c_size_t, c_ptr]),
@@ -136,6 +137,11 @@ def profile_end():
     resident_ms, resident_fp32_instr, bn_act_launches, bn_act_ms, bn_act_bytes)"""
     out = (ctypes.c_double * 12)()
     check(lib.gpfq_profile_end(out))
-    return dict(sweep_launches=int(out[0]), sweep_ms=out[1], sweep_bytes=out[2], sweep_fp32_instr=out[3],
+    prof = dict(sweep_launches=int(out[0]), sweep_ms=out[1], sweep_bytes=out[2], sweep_fp32_instr=out[3],
                 other_launches=int(out[4]), resident_launches=int(out[5]), resident_ms=out[6],
                 resident_fp32_instr=out[7], bn_act_launches=int(out[8]), bn_act_ms=out[9], bn_act_bytes=out[10])
+    for kind, name in ((3, "conv"), (4, "gram_tc"), (5, "gram_path"), (6, "recur")):
+        k = (ctypes.c_double * 4)()
+        check(lib.gpfq_profile_kind(kind, k))
+        prof[name] = dict(launches=int(k[0]), ms=k[1], bytes=k[2], flops=k[3])
+    return prof

@@ -42,8 +42,11 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
 struct ProfileRec {
     cudaEvent_t a, b;
     double bytes, instr;
-    int kind;       // 0 = sweep_kernel launch, 1 = resident_kernel launch, 2 = bn_act_kernel launch
+    int kind;       // 0 = sweep_kernel, 1 = resident_kernel, 2 = bn_act_kernel, 3 = conv1x1_tc_kernel, 4 = gram_tc_kernel,
+                    // 5 = gram_path_kernel, 6 = recur_kernel
 };
+constexpr int kProfileKinds = 8;
+static double g_kind_totals[kProfileKinds][4];      // launches, ms, algorithmic bytes, instructions / flops
 static bool g_profile = false;
 static std::vector<ProfileRec> g_recs;
 static double g_other = 0;
@@ -368,18 +371,24 @@ int gpfq_profile_begin(void) {
 
 int gpfq_profile_end(double* out_host) {
     g_profile = false;
-    double n[3] = {0, 0, 0}, ms_total[3] = {0, 0, 0}, bytes[3] = {0, 0, 0}, instr[3] = {0, 0, 0};
+    double n[kProfileKinds] = {}, ms_total[kProfileKinds] = {}, bytes[kProfileKinds] = {}, instr[kProfileKinds] = {};
     for (auto& r : g_recs) {
         GPFQ_CUDA_TRY(cudaEventSynchronize(r.b));
         float ms = 0;
         GPFQ_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
-        const int k = r.kind >= 0 && r.kind <= 2 ? r.kind : 0;
+        const int k = r.kind >= 0 && r.kind < kProfileKinds ? r.kind : kProfileKinds - 1;
         n[k] += 1;
         ms_total[k] += ms;
         bytes[k] += r.bytes;
         instr[k] += r.instr;
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
+    }
+    for (int k = 0; k < kProfileKinds; ++k) {
+        g_kind_totals[k][0] = n[k];
+        g_kind_totals[k][1] = ms_total[k];
+        g_kind_totals[k][2] = bytes[k];
+        g_kind_totals[k][3] = instr[k];
     }
     if (out_host) {
         out_host[0] = n[0];
@@ -396,6 +405,12 @@ int gpfq_profile_end(double* out_host) {
         out_host[11] = 0;
     }
     g_recs.clear();
+    return 0;
+}
+
+int gpfq_profile_kind(int32_t kind, double* out_host) {
+    GPFQ_REQUIRE(kind >= 0 && kind < kProfileKinds && out_host, "gpfq_profile_kind: bad kind");
+    for (int i = 0; i < 4; ++i) out_host[i] = g_kind_totals[kind][i];
     return 0;
 }
 

@@ -5,30 +5,33 @@
 //
 // These layers are the bulk of the forward passes the reference prescribes (quantize_neural_net.py:256-269 re-runs both
 // networks from the image for every layer; with the solver on the GPU that is 97 % of a step).  fp32 accuracy is kept
-// by the split-TF32 scheme of gram_tc_kernel: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), three MMAs per
+// by the split-TF32 scheme of gram_tc_kernel: x = hi + lo with hi = x rounded to 11 bits and lo = x - hi, three MMAs per
 // product (lo*hi, hi*lo, hi*hi), and -- because the tensor core accumulates fp32 with truncation -- a FRESH TMEM
 // accumulator per 32-channel k-block that the epilogue warps add up in registers with round-to-nearest.
 //
-// Structure (one persistent CTA per SM, 256 threads, tiles of 128 output channels x 128 pixels of one image):
+// Structure (one persistent CTA per SM, 512 threads, tiles of 128 output channels x 128 pixels of one image):
 //   warp 0      TMA producer: per k-block the weight planes w_hi / w_lo (boxes [128][32], SWIZZLE_128B, K-major) and the
 //               RAW fp32 activation (four boxes [32 channels][32 pixels], SWIZZLE_128B_ATOM_32B: the B operand is
-//               MN-major -- the pixel index is the contiguous one in NCHW), 3-stage ring that runs on across tiles;
-//   warps 2-3   split: turn the raw activation tile into its TF32 hi plane in place and the lo plane next to it (an
-//               elementwise map, so the swizzled layout is untouched), fence.proxy.async, release the MMA warp --
-//               the activation is read from HBM exactly once;
+//               MN-major -- the pixel index is the contiguous one in NCHW), 3-stage ring that runs on across tiles; one
+//               bulk L2 prefetch of the tile's residual when there is one;
+//   warps 4-7   split: turn the raw activation tile into its hi plane in place and the lo plane next to it (an
+//               elementwise map, so the swizzled layout is untouched; Veltkamp's split on the FMA pipe, see below),
+//               fence.proxy.async, release the MMA warp -- the activation is read from HBM exactly once;
 //   warp 1      single-thread tcgen05.mma issue, 12 MMAs (M = N = 128, K = 8, kind::tf32) per k-block into one of FOUR
 //               128-column TMEM accumulators (all 512 columns): the MMAs run up to four k-blocks ahead of the drain;
-//   warps 4-7   drain each finished accumulator (tcgen05.ld 32x32b) into 128 fp32 registers per thread (thread = output
-//               channel, register = pixel) and, after the tile's last k-block, apply alpha / beta / residual / clamp and
-//               store the row segment.  While they store, the MMA warp is already working on the next tile.
+//   warps 8-15  drain each finished accumulator (tcgen05.ld 32x32b) into 64 fp32 registers per thread (thread = output
+//               channel, register = pixel) and, after the tile's last k-block, transpose 32 x 16 blocks through shared
+//               memory, apply alpha / beta / residual / clamp and store whole row segments.  While they store, the MMA
+//               warp is already working on the next tile.
 //
 // The MN-major recipe (validated on B200 in round 1, experimental/conv1x1_tf32x3.cu): for 32-bit operands the only
 // MN-major shared-memory layout UMMA accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1), written by TMA with
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; LBO = bytes between 32-pixel chunks (one box, 4096), SBO = 512 (a swizzle
 // atom is 4 channel rows of 128 bytes), +1024 bytes per K = 8 step, instruction-descriptor bit 16 (B is MN-major).
 //
-// Shapes: HW % 4 == 0 (TMA global strides are multiples of 16 bytes); any C (the channel tail of a k-block is zero-filled
-// by TMA on both operands) and any N.  Other shapes return GPFQ_CONV_UNSUPPORTED and the caller uses another path.
+// Shapes: the activation's pixel pitch must be a multiple of 4 floats (TMA global strides are multiples of 16 bytes;
+// gpfq_conv_patches_f32 pads it when it is not); any C (the channel tail of a k-block is zero-filled by TMA on both
+// operands), any N, any HW.
 #include <algorithm>
 
 #include "gpfq_common.cuh"
@@ -46,10 +49,14 @@ constexpr int kAccs = 4;            // TMEM accumulators of kTN columns
 constexpr int kATile = kTM * kBK;   // floats per weight plane tile (16 KB)
 constexpr int kBTile = kBK * kTN;   // floats per activation plane tile (16 KB) = 4 boxes [32 ch][32 px]
 constexpr int kStageFloats = 2 * kATile + 2 * kBTile;      // w_hi | w_lo | x_hi (raw on arrival) | x_lo
-constexpr int kThreads = 256;        // 8 warps, two per SM sub-partition: the register file then allows 255 per thread
-constexpr int kSplitThreads = 64;    // warps 2-3
-constexpr int kStgStride = 36;      // floats per staged row: 32 pixels + 4 of padding (conflict-free float4 rows)
-constexpr int kStgFloats = 4 * 32 * kStgStride;            // one 32 x 32 transposition buffer per drain warp
+// 16 warps = 4 per SM sub-partition (128 registers each): warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-7 split, warps
+// 8-15 drain (two per TMEM lane quarter, 64 accumulator columns each).  Ten warps with 128-column drains were tried first:
+// three warps on a sub-partition cap the allocation at 168 registers and the 128 running sums spill.
+constexpr int kThreads = 512;
+constexpr int kFirstSplitWarp = 4, kSplitWarps = 4;
+constexpr int kFirstDrainWarp = 8, kDrainWarps = 8;
+constexpr int kStgStride = 20;      // floats per staged row: 16 pixels + 4 of padding
+constexpr int kStgFloats = kDrainWarps * 32 * kStgStride;  // one 32 x 16 transposition buffer per drain warp
 constexpr size_t kSmemBytes = (size_t)(kStages * kStageFloats + kStgFloats) * sizeof(float) + 256;
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -122,6 +129,26 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// Veltkamp split at 13 bits: hi = x rounded to nearest at 11 significant bits, lo = x - hi exactly (three roundings, none
+// of them contracted)
+__device__ __forceinline__ void veltkamp_split(float x, float& hi, float& lo) {
+    const float p = __fmul_rn(x, 8193.0f);
+    hi = __fsub_rn(p, __fsub_rn(p, x));
+    lo = __fsub_rn(x, hi);
+}
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
@@ -145,7 +172,6 @@ struct ConvArgs {
     float lo, hi;
     int C, N, HW, B;
     int n_tiles, p_tiles, total_tiles;
-    int four_terms;          // also issue lo*lo (short reductions: the dropped term is not averaged away)
     int prefetch_residual;   // tmRes is valid
 };
 
@@ -185,12 +211,12 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], kSplitThreads / 32);      // one arrival per split warp
+            mbar_init(&split[s], kSplitWarps);       // one arrival per split warp
             mbar_init(&empty[s], 1);
         }
         for (int b = 0; b < kAccs; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);       // one arrival per drain warp
+            mbar_init(&acc_empty[b], kDrainWarps);   // one arrival per drain warp
         }
         fence_barrier_init();
     }
@@ -254,8 +280,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 for (int k8 = 0; k8 < kBK / 8; ++k8) {
                     const uint64_t adv_a = (uint64_t)((k8 * 8 * sizeof(float)) >> 4);     // 32 bytes along K
                     const uint64_t adv_b = (uint64_t)((k8 * 1024) >> 4);                  // 8 channel rows
-                    if (a.four_terms) umma_tf32(d_tmem, d_wl + adv_a, d_xl + adv_b, kIdesc, k8 > 0);
-                    umma_tf32(d_tmem, d_wl + adv_a, d_xh + adv_b, kIdesc, (k8 > 0) | a.four_terms);
+                    umma_tf32(d_tmem, d_wl + adv_a, d_xh + adv_b, kIdesc, k8 > 0);
                     umma_tf32(d_tmem, d_wh + adv_a, d_xl + adv_b, kIdesc, 1);
                     umma_tf32(d_tmem, d_wh + adv_a, d_xh + adv_b, kIdesc, 1);
                 }
@@ -263,9 +288,13 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 umma_commit(&acc_full[b]);
             }
         }
-    } else if (warp < 4) {
-        // split warps (2, 3): raw fp32 (written by TMA) -> hi in place, lo next to it
-        const int t = threadIdx.x - 2 * 32;        // 0 .. kSplitThreads-1
+    } else if (warp >= kFirstSplitWarp && warp < kFirstSplitWarp + kSplitWarps) {
+        // split warps: raw fp32 (written by TMA) -> hi in place, lo next to it.  cvt.rna.tf32 runs on the XU pipe (16
+        // lanes per SM: an ncu capture of the first version showed it 59 % busy and everything else idle), so the split
+        // is Veltkamp's, three fp32 operations on the FMA pipe: p = x * (2^13 + 1), hi = p - (p - x) is x rounded to
+        // nearest at 11 significant bits -- exactly representable in TF32 -- and lo = x - hi is exact; the tensor core
+        // reads the leading 11 bits of lo (|lo| <= 2^-11 |x|, so what it drops is below 2^-21 |x|, of either sign).
+        const int t = threadIdx.x - kFirstSplitWarp * 32;        // 0 .. 32 * kSplitWarps - 1
         const int total = my_tiles * nkb;
         for (int it = 0; it < total; ++it) {
             const int s = it % kStages;
@@ -273,105 +302,111 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats + 2 * kATile);
             float4* lo = hi + kBTile / 4;
 #pragma unroll 8
-            for (int i = 0; i < kBTile / 4 / kSplitThreads; ++i) {
-                const float4 v = hi[t + kSplitThreads * i];
+            for (int i = 0; i < kBTile / 4 / (32 * kSplitWarps); ++i) {
+                const float4 v = hi[t + 32 * kSplitWarps * i];
                 float4 h, l;
-                h.x = to_tf32(v.x); l.x = to_tf32(v.x - h.x);
-                h.y = to_tf32(v.y); l.y = to_tf32(v.y - h.y);
-                h.z = to_tf32(v.z); l.z = to_tf32(v.z - h.z);
-                h.w = to_tf32(v.w); l.w = to_tf32(v.w - h.w);
-                hi[t + kSplitThreads * i] = h;
-                lo[t + kSplitThreads * i] = l;
+                veltkamp_split(v.x, h.x, l.x);
+                veltkamp_split(v.y, h.y, l.y);
+                veltkamp_split(v.z, h.z, l.z);
+                veltkamp_split(v.w, h.w, l.w);
+                hi[t + 32 * kSplitWarps * i] = h;
+                lo[t + 32 * kSplitWarps * i] = l;
             }
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
-    } else {
-        const int quad = warp & 3;                 // TMEM lanes 32*quad .. 32*quad+31 belong to this warp
+    } else if (warp >= kFirstDrainWarp) {
+        // drain warps: warp (quad, half) owns TMEM lanes 32*quad .. +31 (a warp may only touch the lane quarter given by
+        // its index mod 4) and columns 64*half .. +63 of every accumulator
+        const int quad = warp & 3;
+        const int half = (warp - kFirstDrainWarp) >> 2;
         const int row = quad * 32 + lane;          // output channel within the tile
+        constexpr int kCols = kTN / 2;             // 64 columns per drain warp
+        float* stg = staging + (warp - kFirstDrainWarp) * 32 * kStgStride;
         int it = 0;
         for (int i = 0; i < my_tiles; ++i) {
             int img, p0, n0;
             tile_coords(i, img, p0, n0);
-            float run[kTN];
+            float run[kCols];
 #pragma unroll
-            for (int c = 0; c < kTN; ++c) run[c] = 0.f;
+            for (int c = 0; c < kCols; ++c) run[c] = 0.f;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int b = it % kAccs;
                 mbar_wait(&acc_full[b], (uint32_t)((it / kAccs) & 1));
                 tc_fence_after();
 #pragma unroll
-                for (int c0 = 0; c0 < kTN; c0 += 32) {
-                    float v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + c0), v);
+                for (int c0 = 0; c0 < kCols; c0 += 16) {
+                    float v[16];
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + half * kCols + c0), v);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) run[c0 + e] = __fadd_rn(run[c0 + e], v[e]);
+                    for (int e = 0; e < 16; ++e) run[c0 + e] = __fadd_rn(run[c0 + e], v[e]);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[b]);
             }
-            // Epilogue.  run[] holds one output channel per thread; 32 x 32 blocks go through a per-warp shared-memory
-            // transposition so that every global access of the warp covers whole 128-byte row segments (4 rows x 32
+            // Epilogue.  run[] holds one output channel per thread; 32 x 16 blocks go through a per-warp shared-memory
+            // transposition so that every global access of the warp covers whole 64-byte row segments (8 rows x 16
             // pixels per float4 instruction) instead of 32 different rows.
             const bool affine = a.alpha != nullptr;
             const int n_mine = n0 + row;
             const float al_mine = (affine && n_mine < a.N) ? a.alpha[n_mine] : 1.f;
             const float be_mine = (affine && n_mine < a.N) ? a.beta[n_mine] : 0.f;
-            float* stg = staging + (warp - 4) * 32 * kStgStride;
             const float lo = a.lo, hi = a.hi;
             const bool vec = (a.HW & 3) == 0;
+            const int pw0 = p0 + half * kCols;     // first pixel of this warp's columns
 #pragma unroll
-            for (int c0 = 0; c0 < kTN; c0 += 32) {
-                if (p0 + c0 >= a.HW) break;        // uniform over the warp
+            for (int c0 = 0; c0 < kCols; c0 += 16) {
+                if (pw0 + c0 >= a.HW) break;       // uniform over the warp
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * j) =
                         make_float4(run[c0 + 4 * j], run[c0 + 4 * j + 1], run[c0 + 4 * j + 2], run[c0 + 4 * j + 3]);
                 __syncwarp();
                 if (vec) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float4 rr[4];
-                        if (a.residual) {          // four residual loads in flight per thread (L2 hits after the prefetch)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int n = n0 + quad * 32 + 4 * (4 * half + k) + (lane >> 3), p = p0 + c0 + 4 * (lane & 7);
-                                rr[k] = (n < a.N && p < a.HW)
-                                            ? __ldg(reinterpret_cast<const float4*>(a.residual + ((size_t)img * a.N + n) * a.HW + p))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                        }
+                    const int cq = lane & 3;
+                    const int p = pw0 + c0 + 4 * cq;
+                    float4 rr[4];
+                    if (a.residual) {              // four residual loads in flight per thread (L2 hits after the prefetch)
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const int r = 4 * (4 * half + k) + (lane >> 3), cq = lane & 7;
-                            float4 v = *reinterpret_cast<const float4*>(stg + r * kStgStride + 4 * cq);
-                            const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
-                            const int n = n0 + quad * 32 + r, p = p0 + c0 + 4 * cq;
-                            if (n < a.N && p < a.HW) {     // HW % 4 == 0: a float4 is entirely inside or outside the row
-                                const size_t off = ((size_t)img * a.N + n) * a.HW + p;
-                                if (affine) {
-                                    v.x = __fadd_rn(__fmul_rn(v.x, al), be);
-                                    v.y = __fadd_rn(__fmul_rn(v.y, al), be);
-                                    v.z = __fadd_rn(__fmul_rn(v.z, al), be);
-                                    v.w = __fadd_rn(__fmul_rn(v.w, al), be);
-                                }
-                                if (a.residual) {
-                                    v.x = __fadd_rn(v.x, rr[k].x); v.y = __fadd_rn(v.y, rr[k].y);
-                                    v.z = __fadd_rn(v.z, rr[k].z); v.w = __fadd_rn(v.w, rr[k].w);
-                                }
-                                v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
-                                v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
-                                *reinterpret_cast<float4*>(a.out + off) = v;
+                            const int n = n0 + quad * 32 + 8 * k + (lane >> 2);
+                            rr[k] = (n < a.N && p < a.HW)
+                                        ? __ldg(reinterpret_cast<const float4*>(a.residual + ((size_t)img * a.N + n) * a.HW + p))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = 8 * k + (lane >> 2);
+                        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgStride + 4 * cq);
+                        const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
+                        const int n = n0 + quad * 32 + r;
+                        if (n < a.N && p < a.HW) {     // HW % 4 == 0: a float4 is entirely inside or outside the row
+                            const size_t off = ((size_t)img * a.N + n) * a.HW + p;
+                            if (affine) {
+                                v.x = __fadd_rn(__fmul_rn(v.x, al), be);
+                                v.y = __fadd_rn(__fmul_rn(v.y, al), be);
+                                v.z = __fadd_rn(__fmul_rn(v.z, al), be);
+                                v.w = __fadd_rn(__fmul_rn(v.w, al), be);
                             }
+                            if (a.residual) {
+                                v.x = __fadd_rn(v.x, rr[k].x); v.y = __fadd_rn(v.y, rr[k].y);
+                                v.z = __fadd_rn(v.z, rr[k].z); v.w = __fadd_rn(v.w, rr[k].w);
+                            }
+                            v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
+                            v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
+                            *reinterpret_cast<float4*>(a.out + off) = v;
                         }
                     }
                 } else {
-                    for (int r = 0; r < 32; ++r) {     // lane = pixel: one 128-byte row segment per instruction
-                        float v = stg[r * kStgStride + lane];
+                    const int c = lane & 15, r0 = lane >> 4;       // two rows of 16 pixels per instruction
+                    for (int k = 0; k < 16; ++k) {
+                        const int r = 2 * k + r0;
+                        float v = stg[r * kStgStride + c];
                         const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
-                        const int n = n0 + quad * 32 + r, p = p0 + c0 + lane;
+                        const int n = n0 + quad * 32 + r, p = pw0 + c0 + c;
                         if (n < a.N && p < a.HW) {
                             const size_t off = ((size_t)img * a.N + n) * a.HW + p;
                             if (affine) v = __fadd_rn(__fmul_rn(v, al), be);
@@ -474,7 +509,6 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     const int64_t total = (int64_t)a.n_tiles * a.p_tiles * B;
     GPFQ_REQUIRE(total < (1ll << 31), "conv1x1_tc: too many tiles");
     a.total_tiles = (int)total;
-    a.four_terms = C <= 128 ? 1 : 0;
     a.prefetch_residual = 0;
     tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
     if (residual != nullptr && HW % 4 == 0) {

@@ -63,11 +63,12 @@ for (cin, cout, hw, count, with_res) in ((64, 64, 56, 1, False), (64, 256, 56, 1
         ref = ref.clamp(min=0)
         mag = torch.einsum("nc,bchw->bnhw", w.double().abs(), x[:nb].double().abs()) * alpha.double()[None, :, None, None]
         err = ((out[:nb].double() - ref).abs() / (mag + 1e-30)).max().item()
+        l2 = ((out[:nb].double() - ref).norm() / ref.norm()).item()
     bytes_ = 4.0 * B * hw * hw * (cin + cout * (2 if with_res else 1))
     fl = 2.0 * B * hw * hw * cin * cout
     tot_f += tf * count
     tot_c += tu * count
     print(f"{cin:5d}->{cout:5d} @{hw:3d}{' +res' if with_res else '     '}: fused {tf:.3f} ms ({bytes_ / tf / 1e6:7.0f} GB/s = "
           f"{bytes_ / tf / 1e6 / HBM:.2f} of HBM, {fl / tf / 1e9:6.1f} TF/s)   cuDNN conv + bn_act {tu:.3f} ms   "
-          f"worst |err| / sum|terms| {err:.1e}", flush=True)
+          f"worst |err| / sum|terms| {err:.1e}, rel L2 {l2:.1e}", flush=True)
 print(f"per full ResNet-50 forward (stride-1 1x1 layers with HW % 4 == 0): fused {tot_f:.2f} ms, cuDNN + bn_act {tot_c:.2f} ms")
