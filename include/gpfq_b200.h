@@ -134,7 +134,9 @@ size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m
 /* Gram matrices of the layer inputs (the tensor-core piece of the Gram solvers, exposed for tests and
  * profiling):  GT = X Xq^T,  H = Xq Xq^T,  A = X X^T, each (d x ldg) fp64 row-major with ldg = round_up(d, 64).
  * solver = GPFQ_SOLVER_GRAM (tcgen05 split-TF32) or GPFQ_SOLVER_GRAM_F64 (fp64 SIMT).  Workspace:
- * gpfq_workspace_bytes(solver, 1, d, m). */
+ * gpfq_gram_workspace_bytes(solver, d, m) (any d; gpfq_workspace_bytes(solver, 1, d, m) is the same number where the
+ * whole Gram SOLVER supports d, and 0 beyond that). */
+size_t gpfq_gram_workspace_bytes(int32_t solver, int32_t d, int32_t m);
 int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, int32_t d, int32_t m,
                   double* GT, double* H, double* A, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -188,8 +190,8 @@ int gpfq_solve_grouped_f32(const float* W, int64_t ldw, const float* X, const fl
  * Not for use inside a timed region. */
 int gpfq_profile_begin(void);
 int gpfq_profile_end(double* out_host);
-/* After gpfq_profile_end(): totals of one kernel kind over the profiled region, out[4] = { launches, ms, algorithmic
- * bytes, instructions or flops }.  kind: 0 sweep_kernel, 1 resident_kernel, 2 bn_act_kernel, 3 conv1x1_tc_kernel (flops =
+/* After gpfq_profile_end(): totals of one kernel kind over the profiled region, out[5] = { launches, ms, algorithmic
+ * HBM bytes, instructions or flops, aux (sweep_kernel: algorithmic L2 -> SM bytes) }.  kind: 0 sweep_kernel, 1 resident_kernel, 2 bn_act_kernel, 3 conv1x1_tc_kernel (flops =
  * 2*B*HW*C*N algorithmic), 4 gram_tc_kernel (flops = algorithmic 2*d*d*m per product), 5 gram_path_kernel, 6 recur_kernel. */
 int gpfq_profile_kind(int32_t kind, double* out_host);
 

@@ -46,6 +46,7 @@ SIGNATURES = {
     "gpfq_transpose_f32": (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gpfq_im2col_gather_f32": (c_i32, [c_ptr] + [c_i32] * 12 + [c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gpfq_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
+    "gpfq_gram_workspace_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32]),
     "gpfq_gram_f32": (c_i32, [c_i32, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
     "gpfq_gram_path_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i32,
                                    c_i32, c_f32, ctypes.c_uint64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -140,8 +141,8 @@ def profile_end():
     prof = dict(sweep_launches=int(out[0]), sweep_ms=out[1], sweep_bytes=out[2], sweep_fp32_instr=out[3],
                 other_launches=int(out[4]), resident_launches=int(out[5]), resident_ms=out[6],
                 resident_fp32_instr=out[7], bn_act_launches=int(out[8]), bn_act_ms=out[9], bn_act_bytes=out[10])
-    for kind, name in ((3, "conv"), (4, "gram_tc"), (5, "gram_path"), (6, "recur")):
-        k = (ctypes.c_double * 4)()
+    for kind, name in ((0, "sweep"), (3, "conv"), (4, "gram_tc"), (5, "gram_path"), (6, "recur")):
+        k = (ctypes.c_double * 5)()
         check(lib.gpfq_profile_kind(kind, k))
-        prof[name] = dict(launches=int(k[0]), ms=k[1], bytes=k[2], flops=k[3])
+        prof[name] = dict(launches=int(k[0]), ms=k[1], bytes=k[2], flops=k[3], aux=k[4])
     return prof

@@ -41,12 +41,12 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
 
 struct ProfileRec {
     cudaEvent_t a, b;
-    double bytes, instr;
+    double bytes, instr, aux;
     int kind;       // 0 = sweep_kernel, 1 = resident_kernel, 2 = bn_act_kernel, 3 = conv1x1_tc_kernel, 4 = gram_tc_kernel,
                     // 5 = gram_path_kernel, 6 = recur_kernel
 };
 constexpr int kProfileKinds = 8;
-static double g_kind_totals[kProfileKinds][4];      // launches, ms, algorithmic bytes, instructions / flops
+static double g_kind_totals[kProfileKinds][5];      // launches, ms, algorithmic bytes, instructions / flops, aux
 static bool g_profile = false;
 static std::vector<ProfileRec> g_recs;
 static double g_other = 0;
@@ -58,9 +58,9 @@ void profile_mark_begin(cudaStream_t stream) {
     cudaEventCreate(&g_pending);
     cudaEventRecord(g_pending, stream);
 }
-void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr, int kind) {
+void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr, int kind, double aux) {
     if (!g_profile || !g_pending) return;
-    ProfileRec r{g_pending, nullptr, alg_bytes, fp32_instr, kind};
+    ProfileRec r{g_pending, nullptr, alg_bytes, fp32_instr, aux, kind};
     cudaEventCreate(&r.b);
     cudaEventRecord(r.b, stream);
     g_recs.push_back(r);
@@ -372,6 +372,7 @@ int gpfq_profile_begin(void) {
 int gpfq_profile_end(double* out_host) {
     g_profile = false;
     double n[kProfileKinds] = {}, ms_total[kProfileKinds] = {}, bytes[kProfileKinds] = {}, instr[kProfileKinds] = {};
+    double aux[kProfileKinds] = {};
     for (auto& r : g_recs) {
         GPFQ_CUDA_TRY(cudaEventSynchronize(r.b));
         float ms = 0;
@@ -381,6 +382,7 @@ int gpfq_profile_end(double* out_host) {
         ms_total[k] += ms;
         bytes[k] += r.bytes;
         instr[k] += r.instr;
+        aux[k] += r.aux;
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
@@ -389,6 +391,7 @@ int gpfq_profile_end(double* out_host) {
         g_kind_totals[k][1] = ms_total[k];
         g_kind_totals[k][2] = bytes[k];
         g_kind_totals[k][3] = instr[k];
+        g_kind_totals[k][4] = aux[k];
     }
     if (out_host) {
         out_host[0] = n[0];
@@ -410,7 +413,7 @@ int gpfq_profile_end(double* out_host) {
 
 int gpfq_profile_kind(int32_t kind, double* out_host) {
     GPFQ_REQUIRE(kind >= 0 && kind < kProfileKinds && out_host, "gpfq_profile_kind: bad kind");
-    for (int i = 0; i < 4; ++i) out_host[i] = g_kind_totals[kind][i];
+    for (int i = 0; i < 5; ++i) out_host[i] = g_kind_totals[kind][i];
     return 0;
 }
 

@@ -50,7 +50,7 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes);
 // bench-only per-launch timing of the dominant kernel (see gpfq_profile_begin/end)
 bool profile_on();
 void profile_mark_begin(cudaStream_t stream);
-void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr, int kind = 0);
+void profile_mark_end(cudaStream_t stream, double alg_bytes, double fp32_instr, int kind = 0, double aux = 0.0);
 void profile_count_other(int n);
 
 template <typename... KArgs, typename... Args>

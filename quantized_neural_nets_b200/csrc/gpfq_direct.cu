@@ -1432,7 +1432,10 @@ static int launch_sweep(const DirectPlan& p, const CUtensorMap& tmX, const CUten
                        4.0 * kB * (double)a.mpad * (2 + (a.has_next ? 1 : 0)) + 8.0 * a.n_rows * kB +
                        (a.has_next ? 8.0 * p.j_tiles * (double)a.n_rows * kB : 0.0);
         double instr = nm * (4.0 * a.bvalid + (a.has_next ? 1.0 * kB : 0.0));
-        profile_mark_end(stream, bytes, instr);
+        // L2 -> SM algorithmic bytes: the HBM bytes above, plus the X / Xq block tiles once more
+        // for every further neuron tile (each CTA row of the grid streams all columns of the block through L2)
+        const double l2 = bytes + (p.n_tiles - 1) * 4.0 * kB * (double)a.mpad * (2 + (a.has_next ? 1 : 0));
+        profile_mark_end(stream, bytes, instr, 0, l2);
     }
     GPFQ_CHECK_LAUNCH();
     return 0;
@@ -1581,9 +1584,11 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         r.norm32 = norm32 + (size_t)blk * kB; r.delta = delta; r.Npad = p.Npad;
         r.n_rows = n_rows; r.d = d; r.t0 = t0; r.bvalid = bvalid; r.j_tiles = p.j_tiles;
         r.first = (blk == 0); r.mode = mode; r.Kf = (float)K; r.lam = lam; r.seed = seed; r.n_base = n_base;
+        profile_mark_begin(stream);
         if (p.j_tiles >= 24) GPFQ_CUDA_TRY(launch_pdl(recur_kernel<8>, dim3(n_rows), dim3(256), 0, stream, r));
         else if (p.j_tiles >= 8) GPFQ_CUDA_TRY(launch_pdl(recur_kernel<2>, dim3((unsigned)ceil_div(n_rows, 4)), dim3(256), 0, stream, r));
         else GPFQ_CUDA_TRY(launch_pdl(recur_kernel<1>, dim3((unsigned)ceil_div(n_rows, 8)), dim3(256), 0, stream, r));
+        if (profile_on()) profile_mark_end(stream, 8.0 * p.j_tiles * (double)n_rows * kB, 0.0, 6);
         GPFQ_CHECK_LAUNCH();
         profile_count_other(1);
 

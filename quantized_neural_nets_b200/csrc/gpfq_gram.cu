@@ -62,6 +62,9 @@ size_t gram_workspace_bytes(int solver, int n_rows, int d, int m) {
     return gram_plan(solver, d, m).total;
 }
 
+// workspace of gram_matrices() alone (gpfq_gram_f32): no limit on d -- only the recurrence kernel has one
+size_t gram_matrices_workspace_bytes(int solver, int d, int m) { return gram_plan(solver, d, m).total; }
+
 // ------------------------------------------------------------------------------------------
 // fp64 SIMT Gram products.  CTA (bi, bj, split): 64x64 output tiles of
 //   GT[bi][bj] = X_bi Xq_bj^T   (always),   H[bi][bj] = Xq_bi Xq_bj^T,  A[bi][bj] = X_bi X_bj^T  (bi >= bj only)
@@ -373,9 +376,12 @@ int gram_path(const float* W, int64_t ldw, int d, int n_rows, const double* GT, 
                                                                              : (const void*)gram_path_kernel<1>;
     if (int rc = ensure_dynamic_smem(fn, smem)) return rc;
     const unsigned grid = (unsigned)ceil_div(n_rows, nb * kPathWarps);
+    profile_mark_begin(stream);
     if (nb == 4) gram_path_kernel<4><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
     else if (nb == 2) gram_path_kernel<2><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
     else gram_path_kernel<1><<<grid, kPathWarps * 32, smem, stream>>>(a, dpad32);
+    if (profile_on())      // fp64 FMAs: per neuron ~2 d^2 (two left-looking projections) + the norm terms
+        profile_mark_end(stream, 24.0 * (double)d * d * ceil_div(n_rows, nb * kPathWarps), 2.5 * (double)n_rows * d * d, 5);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

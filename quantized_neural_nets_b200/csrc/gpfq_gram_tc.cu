@@ -342,7 +342,11 @@ int gram_tc_form(const float* X, const float* Xq, int64_t ldx, int d, int m, dou
     const size_t smem = (size_t)kStages * kStageFloatsTC * sizeof(float) + 256;
     if (int rc = ensure_dynamic_smem((const void*)gram_tc_kernel, smem)) return rc;
     dim3 grid((unsigned)(p.pairs_full + 2 * p.pairs_sym), (unsigned)p.chunks);
+    profile_mark_begin(stream);
     gram_tc_kernel<<<grid, kTcThreads, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], a);
+    if (profile_on())      // bytes: the four TF32 planes once; flops: the tile products actually formed (algorithmic, x1 not x3)
+        profile_mark_end(stream, 16.0 * d * (double)p.ldk,
+                         2.0 * kTile * kTile * (double)p.ldk * (p.pairs_full + 2 * p.pairs_sym), 4);
     GPFQ_CHECK_LAUNCH();
     gram_tc_finish_kernel<<<(unsigned)ceil_div(ldg * ldg, 256), 256, 0, stream>>>(partial, p.tiles, p.pairs_full,
                                                                                  p.pairs_sym, p.chunks, d, ldg, GT, H, A);

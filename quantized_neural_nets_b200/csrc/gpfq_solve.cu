@@ -8,6 +8,7 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
                  int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream);
 size_t gram_workspace_bytes(int solver, int n_rows, int d, int m);
+size_t gram_matrices_workspace_bytes(int solver, int d, int m);
 int gram_solve(int solver, const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m,
                int n_rows, const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q,
                int64_t ldq, int8_t* levels, double* row_err2, double* row_ref2, void* workspace, size_t workspace_bytes,
@@ -32,6 +33,11 @@ size_t gpfq_workspace_bytes(int32_t solver, int32_t n_rows, int32_t d, int32_t m
     if (solver == GPFQ_SOLVER_DIRECT) return direct_workspace_bytes(n_rows, d, m);
     if (solver == GPFQ_SOLVER_GRAM || solver == GPFQ_SOLVER_GRAM_F64) return gram_workspace_bytes(solver, n_rows, d, m);
     return 0;
+}
+
+size_t gpfq_gram_workspace_bytes(int32_t solver, int32_t d, int32_t m) {
+    if (d <= 0 || m <= 0 || (solver != GPFQ_SOLVER_GRAM && solver != GPFQ_SOLVER_GRAM_F64)) return 0;
+    return gram_matrices_workspace_bytes(solver, d, m);
 }
 
 int gpfq_gram_f32(int32_t solver, const float* X, const float* Xq, int64_t ldx, int32_t d, int32_t m, double* GT,

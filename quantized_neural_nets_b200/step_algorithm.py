@@ -215,9 +215,7 @@ def local_gram_matrices(Xfm_local, Xqfm_local, ldx, d, m_local):
     cores (gpfq_gram_f32, split-TF32)."""
     ldg = (d + 63) // 64 * 64
     grams = torch.empty((3, ldg, ldg), dtype=torch.float64, device=Xfm_local.device)
-    nbytes = lib.gpfq_workspace_bytes(_lib.SOLVER_GRAM, 1, d, m_local)
-    if nbytes == 0:
-        raise RuntimeError(f"libgpfq_b200: the Gram solver does not support d={d}")
+    nbytes = lib.gpfq_gram_workspace_bytes(_lib.SOLVER_GRAM, d, m_local)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=Xfm_local.device)
     launch(lib.gpfq_gram_f32, _lib.SOLVER_GRAM, Xfm_local, Xqfm_local, ldx, d, m_local, grams[0], grams[1], grams[2], ws,
            nbytes)
