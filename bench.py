@@ -39,6 +39,11 @@ NCU_BN_ACT_TRAFFIC = {"dram_bytes_per_launch": 2440.1e6, "algorithmic_bytes_same
                       "launch": "BatchNorm + residual + ReLU of a (256, 256, 56, 56) activation",
                       "source": "profiles/r01_bn_act_kernel_ncu_full_summary.txt"}
 
+# dram bytes of one conv1x1_tc_kernel launch (ncu --set full; filled from profiles/r02_conv1x1_tc_kernel_ncu_full_summary.txt)
+NCU_CONV_TRAFFIC = {"dram_bytes_per_launch": None, "algorithmic_bytes_same_launch": None, "launch": "pending", "source": None}
+
+L2_PEAK_GBS = 8300.0     # L2-resident read bandwidth measured by tools/microbench.cu on this pool's B200 (r01)
+
 METRIC = "resnet50_4bit_gpfq_weights_samples_per_s"   # the metric name follows --model/--bits when they differ
 UNIT = "weights*samples/s"
 
@@ -327,8 +332,15 @@ def run_cuda_arm(args):
                 "launches_per_step": prof["sweep_launches"],
                 "avg_launch_us": 1e3 * prof["sweep_ms"] / max(1, prof["sweep_launches"]),
                 "kernel_ms_per_step": prof["sweep_ms"], "share_of_step": prof["sweep_ms"] / step_ms,
+                "l2": {"note": "north_star asks for the direct kernel against the L2 bandwidth roofline: algorithmic L2 -> SM "
+                               "bytes (SURVEY.md 8d: the HBM bytes plus the X / Xq block tiles once per further neuron "
+                               "tile of the grid) over the same CUDA-event time; peak = L2-resident read bandwidth "
+                               "measured on this pool's B200 by tools/microbench.cu (r01)",
+                       "achieved": prof["sweep"]["aux"] / sweep_s / 1e9 if sweep_s > 0 else 0.0, "peak": L2_PEAK_GBS,
+                       "unit": "GB/s", "frac": (prof["sweep"]["aux"] / sweep_s / 1e9) / L2_PEAK_GBS if sweep_s > 0 else 0.0},
                 "fp32": {"note": "the sweep is fp32-issue bound by design: 5 separately rounded fp32 instructions per "
-                                 "(neuron, sample, feature)",
+                                 "(neuron, sample, feature); at the fp32 issue peak it would move 8 bytes of U per 160 "
+                                 "instructions = 1.9 TB/s, so neither HBM nor L2 can be its bound",
                          "achieved_ginstr_s": prof["sweep_fp32_instr"] / sweep_s / 1e9 if sweep_s > 0 else 0.0,
                          "peak_ginstr_s": fp32_peak / 1e9,
                          "frac": (prof["sweep_fp32_instr"] / sweep_s) / fp32_peak if sweep_s > 0 else 0.0},
@@ -340,6 +352,13 @@ def run_cuda_arm(args):
                 "share_of_step": prof["resident_ms"] / step_ms,
                 "fp32_frac": (prof["resident_fp32_instr"] / (prof["resident_ms"] * 1e-3)) / fp32_peak
                 if prof["resident_ms"] > 0 else 0.0},
+            "gram_kernel_roofline": gram_roofline(prof, peaks, step_ms),
+            "conv_kernel": conv_summary(prof, hbm_peak, peaks, step_ms),
+            "parity": {"min_level_agreement_of_gated_layers": sa_min_agreement(),
+                       "note": "per LAYER (not per shape): a Gram variant -- and, sharded, the Gram-reduce mode -- is used "
+                               "for a layer only if it reproduced >= 99.9 % of the direct solver's levels on that layer's own "
+                               "data during warm-up; the direct solver itself is pinned against the reference by the "
+                               "bit-exact golden tests and the teacher-forced network tests (tests/)"},
             "rel_err_mean": sum(r for r in rel if r == r) / max(1, sum(1 for r in rel if r == r)),
             "rel_err_nan_layers": sum(1 for r in rel if r != r),
             "forward_mode": args.forward if world > 1 else "single GPU",
@@ -351,7 +370,22 @@ def run_cuda_arm(args):
             "phase_ms_per_step": {k: round(v, 2) for k, v in phases.items()},
             "solve_ms_per_layer": [round(per_layer[i].get("solve", 0.0), 3) for i in sorted(per_layer)],
         }
-        if prof["bn_act_ms"] > max(prof["sweep_ms"], prof["resident_ms"]):
+        if prof["conv"]["ms"] > max(prof["sweep_ms"], prof["resident_ms"], prof["bn_act_ms"]):
+            c = prof["conv"]
+            gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9
+            out["roofline"] = {
+                "kernel": "gpfq::conv1x1_tc_kernel", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": gbs / hbm_peak, "traffic": NCU_CONV_TRAFFIC["dram_bytes_per_launch"], "traffic_detail": NCU_CONV_TRAFFIC,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "launches_per_step": c["launches"], "avg_launch_us": 1e3 * c["ms"] / max(1, c["launches"]),
+                "kernel_ms_per_step": c["ms"], "share_of_step": c["ms"] / step_ms,
+                "tensor": out["conv_kernel"]["tensor"],
+                "note": "the kernel of this library with the largest share of the step: the calibration forward's "
+                        "convolutions (tcgen05 split-TF32 GEMM + fused BatchNorm / residual / ReLU epilogue); algorithmic "
+                        "bytes = read the activation (or patch matrix) once (+ residual), write the output once, summed "
+                        "over all its launches of one step.  The GPFQ kernels are in direct_kernel_roofline / "
+                        "resident_kernel / gram_kernel_roofline."}
+        elif prof["bn_act_ms"] > max(prof["sweep_ms"], prof["resident_ms"]):
             bn_gbs = prof["bn_act_bytes"] / (prof["bn_act_ms"] * 1e-3) / 1e9
             out["roofline"] = {
                 "kernel": "gpfq::bn_act_kernel", "bound": "hbm", "achieved": bn_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -383,11 +417,133 @@ def run_cuda_arm(args):
         if other_ms is not None:
             out["other_forward_mode"] = {"mode": other, "ms_per_step": other_ms / args.steps,
                                          "value": units / (other_ms / args.steps * 1e-3)}
+        if world == 1 and args.all_configs and args.model == "resnet50" and args.bits == 4:
+            out["all_configs"] = measure_other_configs(args, dev)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(args, shapes, units)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    return out
+
+
+def sa_min_agreement():
+    from quantized_neural_nets_b200 import step_algorithm as sa
+    return round(sa.min_gated_agreement(), 6)
+
+
+def gram_roofline(prof, peaks, step_ms):
+    """tensor-pipe view of the Gram solver's GEMM kernel (north_star: 'tensor-pipe utilisation for the Gram GEMMs')."""
+    g, gp = prof["gram_tc"], prof["gram_path"]
+    tf32_peak = 0.5 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    s = g["ms"] * 1e-3
+    alg = g["flops"] / s / 1e12 if s > 0 else 0.0
+    return {"kernel": "gpfq::gram_tc_kernel", "bound": "tensor", "unit": "TFLOP/s",
+            "achieved_algorithmic": alg, "achieved_issued": 3.0 * alg, "peak": tf32_peak,
+            "peak_source": "half of MEASURED_PEAKS.json bf16_tflops_sustained (dense TF32 = bf16 / 2)" if peaks else "fallback",
+            "frac": 3.0 * alg / tf32_peak if tf32_peak > 0 else 0.0,
+            "note": "split-TF32: three MMAs per product, so issued = 3 x algorithmic; flops = the 128 x 128 tile products formed",
+            "launches_per_step": g["launches"], "kernel_ms_per_step": g["ms"], "share_of_step": g["ms"] / step_ms,
+            "gram_path_kernel": {"launches_per_step": gp["launches"], "kernel_ms_per_step": gp["ms"],
+                                 "fp64_tflops": 2.0 * gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0},
+            "recur_kernel": {"launches_per_step": prof["recur"]["launches"], "kernel_ms_per_step": prof["recur"]["ms"]}}
+
+
+def conv_summary(prof, hbm_peak, peaks, step_ms):
+    c = prof["conv"]
+    s = c["ms"] * 1e-3
+    tf32_peak = 0.5 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    alg = c["flops"] / s / 1e12 if s > 0 else 0.0
+    return {"kernel": "gpfq::conv1x1_tc_kernel", "launches_per_step": c["launches"], "kernel_ms_per_step": c["ms"],
+            "share_of_step": c["ms"] / step_ms, "hbm_gbs": c["bytes"] / s / 1e9 if s > 0 else 0.0,
+            "hbm_frac": (c["bytes"] / s / 1e9) / hbm_peak if s > 0 else 0.0,
+            "tensor": {"achieved_algorithmic_tflops": alg, "achieved_issued_tflops": 3.0 * alg, "peak_tflops": tf32_peak,
+                       "frac": 3.0 * alg / tf32_peak if tf32_peak > 0 else 0.0}}
+
+
+def measure_other_configs(args, dev):
+    """BASELINE.json's other configurations on one GPU, driver-observed: {name: summary}.  Each: 2 warm-up steps (per-layer
+    solver choice behind the parity gate) + 2 timed steps of quantize_network() with the bench's settings, and one
+    instrumented step for the forward / solve split."""
+    import quantized_neural_nets_b200 as qb
+    from quantized_neural_nets_b200 import _lib, step_algorithm as sa
+    out = {}
+    for tag, name, bits, reg, lamb in (("alexnet_4bit", "alexnet", 4, None, 0.1), ("resnet18_4bit", "resnet18", 4, None, 0.1),
+                                       ("vgg16_4bit_L1", "vgg16", 4, "L1", 0.1), ("resnet50_3bit", "resnet50", 3, None, 0.1)):
+        model = build_model(name).to(dev)
+        shapes = layer_shapes(model, args.batch, args.retain)
+        units = float(sum(N * d * m for (N, d, m, g) in shapes))
+        gen = torch.Generator(device=dev).manual_seed(1)
+        pool = [torch.randn(args.batch, 3, 224, 224, device=dev, generator=gen) for _ in range(2)]
+        log0 = len(sa.AUTO_LOG)
+
+        def step(profile=False):
+            np.random.seed(0)
+            qnn = qb.QuantizeNeuralNet(model, name, args.batch, BatchPool(pool), bits, bits, [], 1.16, 1.16, 1, 1, reg, lamb,
+                                       args.retain, False, dev, profile=profile,
+                                       solver=None if args.solver == "direct" else args.solver,
+                                       fuse_forward=args.fuse_forward, pointwise_gemm=args.pointwise_gemm)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            qnn.quantize_network()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b), qnn
+
+        for _ in range(2):
+            step()
+        ms = sum(step()[0] for _ in range(2)) / 2
+        _, qprof = step(profile=True)
+        phases, per_layer = qprof.phase_times_ms()
+        rel = [float(r) for (_, _, r) in qprof.layer_log]
+        picked = [ag for (k, tm, ag, ch) in sa.AUTO_LOG[log0:] if ch not in (_lib.SOLVER_DIRECT, "groups_loop", "gather_inputs")]
+        out[tag] = {"workload": f"{name} {bits}-bit bs={args.batch} retain={args.retain}" + (f" reg={reg} lamb={lamb}" if reg else ""),
+                    "units_per_step": units, "layers": len(shapes), "ms_per_step": ms, "value": units / (ms * 1e-3),
+                    "phase_ms": {k: round(v, 2) for k, v in phases.items()},
+                    "rel_err_mean": sum(r for r in rel if r == r) / max(1, sum(1 for r in rel if r == r)),
+                    "gram_layers": len(picked), "min_level_agreement_of_gated_layers": round(min(picked), 6) if picked else 1.0}
+        if name == "vgg16":
+            out[tag]["fc6_variants"] = fc6_variants(dev, per_layer[13].get("solve", 0.0))
+        del model, pool, qprof
+        torch.cuda.empty_cache()
+    return out
+
+
+def fc6_variants(dev, direct_ms):
+    """BASELINE.json configs[4] names VGG-16 fc6 (4096 x 25088, m = 256) as the Gram / tcgen05 showcase, SURVEY.md 8a
+    asks that both variants be timed on it and the choice reported honestly.  m << d is the opposite of the Gram regime:
+    the three 25088 x 25088 fp64 Gram matrices are 15.1 GB and the recurrence needs about 2.5 N d^2 = 6.4e12 fp64 FMAs.
+    Timed here: the direct solver on the layer (from the instrumented step) and the Gram FORMATION alone (tcgen05,
+    gpfq_gram_f32); the recurrence kernel keeps a neuron's (w, q) rows in shared memory and supports d <= 3104, so its
+    cost is given as a lower bound from the fp64 rate it reaches on the layers it does run."""
+    from quantized_neural_nets_b200 import _lib
+    lib, launch = _lib.lib, _lib.launch
+    d, m, N = 25088, 256, 4096
+    out = {"direct_ms": round(direct_ms, 3), "chosen": "direct"}
+    try:
+        g = torch.Generator(device=dev).manual_seed(5)
+        X = torch.relu(torch.randn(d, m, device=dev, generator=g))
+        ldg = (d + 63) // 64 * 64
+        grams = torch.empty((3, ldg, ldg), dtype=torch.float64, device=dev)
+        nbytes = lib.gpfq_gram_workspace_bytes(_lib.SOLVER_GRAM, d, m)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            launch(lib.gpfq_gram_f32, _lib.SOLVER_GRAM, X, X, m, d, m, grams[0], grams[1], grams[2], ws, nbytes)
+            b.record()
+            torch.cuda.synchronize()
+        out["gram_formation_ms"] = round(a.elapsed_time(b), 3)
+        out["gram_matrices_gb"] = round(3 * ldg * ldg * 8 / 1e9, 1)
+        out["gram_recurrence_lower_bound_ms"] = round(2.5 * N * float(d) * d / 9.0e12 * 1e3, 1)
+        out["note"] = ("Gram recurrence bound = 2.5 N d^2 fp64 FMAs at 9 TFMA/s (the fp64 FMA rate of B200 measured by "
+                       "tools/microbench.cu is 18 TFLOP/s); the direct solver wins by more than an order of magnitude, as "
+                       "m << d predicts")
+        del grams, ws, X
+        torch.cuda.empty_cache()
+    except Exception as exc:          # out of memory on a smaller part: the comparison is informative, not required
+        out["gram_formation_error"] = str(exc)[:200]
     return out
 
 
@@ -452,6 +608,9 @@ def main():
                     help="keep cuDNN for the stride-1 1x1 convolutions of the calibration forward instead of one "
                          "strided-batched cuBLAS SGEMM each (gpfq_conv1x1_f32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-all-configs", dest="all_configs", action="store_false",
+                    help="N = 1 only: skip the summary block of BASELINE.json's other configurations (AlexNet, ResNet-18, "
+                         "VGG-16 L1 incl. the fc6 variant comparison, ResNet-50 3-bit)")
     ap.add_argument("--no-validate-cpu", dest="validate_cpu", action="store_false",
                     help="skip the one complete real-reference run (AlexNet, about a minute of host time) that checks the "
                          "CPU arm's sampled-and-extrapolated figure")

@@ -47,24 +47,31 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
 // C * kh * kw channels; a 1x1 kernel with stride 2 is a plain strided gather, stride 1 a copy that pads the row pitch.
 __global__ void __launch_bounds__(256)
 conv_patches_kernel(const float* __restrict__ in, int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
-                    int dw, int Ho, int Wo, float* __restrict__ out, int64_t ld, int64_t rows_total) {
-    // one warp-row of 256 threads walks the pixels of one (image, channel, ki, kj) row; grid.y strides over the rows
+                    int dw, int Ho, int Wo, float* __restrict__ out, int64_t ld, int64_t planes) {
+    // A CTA takes 1024 consecutive output pixels of one (image, channel) plane and walks all kh * kw taps over them,
+    // so the taps re-read the same input rows through L1 and every store is a full float4 (ld % 4 == 0).
     const int HWo = Ho * Wo;
-    for (int64_t row = blockIdx.y; row < rows_total; row += gridDim.y) {
-        const int kj = (int)(row % kw);
-        const int ki = (int)((row / kw) % kh);
-        const int64_t bc = row / ((int64_t)kw * kh);          // b * C + c
+    const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (p >= ld) return;
+    int yo[4], xo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        yo[e] = (p + e) / Wo;
+        xo[e] = (p + e) - yo[e] * Wo;
+    }
+    for (int64_t bc = blockIdx.y; bc < planes; bc += gridDim.y) {
         const float* src = in + bc * (int64_t)H * W;
-        float* dst = out + row * ld;
-        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < ld; p += gridDim.x * blockDim.x) {
-            float v = 0.f;
-            if (p < HWo) {
-                const int yo = p / Wo, xo = p - yo * Wo;
-                const int y = yo * sh - ph + ki * dh, x = xo * sw - pw + kj * dw;
-                if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(src + (int64_t)y * W + x);
+        float* dst = out + bc * (int64_t)kh * kw * ld + p;
+        for (int ki = 0; ki < kh; ++ki)
+            for (int kj = 0; kj < kw; ++kj) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int y = yo[e] * sh - ph + ki * dh, x = xo[e] * sw - pw + kj * dw;
+                    v[e] = (p + e < HWo && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (int64_t)y * W + x) : 0.f;
+                }
+                *reinterpret_cast<float4*>(dst + (int64_t)(ki * kw + kj) * ld) = make_float4(v[0], v[1], v[2], v[3]);
             }
-            dst[p] = v;
-        }
     }
 }
 }  // namespace gpfq
@@ -103,10 +110,11 @@ extern "C" int gpfq_conv_patches_f32(const float* in, int32_t B, int32_t C, int3
     GPFQ_REQUIRE(Ho >= 1 && Wo >= 1 && ld >= (int64_t)Ho * Wo, "gpfq_conv_patches_f32: empty output or ld too small");
     GPFQ_REQUIRE(in && out, "gpfq_conv_patches_f32: null pointer");
     if (B == 0) return 0;
-    const int64_t rows = (int64_t)B * C * kh * kw;
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div(ld, 256), 64), (unsigned)std::min<int64_t>(rows, 65535));
+    GPFQ_REQUIRE(ld % 4 == 0 && ((uintptr_t)out & 15) == 0, "gpfq_conv_patches_f32: ld must be a multiple of 4, out 16-byte aligned");
+    const int64_t planes = (int64_t)B * C;
+    dim3 grid((unsigned)ceil_div(ld, 1024), (unsigned)std::min<int64_t>(planes, 65535));
     conv_patches_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, out, ld,
-                                                                rows);
+                                                                planes);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

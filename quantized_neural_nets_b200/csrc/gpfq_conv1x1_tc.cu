@@ -349,11 +349,11 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 mbar_wait(&acc_full[b], (uint32_t)((it / kAccs) & 1));
                 tc_fence_after();
 #pragma unroll
-                for (int c0 = 0; c0 < kCols; c0 += 32) {
-                    float v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + half * kCols + c0), v);
+                for (int c0 = 0; c0 < kCols; c0 += 16) {
+                    float v[16];
+                    tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + half * kCols + c0), v);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) run[c0 + e] = __fadd_rn(run[c0 + e], v[e]);
+                    for (int e = 0; e < 16; ++e) run[c0 + e] = __fadd_rn(run[c0 + e], v[e]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -365,26 +365,20 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             const float lo = a.lo, hi = a.hi;
             const bool vec = (a.HW & 3) == 0;
             const int pw0 = p0 + half * kCols;     // first pixel of this warp's columns
-            // residual loads run one 16-column block ahead of their use (they hit L2 after the tile's bulk prefetch)
-            float4 rr[4], rr_next[4];
-            auto load_residual = [&](int c0, float4* dst) {
-                const int p = pw0 + c0 + 4 * (lane & 3);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int n = n0 + quad * 32 + 8 * k + (lane >> 2);
-                    dst[k] = (c0 < kCols && n < a.N && p < a.HW)
-                                 ? __ldg(reinterpret_cast<const float4*>(a.residual + ((size_t)img * a.N + n) * a.HW + p))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            if (vec && a.residual) load_residual(0, rr_next);
 #pragma unroll
             for (int c0 = 0; c0 < kCols; c0 += 16) {
                 if (pw0 + c0 >= a.HW) break;       // uniform over the warp
+                // the block's four residual loads go out before the transposition (L2 hits after the tile's bulk prefetch)
+                float4 rr[4];
                 if (vec && a.residual) {
+                    const int p = pw0 + c0 + 4 * (lane & 3);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) rr[k] = rr_next[k];
-                    load_residual(c0 + 16, rr_next);
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = n0 + quad * 32 + 8 * k + (lane >> 2);
+                        rr[k] = (n < a.N && p < a.HW)
+                                    ? __ldg(reinterpret_cast<const float4*>(a.residual + ((size_t)img * a.N + n) * a.HW + p))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
