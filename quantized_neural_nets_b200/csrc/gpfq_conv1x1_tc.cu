@@ -32,6 +32,8 @@
 // Shapes: the activation's pixel pitch must be a multiple of 4 floats (TMA global strides are multiples of 16 bytes;
 // gpfq_conv_patches_f32 pads it when it is not); any C (the channel tail of a k-block is zero-filled by TMA on both
 // operands), any N, any HW.
+#include <math.h>
+
 #include <algorithm>
 
 #include "gpfq_common.cuh"
@@ -149,6 +151,17 @@ __device__ __forceinline__ void veltkamp_split(float x, float& hi, float& lo) {
     hi = __fsub_rn(p, __fsub_rn(p, x));
     lo = __fsub_rn(x, hi);
 }
+// max / min that propagate NaN (torch.clamp and the elementwise kernel's `v < lo ? lo : v` keep a NaN input)
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
@@ -191,6 +204,7 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, i
 
 // tmWh / tmWl: (N x Cp) planes, box [128][32], SWIZZLE_128B.  tmX: RAW activation as (HW, C, B), box (32, 32, 1),
 // SWIZZLE_128B_ATOM_32B; channels beyond C and pixels beyond HW arrive as zeros.
+template <bool AFFINE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
@@ -332,15 +346,19 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         const int row = quad * 32 + lane;          // output channel within the tile
         constexpr int kCols = kTN / 2;             // 64 columns per drain warp
         float* stg = staging + (warp - kFirstDrainWarp) * 32 * kStgStride;
+        float al_mine = 1.f, be_mine = 0.f;
+        int n0_loaded = -1;
         int it = 0;
         for (int i = 0; i < my_tiles; ++i) {
             int img, p0, n0;
             tile_coords(i, img, p0, n0);
             // the channel's affine coefficients are fetched now, a whole mainloop before the epilogue needs them
-            const bool affine = a.alpha != nullptr;
             const int n_mine = n0 + row;
-            const float al_mine = (affine && n_mine < a.N) ? __ldg(a.alpha + n_mine) : 1.f;
-            const float be_mine = (affine && n_mine < a.N) ? __ldg(a.beta + n_mine) : 0.f;
+            if (AFFINE && n0 != n0_loaded) {       // with 1, 2 or 4 channel tiles a CTA keeps the same one for all its tiles
+                al_mine = n_mine < a.N ? __ldg(a.alpha + n_mine) : 1.f;
+                be_mine = n_mine < a.N ? __ldg(a.beta + n_mine) : 0.f;
+                n0_loaded = n0;
+            }
             float run[kCols];
 #pragma unroll
             for (int c = 0; c < kCols; ++c) run[c] = 0.f;
@@ -361,57 +379,69 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             }
             // Epilogue.  run[] holds one output channel per thread; 32 x 16 blocks go through a per-warp shared-memory
             // transposition so that every global access of the warp covers whole 64-byte row segments (8 rows x 16
-            // pixels per float4 instruction) instead of 32 different rows.
+            // pixels per float4 instruction) instead of 32 different rows.  An ncu capture of the first version showed
+            // this code to be 47 % of ALL instructions the kernel executes (1440 per warp and tile): everything that does
+            // not depend on the 16-column block is hoisted out of it.
             const float lo = a.lo, hi = a.hi;
+            const bool clamp_lo = lo > -INFINITY, clamp_hi = hi < INFINITY;
             const bool vec = (a.HW & 3) == 0;
             const int pw0 = p0 + half * kCols;     // first pixel of this warp's columns
+            const int rq = lane >> 2, cq = lane & 3;
+            // in the transposed domain this thread owns pixels 4*cq..4*cq+3 of rows 8k + rq, k = 0..3, of every block
+            float al4[4], be4[4];
+            bool rv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                al4[k] = __shfl_sync(0xffffffffu, al_mine, 8 * k + rq);
+                be4[k] = __shfl_sync(0xffffffffu, be_mine, 8 * k + rq);
+                rv[k] = n0 + quad * 32 + 8 * k + rq < a.N;
+            }
+            const size_t row_base = ((size_t)img * a.N + n0 + quad * 32 + rq) * a.HW + pw0 + 4 * cq;
+            const size_t kstride = (size_t)8 * a.HW;
+            float* optr = a.out + row_base;
+            const float* rptr = RES ? a.residual + row_base : nullptr;
+            const float* sread = stg + rq * kStgStride + 4 * cq;
 #pragma unroll
             for (int c0 = 0; c0 < kCols; c0 += 16) {
                 if (pw0 + c0 >= a.HW) break;       // uniform over the warp
-                // the block's four residual loads go out before the transposition (L2 hits after the tile's bulk prefetch)
-                float4 rr[4];
-                if (vec && a.residual) {
-                    const int p = pw0 + c0 + 4 * (lane & 3);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = n0 + quad * 32 + 8 * k + (lane >> 2);
-                        rr[k] = (n < a.N && p < a.HW)
-                                    ? __ldg(reinterpret_cast<const float4*>(a.residual + ((size_t)img * a.N + n) * a.HW + p))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * j) =
-                        make_float4(run[c0 + 4 * j], run[c0 + 4 * j + 1], run[c0 + 4 * j + 2], run[c0 + 4 * j + 3]);
-                __syncwarp();
                 if (vec) {
-                    const int cq = lane & 3;
-                    const int p = pw0 + c0 + 4 * cq;
+                    const bool pv = pw0 + c0 + 4 * cq < a.HW;      // HW % 4 == 0: a float4 is entirely inside or outside
+                    // the block's four residual loads go out before the transposition (L2 hits after the bulk prefetch)
+                    float4 rr[4];
+                    if (RES) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            rr[k] = (rv[k] && pv) ? __ldg(reinterpret_cast<const float4*>(rptr + k * kstride + c0))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * j) =
+                            make_float4(run[c0 + 4 * j], run[c0 + 4 * j + 1], run[c0 + 4 * j + 2], run[c0 + 4 * j + 3]);
+                    __syncwarp();
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int r = 8 * k + (lane >> 2);
-                        float4 v = *reinterpret_cast<const float4*>(stg + r * kStgStride + 4 * cq);
-                        const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
-                        const int n = n0 + quad * 32 + r;
-                        if (n < a.N && p < a.HW) {     // HW % 4 == 0: a float4 is entirely inside or outside the row
-                            const size_t off = ((size_t)img * a.N + n) * a.HW + p;
-                            if (affine) {
-                                v.x = __fadd_rn(__fmul_rn(v.x, al), be);
-                                v.y = __fadd_rn(__fmul_rn(v.y, al), be);
-                                v.z = __fadd_rn(__fmul_rn(v.z, al), be);
-                                v.w = __fadd_rn(__fmul_rn(v.w, al), be);
-                            }
-                            if (a.residual) {
-                                v.x = __fadd_rn(v.x, rr[k].x); v.y = __fadd_rn(v.y, rr[k].y);
-                                v.z = __fadd_rn(v.z, rr[k].z); v.w = __fadd_rn(v.w, rr[k].w);
-                            }
-                            v.x = v.x < lo ? lo : v.x; v.y = v.y < lo ? lo : v.y; v.z = v.z < lo ? lo : v.z; v.w = v.w < lo ? lo : v.w;
-                            v.x = v.x > hi ? hi : v.x; v.y = v.y > hi ? hi : v.y; v.z = v.z > hi ? hi : v.z; v.w = v.w > hi ? hi : v.w;
-                            *reinterpret_cast<float4*>(a.out + off) = v;
+                        float4 v = *reinterpret_cast<const float4*>(sread + 8 * k * kStgStride);
+                        if (AFFINE) {
+                            v.x = __fadd_rn(__fmul_rn(v.x, al4[k]), be4[k]);
+                            v.y = __fadd_rn(__fmul_rn(v.y, al4[k]), be4[k]);
+                            v.z = __fadd_rn(__fmul_rn(v.z, al4[k]), be4[k]);
+                            v.w = __fadd_rn(__fmul_rn(v.w, al4[k]), be4[k]);
                         }
+                        if (RES) {
+                            v.x = __fadd_rn(v.x, rr[k].x); v.y = __fadd_rn(v.y, rr[k].y);
+                            v.z = __fadd_rn(v.z, rr[k].z); v.w = __fadd_rn(v.w, rr[k].w);
+                        }
+                        if (clamp_lo) { v.x = max_nan(v.x, lo); v.y = max_nan(v.y, lo); v.z = max_nan(v.z, lo); v.w = max_nan(v.w, lo); }
+                        if (clamp_hi) { v.x = min_nan(v.x, hi); v.y = min_nan(v.y, hi); v.z = min_nan(v.z, hi); v.w = min_nan(v.w, hi); }
+                        if (rv[k] && pv) *reinterpret_cast<float4*>(optr + k * kstride + c0) = v;
                     }
                 } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * j) =
+                            make_float4(run[c0 + 4 * j], run[c0 + 4 * j + 1], run[c0 + 4 * j + 2], run[c0 + 4 * j + 3]);
+                    __syncwarp();
                     const int c = lane & 15, r0 = lane >> 4;       // two rows of 16 pixels per instruction
                     for (int k = 0; k < 16; ++k) {
                         const int r = 2 * k + r0;
@@ -420,10 +450,10 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                         const int n = n0 + quad * 32 + r, p = pw0 + c0 + c;
                         if (n < a.N && p < a.HW) {
                             const size_t off = ((size_t)img * a.N + n) * a.HW + p;
-                            if (affine) v = __fadd_rn(__fmul_rn(v, al), be);
-                            if (a.residual) v = __fadd_rn(v, __ldg(a.residual + off));
-                            v = v < lo ? lo : v;
-                            v = v > hi ? hi : v;
+                            if (AFFINE) v = __fadd_rn(__fmul_rn(v, al), be);
+                            if (RES) v = __fadd_rn(v, __ldg(a.residual + off));
+                            if (clamp_lo) v = max_nan(v, lo);
+                            if (clamp_hi) v = min_nan(v, hi);
                             a.out[off] = v;
                         }
                     }
@@ -529,10 +559,14 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
         a.prefetch_residual = 1;
     }
-    if (int rc = ensure_dynamic_smem((const void*)conv1x1_tc_kernel, kSmemBytes)) return rc;
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
+    static const KernelFn table[2][2] = {{conv1x1_tc_kernel<false, false>, conv1x1_tc_kernel<false, true>},
+                                         {conv1x1_tc_kernel<true, false>, conv1x1_tc_kernel<true, true>}};
+    const KernelFn fn = table[alpha != nullptr][residual != nullptr];
+    if (int rc = ensure_dynamic_smem((const void*)fn, kSmemBytes)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
     profile_mark_begin(stream);
-    conv1x1_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, tmRes, a);
+    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, tmRes, a);
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
                          2.0 * B * (double)HW * C * N, 3);
