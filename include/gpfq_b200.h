@@ -81,6 +81,12 @@ int gpfq_conv_patches_f32(const float* in, int32_t B, int32_t C, int32_t H, int3
 int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Calibration-forward helper: MaxPool2d with a square k x k window, stride, implicit -inf padding (2*pad <= k), floor mode,
+ * dilation 1, of `planes` = B*C contiguous H x W planes; out is planes x Ho x Wo, Ho = (H + 2*pad - k) / stride + 1.
+ * NaN propagates as in PyTorch. */
+int gpfq_maxpool2d_f32(const float* in, int64_t planes, int32_t H, int32_t W, int32_t k, int32_t stride, int32_t pad,
+                       float* out, void* stream);
+
 /* Packed low-bit export of a quantized layer (the reference stores fp32 values that lie on the alphabet,
  * quantize_neural_net.py:163,193; main.py:127-131 saves them as fp32).  A weight is one of the 2K+1 values
  * delta*{-K..K} (MSQ / SOFT / STOCHASTIC) or of the 2K+3 values {0, +-(lam + k*delta), k = 0..K} (HARD), so it is

@@ -36,6 +36,7 @@ SIGNATURES = {
     "gpfq_conv1x1_bn_act_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_f32,
                                         c_f32, c_ptr, ctypes.c_size_t, c_ptr]),
     "gpfq_conv_patches_f32": (c_i32, [c_ptr] + [c_i32] * 12 + [c_ptr, c_i64, c_ptr]),
+    "gpfq_maxpool2d_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "gpfq_packed_bits": (c_i32, [c_i32, c_i32]),
     "gpfq_pack_levels_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, c_ptr, c_ptr, c_ptr]),
     "gpfq_unpack_levels_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_i32, c_f32, c_ptr, c_ptr, c_ptr]),

@@ -9,6 +9,8 @@
 #include <utility>
 #include <vector>
 
+#include <math.h>
+
 #include "gpfq_common.cuh"
 
 namespace gpfq {
@@ -198,6 +200,35 @@ __global__ void unpack_levels_kernel(const uint8_t* __restrict__ in, int64_t n, 
             if (q) q[e] = value_of_level(lv, delta, mode, lam);
             if (levels) levels[e] = (int8_t)lv;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Calibration-forward helper: MaxPool2d (square window, padding with -inf, floor mode) of an NCHW tensor.  One thread per
+// output pixel, consecutive threads along the row; the k x k windows of neighbouring outputs overlap, so the input is
+// read from HBM once and re-read through L1.  NaN propagates as in PyTorch (a NaN in the window wins).
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int k, int s, int p, int Ho, int Wo,
+               float* __restrict__ out) {
+    const int64_t total = planes * Ho * Wo;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int xo = (int)(e % Wo);
+        const int yo = (int)((e / Wo) % Ho);
+        const int64_t pl = e / ((int64_t)Wo * Ho);
+        const float* src = in + pl * (int64_t)H * W;
+        const int y0 = yo * s - p, x0 = xo * s - p;
+        float m = -INFINITY;
+        for (int i = 0; i < k; ++i) {
+            const int y = y0 + i;
+            if (y < 0 || y >= H) continue;
+            for (int j = 0; j < k; ++j) {
+                const int x = x0 + j;
+                if (x < 0 || x >= W) continue;
+                const float v = __ldg(src + (int64_t)y * W + x);
+                m = (v > m || v != v) ? v : m;
+            }
+        }
+        out[e] = m;
     }
 }
 
@@ -474,6 +505,20 @@ int gpfq_unpack_levels_f32(const uint8_t* packed, int64_t n, const float* delta,
     level_layout(K, mode, &offset, &nbits);
     const int blocks = (int)std::min<int64_t>(ceil_div(ceil_div(n, 8), 256), 148 * 8);
     unpack_levels_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(packed, n, delta, offset, nbits, mode, lam, Q, levels);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
+int gpfq_maxpool2d_f32(const float* in, int64_t planes, int32_t H, int32_t W, int32_t k, int32_t stride, int32_t pad,
+                       float* out, void* stream) {
+    GPFQ_REQUIRE(planes >= 0 && H >= 1 && W >= 1 && k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k,
+                 "gpfq_maxpool2d_f32: bad geometry");
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    GPFQ_REQUIRE(Ho >= 1 && Wo >= 1 && in && out, "gpfq_maxpool2d_f32: empty output or null pointer");
+    if (planes == 0) return 0;
+    const int64_t total = planes * Ho * Wo;
+    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        in, planes, H, W, k, stride, pad, Ho, Wo, out);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

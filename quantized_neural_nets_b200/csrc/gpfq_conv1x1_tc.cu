@@ -10,11 +10,11 @@
 // accumulator per 32-channel k-block that the epilogue warps add up in registers with round-to-nearest.
 //
 // Structure (one persistent CTA per SM, 512 threads, tiles of 128 output channels x 128 pixels of one image):
-//   warp 0      TMA producer: per k-block the weight planes w_hi / w_lo (boxes [128][32], SWIZZLE_128B, K-major) and the
+//   warp 0      TMA producer: per k-block the RAW fp32 weight tile (box [128][32], SWIZZLE_128B, K-major) and the
 //               RAW fp32 activation (four boxes [32 channels][32 pixels], SWIZZLE_128B_ATOM_32B: the B operand is
 //               MN-major -- the pixel index is the contiguous one in NCHW), 3-stage ring that runs on across tiles; one
 //               bulk L2 prefetch of the tile's residual when there is one;
-//   warps 4-7   split: turn the raw activation tile into its hi plane in place and the lo plane next to it (an
+//   warps 4-7   split: turn the raw weight and activation tiles into their hi planes in place and the lo planes next to them (an
 //               elementwise map, so the swizzled layout is untouched; Veltkamp's split on the FMA pipe, see below),
 //               fence.proxy.async, release the MMA warp -- the activation is read from HBM exactly once;
 //   warp 1      single-thread tcgen05.mma issue, 12 MMAs (M = N = 128, K = 8, kind::tf32) per k-block into one of FOUR
@@ -188,17 +188,14 @@ struct ConvArgs {
     int prefetch_residual;   // tmRes is valid
 };
 
-// hi = rna_tf32(w), lo = rna_tf32(w - hi) of the (N x C) weight, rows padded with zeros to Cp columns
-__global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, int Cp, float* __restrict__ hi,
-                                    float* __restrict__ lo) {
+// copy of the (N x C) weight with its rows padded with zeros to Cp columns (only when C % 4 != 0: TMA needs row pitches
+// that are multiples of 16 bytes)
+__global__ void pad_weight_kernel(const float* __restrict__ W, int N, int C, int Cp, float* __restrict__ out) {
     const int64_t n = (int64_t)N * Cp;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = e / Cp;
         const int c = (int)(e % Cp);
-        const float v = c < C ? W[r * C + c] : 0.f;
-        const float h = to_tf32(v);
-        hi[e] = h;
-        lo[e] = to_tf32(v - h);
+        out[e] = c < C ? W[r * C + c] : 0.f;
     }
 }
 
@@ -206,8 +203,8 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, i
 // SWIZZLE_128B_ATOM_32B; channels beyond C and pixels beyond HW arrive as zeros.
 template <bool AFFINE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
-conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
+conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     float* staging = tiles + (size_t)kStages * kStageFloats;
@@ -264,10 +261,9 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                     const int s = it % kStages;
                     mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
                     float* st = tiles + (size_t)s * kStageFloats;
-                    mbar_expect_tx(&full[s], (uint32_t)((2 * kATile + kBTile) * sizeof(float)));
+                    mbar_expect_tx(&full[s], (uint32_t)((kATile + kBTile) * sizeof(float)));
                     const int c0 = kb * kBK;
-                    tma_load_2d(st, &tmWh, c0, n0, &full[s]);
-                    tma_load_2d(st + kATile, &tmWl, c0, n0, &full[s]);
+                    tma_load_2d(st, &tmW, c0, n0, &full[s]);
 #pragma unroll
                     for (int j = 0; j < kTN / kPx; ++j)
                         tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx, c0, img, &full[s]);
@@ -282,8 +278,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 const uint32_t ph = (uint32_t)((it / kStages) & 1);
                 const int b = it % kAccs;
                 mbar_wait(&acc_empty[b], (uint32_t)(((it / kAccs) & 1) ^ 1));
-                mbar_wait(&full[s], ph);       // weight planes (TMA)
-                mbar_wait(&split[s], ph);      // activation planes (split warps)
+                mbar_wait(&split[s], ph);      // both operands split into their hi / lo planes
                 tc_fence_after();
                 const float* st = tiles + (size_t)s * kStageFloats;
                 const uint64_t d_wh = desc_k_major(st), d_wl = desc_k_major(st + kATile);
@@ -321,6 +316,20 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         for (int it = 0; it < total; ++it) {
             const int s = it % kStages;
             mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+            // the weight tile first (half the size), then the activation tile; both arrive RAW from TMA
+            float4* whi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats);
+            float4* wlo = whi + kATile / 4;
+#pragma unroll 8
+            for (int i = 0; i < kATile / 4 / (32 * kSplitWarps); ++i) {
+                const float4 v = whi[t + 32 * kSplitWarps * i];
+                float4 h, l;
+                veltkamp_split(v.x, h.x, l.x);
+                veltkamp_split(v.y, h.y, l.y);
+                veltkamp_split(v.z, h.z, l.z);
+                veltkamp_split(v.w, h.w, l.w);
+                whi[t + 32 * kSplitWarps * i] = h;
+                wlo[t + 32 * kSplitWarps * i] = l;
+            }
             float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats + 2 * kATile);
             float4* lo = hi + kBTile / 4;
 #pragma unroll 8
@@ -507,7 +516,8 @@ int sm_count() {
 
 }  // namespace
 
-size_t conv1x1_tc_workspace_bytes(int N, int C) { return (size_t)2 * N * round_up(C, kBK) * sizeof(float) + 256; }
+// only a zero-padded copy of W when its row pitch is not a multiple of 16 bytes
+size_t conv1x1_tc_workspace_bytes(int N, int C) { return (C % 4 == 0 ? 0 : (size_t)N * round_up(C, 4) * sizeof(float)) + 256; }
 
 // x is read through TMA: its pixel pitch x_ld (floats between consecutive channels) must be a multiple of 4
 bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld) { return C >= 1 && N >= 1 && HW >= 1 && x_ld >= HW && x_ld % 4 == 0; }
@@ -521,20 +531,24 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
                      ((uintptr_t)residual & 15) == 0,
                  "conv1x1_tc: workspace must be 256-byte aligned, tensors 16-byte aligned");
     GPFQ_REQUIRE((const void*)x != (const void*)out && (const void*)residual != (const void*)out, "conv1x1_tc: out must not alias an input");
-    const int Cp = (int)round_up(C, kBK);
-    float* w_hi = (float*)workspace;
-    float* w_lo = w_hi + (size_t)N * Cp;
-    const int64_t n_w = (int64_t)N * Cp;
-    split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
-    GPFQ_CHECK_LAUNCH();
+    const float* w_src = W;
+    int64_t w_ld = C;
+    if (C % 4 != 0) {
+        w_ld = round_up(C, 4);
+        float* padded = (float*)workspace;
+        const int64_t n_w = (int64_t)N * w_ld;
+        pad_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, (int)w_ld, padded);
+        GPFQ_CHECK_LAUNCH();
+        w_src = padded;
+    }
+    GPFQ_REQUIRE(((uintptr_t)w_src & 15) == 0, "conv1x1_tc: W must be 16-byte aligned");
 
-    CUtensorMap tmWh, tmWl, tmX, tmRes;
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)Cp, (cuuint64_t)N};
-        cuuint64_t strides[1] = {(cuuint64_t)Cp * sizeof(float)};
+    CUtensorMap tmW, tmX, tmRes;
+    {   // the weight as it is (fp32, K-major): its TF32 planes are made in the kernel, one tile at a time
+        cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)w_ld * sizeof(float)};
         cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTM};
-        if (int rc = make_map(&tmWh, w_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-        if (int rc = make_map(&tmWl, w_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        if (int rc = make_map(&tmW, w_src, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
@@ -559,14 +573,14 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
         a.prefetch_residual = 1;
     }
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
     static const KernelFn table[2][2] = {{conv1x1_tc_kernel<false, false>, conv1x1_tc_kernel<false, true>},
                                          {conv1x1_tc_kernel<true, false>, conv1x1_tc_kernel<true, true>}};
     const KernelFn fn = table[alpha != nullptr][residual != nullptr];
     if (int rc = ensure_dynamic_smem((const void*)fn, kSmemBytes)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
     profile_mark_begin(stream);
-    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, tmRes, a);
+    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmW, tmX, tmRes, a);
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
                          2.0 * B * (double)HW * C * N, 3);

@@ -140,6 +140,33 @@ class FusedConvBNAct(nn.Module):
         return out
 
 
+class FastMaxPool(nn.Module):
+    """nn.MaxPool2d through gpfq_maxpool2d_f32 (one pass at HBM speed; PyTorch's NCHW kernel reaches a quarter of it on the
+    stem's 112 x 112 planes).  Anything the kernel does not cover runs the wrapped module."""
+
+    def __init__(self, pool):
+        super().__init__()
+        self.pool = pool
+
+    def forward(self, x):
+        pool = self.pool
+        k, s, p, d = pool.kernel_size, pool.stride, pool.padding, pool.dilation
+        one = lambda v: v if isinstance(v, int) else (v[0] if len(set(v)) == 1 else None)
+        k, s, p, d = one(k), one(s if s is not None else k), one(p), one(d)
+        ok = (None not in (k, s, p, d) and d == 1 and not pool.ceil_mode and not pool.return_indices and 2 * p <= k
+              and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.numel() > 0
+              and not pool._forward_hooks and not pool._forward_pre_hooks)
+        if ok:
+            B, C, H, W = x.shape
+            Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+            ok = Ho >= 1 and Wo >= 1
+        if not ok:
+            return pool(x)
+        out = torch.empty((B, C, Ho, Wo), dtype=torch.float32, device=x.device)
+        launch(lib.gpfq_maxpool2d_f32, x, B * C, H, W, k, s, p, out)
+        return out
+
+
 def _activation_bounds(node, modules):
     """(lo, hi) if ``node`` is a ReLU / ReLU6 (module or functional), else None."""
     if node.op == 'call_module':
@@ -223,6 +250,13 @@ def fuse_inference_forward(network, fuse_pointwise=True):
         if conv_node is not None:
             graph.erase_node(conv_node)
         sites += 1
+    pools = 0
+    for node in list(graph.nodes):                      # MaxPool2d modules -> the one-pass kernel
+        if node.op == 'call_module' and type(modules.get(node.target)) is nn.MaxPool2d and len(node.args) == 1:
+            name = f"_gpfq_maxpool_{pools}"
+            gm.add_submodule(name, FastMaxPool(modules[node.target]))
+            node.target = name
+            pools += 1
     graph.lint()
     gm.recompile()
     gm.fused_conv_sites = conv_sites

@@ -435,3 +435,16 @@ def test_slice_exchange_kernels_round_trip(reg, lam, groups):
     bad = torch.zeros(1, dtype=torch.int32, device=DEV)
     launch(lib.gpfq_pack_slice_f32, Qbad, d, d, 0, N, N, delta, K, mode, float(lam), e2, r2, buf, bad)
     assert int(bad.item()) == 1
+
+
+@pytest.mark.parametrize("shape,k,s,p", [((3, 5, 17, 23), 3, 2, 1), ((2, 4, 8, 8), 2, 2, 0), ((1, 3, 9, 9), 3, 1, 1),
+                                         ((2, 64, 112, 112), 3, 2, 1)])
+def test_maxpool_kernel_matches_pytorch(shape, k, s, p):
+    from quantized_neural_nets_b200.forward_fusion import FastMaxPool
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(11)).to(DEV)
+    x[0, 0, 1, 1] = float("nan")
+    pool = torch.nn.MaxPool2d(k, s, p)
+    got, want = FastMaxPool(pool)(x), pool(x)
+    assert got.shape == want.shape
+    assert torch.equal(torch.nan_to_num(got, nan=7.0), torch.nan_to_num(want, nan=7.0))
+    assert torch.isnan(got).sum() == torch.isnan(want).sum() > 0
