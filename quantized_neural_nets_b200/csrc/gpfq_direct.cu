@@ -45,10 +45,9 @@ static int resident_max_clusters(int TN, int CS, size_t smem);
 
 struct DirectPlan {
     int R, TN, n_tiles, TJ, j_tiles, nblk, gram_slices, gram_slice_len;
-    int pR, p_n_tiles, pTJ, p_j_tiles, use_persistent;     // single-launch variant
     int use_resident, r_cluster, r_TN, r_mpad;              // U resident in shared memory (+ cluster split of m)
     int64_t Npad, mpad;
-    size_t off_U, off_G, off_H, off_norm, off_gpart, off_part, off_epart, off_sync, total;
+    size_t off_U, off_G, off_H, off_norm, off_gpart, off_part, off_epart, total;
 };
 
 static DirectPlan make_plan(int n_rows, int d, int m) {
@@ -87,36 +86,6 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     }
     p.TN = 32 * p.R;
     p.n_tiles = (int)ceil_div(n_rows, p.TN);
-    // Single-launch (persistent) variant: one tile pass per CTA per block, recurrence inside the kernel.
-    double pbest = 1e300;
-    for (int R : {2, 1}) {
-        const int TN = 32 * R;
-        const int nt = (int)ceil_div(n_rows, TN);
-        const double eff = R == 2 ? 0.50 : 0.40;
-        const double stage_cycles = (double)TN * kJS * 5.0 * kB / 128.0 / eff;
-        const double recur_cycles = 9000.0 * (double)ceil_div(TN, kWarps * 4);
-        for (int jt = min_jt; jt <= stages; ++jt) {
-            const int tj_stages = (int)ceil_div(stages, jt);
-            const int jt_eff = (int)ceil_div(stages, tj_stages);
-            const int64_t tiles = (int64_t)nt * jt_eff;
-            const double cost = (double)ceil_div(tiles, 148) * (7000.0 + tj_stages * stage_cycles) + recur_cycles +
-                                40.0 * jt_eff;      // the last arrival sums jt_eff partials per neuron
-            if (cost < pbest * 0.999) {
-                pbest = cost;
-                p.pR = R;
-                p.pTJ = tj_stages * kJS;
-                p.p_j_tiles = jt_eff;
-            }
-        }
-    }
-    p.p_n_tiles = (int)ceil_div(n_rows, 32 * p.pR);
-    // per block the multi-launch path pays two launches (~6 us each incl. CPU cost) on top of its kernels
-    static const int force_p = getenv("GPFQ_PERSISTENT") ? atoi(getenv("GPFQ_PERSISTENT")) : -1;   // tuning aid
-    // Measured on B200 (r01): correct, but its serialised per-block chain (flag -> stage -> sweep -> ticket ->
-    // recurrence) costs 38 us per block against 31 us for the multi-launch path, whose recurrences spread over
-    // all SMs.  Kept for GPFQ_PERSISTENT=1 experiments; not selected by default.
-    p.use_persistent = (force_p >= 0) ? force_p : 0;
-    (void)pbest;
     // Resident variant (one launch per layer, U in shared memory).  A cluster of CS CTAs shares TN neurons and
     // splits the columns.  Fitted to B200 measurements (tools/resident_sweep.py, r01), per
     // 32-feature block:
@@ -178,12 +147,11 @@ static DirectPlan make_plan(int n_rows, int d, int m) {
     p.off_U = take((size_t)std::max<int64_t>(p.mpad, p.use_resident ? p.r_mpad : 0) * p.Npad * sizeof(float));
     p.off_G = take((size_t)p.nblk * kB * kB * sizeof(double));
     p.off_H = take((size_t)p.nblk * kB * kB * sizeof(double));
-    p.off_norm = take((size_t)p.nblk * kB * sizeof(float));
+    p.off_norm = take((size_t)p.nblk * 2 * kB * sizeof(float));
     p.off_gpart = take((size_t)p.nblk * p.gram_slices * 2 * kB * kB * sizeof(double));
-    const int max_jt = std::max(p.j_tiles, p.p_j_tiles);
+    const int max_jt = p.j_tiles;
     p.off_part = take((size_t)max_jt * p.Npad * kB * sizeof(double));
     p.off_epart = take((size_t)max_jt * p.Npad * sizeof(double));
-    p.off_sync = take((size_t)2 * p.p_n_tiles * sizeof(unsigned int));
     p.total = off;
     return p;
 }
@@ -276,9 +244,11 @@ __global__ void block_gram_finish_kernel(const double* __restrict__ gpart, int s
     G[e] = g;
     H[e] = h;
     const int t = r / kB, s = r % kB;
-    if (t == s) {
+    if (t == s) {       // norm32[blk] = kB squared norms, then their reciprocals (0 = take the IEEE division, see div_by)
         const float root = sqrtf((float)h);
-        norm32[blk * kB + t] = __fmul_rn(root, root);
+        const float nrm = __fmul_rn(root, root);
+        norm32[blk * 2 * kB + t] = nrm;
+        norm32[blk * 2 * kB + kB + t] = recip_or_zero(nrm);
     }
 }
 
@@ -308,7 +278,7 @@ template <int WPN>
 __global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
     __shared__ double Gs[kB][kB + 1];
     __shared__ double Hs[kB][kB + 1];
-    __shared__ float ns[kB];
+    __shared__ float ns[2 * kB];          // squared norms, then their reciprocals
     __shared__ double psum[8][kB];
     pdl_trigger();
     pdl_wait();
@@ -316,7 +286,7 @@ __global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
         Gs[e / kB][e % kB] = a.G[e];
         Hs[e / kB][e % kB] = a.H[e];
     }
-    if (threadIdx.x < kB) ns[threadIdx.x] = a.norm32[threadIdx.x];
+    if (threadIdx.x < 2 * kB) ns[threadIdx.x] = a.norm32[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.x * (8 / WPN) + warp / WPN;
@@ -347,6 +317,7 @@ __global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
     const int t_mine = a.t0 + lane;
     const float w = (t_mine < a.d) ? a.W[(int64_t)n * a.ldw + t_mine] : 0.f;
     const float delta = *a.delta;
+    const float rdelta = recip_or_zero(delta);
     float q_mine = 0.f;
     int lv_mine = 0;
     for (int t = 0; t < a.bvalid; ++t) {
@@ -354,10 +325,10 @@ __global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
         const float wt = __shfl_sync(0xffffffffu, w, t);
         const double dot = fma((double)wt, Gs[t][t], pt);   // <u_{t-1} + w_t x_t, xq_t>
         const float nrm = ns[t];
-        const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;   // step_algorithm.py:143-146
+        const float arg = (nrm > 0.f) ? div_by((float)dot, nrm, ns[kB + t]) : 0.f;   // step_algorithm.py:143-146
         int lv;
         const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv, a.seed, (uint32_t)(a.n_base + n),
-                                     (uint32_t)(a.t0 + t));
+                                     (uint32_t)(a.t0 + t), rdelta);
         if (lane == t) {
             q_mine = q;
             lv_mine = lv;
@@ -585,354 +556,6 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
 
 // ==========================================================================================
-// Persistent single-launch variant of the same algorithm, for layers whose per-block sweep is short
-// (small m and/or few neurons): the per-block launches, their CPU cost and the inter-kernel gaps dominate
-// there.  One cooperative launch per layer; CTA c owns the tiles c, c+grid, ... for the WHOLE layer.
-// Synchronisation is per neuron tile, not grid-wide:
-//   tickets[ntile] : every CTA that finishes the dot products of block k+1 for one (ntile, jt) takes a ticket;
-//                    the LAST of the j_tiles arrivals runs the block's recurrence for that tile's neurons
-//                    (8 warps x 4 interleaved neurons per round) and publishes
-//   flags[ntile]   = k+2  ("q of block k+1 is in global memory"), which the tile's CTAs wait for.
-// Data written by other CTAs (Q tiles, partial dots) and this CTA's own U tile are read with ld.global.cg.
-struct PersistArgs {
-    const float* W;
-    int64_t ldw;
-    float* Q;
-    int64_t ldq;
-    int8_t* levels;
-    int64_t ldl;
-    float* U;
-    double* part;
-    double* epart;
-    const double* G;        // [nblk][kB][kB]
-    const double* H;
-    const float* norm32;    // [nblk][kB]
-    const float* delta;
-    unsigned int* sync;     // tickets[n_tiles] | flags[n_tiles], zeroed before the launch
-    int64_t Npad, mpad;
-    int n_rows, d, nblk, TJ, j_tiles, n_tiles, mode, want_err, store_last_u, n_base;
-    unsigned long long seed;
-    float Kf, lam;
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-
-// The kB sequential decisions of block `blk` for the TN neurons of one tile; executed by a whole CTA.
-// lane = neuron (warps 0 .. TN/32-1): the neuron's 32 pending projections sit in the lane's registers, shifted so
-// that p[0] is the current feature; Gz / Hz are the block's Gram rows zero padded to 2*kB columns.
-template <int TN>
-__device__ void recur_tile(const PersistArgs& a, int row0, int blk, double* Gz, double* Hz, float* ns, float* qstage) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t0 = blk * kB;
-    const int bvalid = min(kB, a.d - t0);
-    __syncthreads();
-    for (int e = tid; e < kB * kB; e += kThreads) {
-        Gz[(e / kB) * 2 * kB + e % kB] = a.G[(size_t)blk * kB * kB + e];
-        Hz[(e / kB) * 2 * kB + e % kB] = a.H[(size_t)blk * kB * kB + e];
-    }
-    if (tid < kB) ns[tid] = a.norm32[(size_t)blk * kB + tid];
-    __syncthreads();
-    const float delta = *a.delta;
-    const int nl = warp * 32 + lane;
-    if (nl < TN) {
-        const int n = row0 + nl;
-        const bool valid = n < a.n_rows;
-        double p[kB];
-#pragma unroll
-        for (int s = 0; s < kB; ++s) p[s] = 0.0;
-        if (valid && blk > 0) {
-            for (int jt = 0; jt < a.j_tiles; ++jt) {           // fixed order
-                const double2* src = reinterpret_cast<const double2*>(a.part + ((int64_t)jt * a.Npad + n) * kB);
-#pragma unroll
-                for (int s = 0; s < kB / 2; ++s) {
-                    const double2 v = __ldcg(src + s);
-                    p[2 * s] += v.x;
-                    p[2 * s + 1] += v.y;
-                }
-            }
-        }
-        const float* wrow = a.W + (int64_t)(valid ? n : 0) * a.ldw + t0;
-        for (int t = 0; t < bvalid; ++t) {
-            const float wt = valid ? wrow[t] : 0.f;
-            const double* g = Gz + t * (2 * kB) + t;
-            const double* h = Hz + t * (2 * kB) + t;
-            const double dot = fma((double)wt, g[0], p[0]);
-            const float nrm = ns[t];
-            const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
-            int lv;
-            const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv, a.seed, (uint32_t)(a.n_base + n),
-                                         (uint32_t)(t0 + t));
-            qstage[t * TN + nl] = q;
-            if (a.levels && valid) a.levels[(int64_t)n * a.ldl + t0 + t] = (int8_t)lv;
-            const double wd = (double)wt, qd = -(double)q;
-#pragma unroll
-            for (int j = 0; j < kB - 1; ++j) p[j] = fma(qd, h[1 + j], fma(wd, g[1 + j], p[j + 1]));
-            p[kB - 1] = 0.0;
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < TN * bvalid; e += kThreads) {       // coalesced copy of the block's q to global Q
-        const int n2 = e / bvalid, t = e % bvalid;
-        if (row0 + n2 < a.n_rows) a.Q[(int64_t)(row0 + n2) * a.ldq + t0 + t] = qstage[t * TN + n2];
-    }
-    __threadfence();
-    __syncthreads();
-}
-
-template <int R>
-__global__ void __launch_bounds__(kThreads, 1)
-persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXq,
-                  const PersistArgs a) {
-    constexpr int TN = 32 * R;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-    float* base = reinterpret_cast<float*>(smem_raw + 128);
-    float* wsm = base + 2 * kStageFloats;
-    float* qsm = wsm + kB * TN;
-    double* Gs = reinterpret_cast<double*>(qsm + kB * TN);          // [kB][2 kB], columns kB.. stay zero
-    double* Hs = Gs + 2 * kB * kB;
-    float* ns = reinterpret_cast<float*>(Hs + 2 * kB * kB);         // [kB]
-    float* qstage = ns + kB;                                        // [kB][TN]
-    __shared__ int s_last;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles = a.n_tiles * a.j_tiles;
-    unsigned int* tickets = a.sync;
-    unsigned int* flags = a.sync + a.n_tiles;
-
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_barrier_init();
-    }
-    for (int e = tid; e < 4 * kB * kB; e += kThreads) Gs[e] = 0.0;
-    __syncthreads();
-    uint32_t gs = 0;   // stages issued so far by this CTA: buffer = gs & 1, mbarrier parity = (gs >> 1) & 1
-
-    // block 0 has no history: its recurrence runs on the CTA that owns the tile's first column range
-    for (int T = blockIdx.x; T < tiles; T += gridDim.x)
-        if (T % a.j_tiles == 0) {
-            recur_tile<TN>(a, (T / a.j_tiles) * TN, 0, Gs, Hs, ns, qstage);
-            if (tid == 0) st_release_u32(&flags[T / a.j_tiles], 1u);
-        }
-
-    float4* U4 = reinterpret_cast<float4*>(a.U);
-    for (int blk = 0; blk < a.nblk; ++blk) {
-        const int t0 = blk * kB;
-        const int bvalid = min(kB, a.d - t0);
-        const int nb4 = (bvalid + 3) >> 2;
-        const bool has_next = blk + 1 < a.nblk;
-        const bool first = blk == 0;
-        const bool store_u = has_next || a.store_last_u;
-        const bool want_err = !has_next && a.want_err;
-        const uint32_t stage_bytes = (uint32_t)((2 + (has_next ? 1 : 0)) * kB * kJS * sizeof(float));
-        for (int T = blockIdx.x; T < tiles; T += gridDim.x) {
-            const int ntile = T / a.j_tiles, jt = T % a.j_tiles;
-            const int row0 = ntile * TN;
-            const int64_t jbeg = (int64_t)jt * a.TJ;
-            const int64_t jend = min(jbeg + (int64_t)a.TJ, a.mpad);
-            const int nst = (int)((jend - jbeg) / kJS);
-
-            if (tid == 0) {
-                unsigned int spins = 0;
-                while (ld_acquire_u32(&flags[ntile]) < (unsigned)(blk + 1)) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 25)) __trap();    // seconds: a lost flag must not hang the GPU
-                }
-            }
-            __syncthreads();
-
-            auto issue = [&](int st, uint32_t g) {
-                float* buf = base + (g & 1) * kStageFloats;
-                uint64_t* bar = &bars[g & 1];
-                const int col = (int)(jbeg + (int64_t)st * kJS);
-                mbar_expect_tx(bar, stage_bytes);
-                tma_load_2d(buf, &tmX, col, t0, bar);
-                tma_load_2d(buf + kB * kJS, &tmXq, col, t0, bar);
-                if (has_next) tma_load_2d(buf + 2 * kB * kJS, &tmXq, col, t0 + kB, bar);
-            };
-            if (tid == 0 && nst > 0) issue(0, gs);
-
-            for (int e = tid; e < TN * (kB / 4); e += kThreads) {
-                const int nl = e >> 3, g = e & 7;
-                const int row = row0 + nl;
-                float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), qv = wv;
-                if (row < a.n_rows) {
-                    const float* wp = a.W + (int64_t)row * a.ldw;
-                    const float* qp = a.Q + (int64_t)row * a.ldq;
-                    const int t = t0 + 4 * g;
-                    if (t + 0 < a.d) { wv.x = wp[t + 0]; qv.x = __ldcg(qp + t + 0); }
-                    if (t + 1 < a.d) { wv.y = wp[t + 1]; qv.y = __ldcg(qp + t + 1); }
-                    if (t + 2 < a.d) { wv.z = wp[t + 2]; qv.z = __ldcg(qp + t + 2); }
-                    if (t + 3 < a.d) { wv.w = wp[t + 3]; qv.w = __ldcg(qp + t + 3); }
-                }
-                reinterpret_cast<float4*>(wsm)[g * TN + nl] = wv;
-                reinterpret_cast<float4*>(qsm)[g * TN + nl] = qv;
-            }
-            __syncthreads();
-
-            float P[R][kB];
-#pragma unroll
-            for (int i = 0; i < R; ++i)
-#pragma unroll
-                for (int s = 0; s < kB; ++s) P[i][s] = 0.f;
-            double esum[R];
-#pragma unroll
-            for (int i = 0; i < R; ++i) esum[i] = 0.0;
-
-            const int nq = nst * kChunksPerStage;
-            auto u_index = [&](int q) -> int64_t {
-                const int st = q / kChunksPerStage, c = q % kChunksPerStage;
-                const int64_t j = jbeg + (int64_t)st * kJS + warp * kColsPerWarp + c * 4;
-                return (j >> 2) * a.Npad + row0 + lane;
-            };
-            float4 ucur[R], unext[R];
-#pragma unroll
-            for (int i = 0; i < R; ++i) ucur[i] = unext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!first && nq > 0) {
-                const int64_t idx = u_index(0);
-#pragma unroll
-                for (int i = 0; i < R; ++i) ucur[i] = __ldcg(U4 + idx + 32 * i);
-            }
-            for (int q = 0; q < nq; ++q) {
-                const int st = q / kChunksPerStage, c = q % kChunksPerStage;
-                const uint32_t g = gs + (uint32_t)st;
-                if (c == 0) {
-                    if (tid == 0 && st + 1 < nst) issue(st + 1, g + 1);
-                    mbar_wait(&bars[g & 1], (g >> 1) & 1);
-                }
-                if (!first && q + 1 < nq) {
-                    const int64_t idx = u_index(q + 1);
-#pragma unroll
-                    for (int i = 0; i < R; ++i) unext[i] = __ldcg(U4 + idx + 32 * i);
-                }
-                const float* buf = base + (g & 1) * kStageFloats;
-                const int jl = warp * kColsPerWarp + c * 4;
-                const float* sx = buf + jl;
-                const float* sxq = buf + kB * kJS + jl;
-                const float* sxn = buf + 2 * kB * kJS + jl;
-#pragma unroll 2
-                for (int g4 = 0; g4 < nb4; ++g4) {
-                    float4 wv[R], qv[R];
-#pragma unroll
-                    for (int i = 0; i < R; ++i) {
-                        wv[i] = reinterpret_cast<const float4*>(wsm)[g4 * TN + lane + 32 * i];
-                        qv[i] = reinterpret_cast<const float4*>(qsm)[g4 * TN + lane + 32 * i];
-                    }
-#pragma unroll
-                    for (int ss = 0; ss < 4; ++ss) {
-                        const float4 xs = *reinterpret_cast<const float4*>(sx + (4 * g4 + ss) * kJS);
-                        const float4 xq = *reinterpret_cast<const float4*>(sxq + (4 * g4 + ss) * kJS);
-#pragma unroll
-                        for (int i = 0; i < R; ++i) {
-                            const float w = ss == 0 ? wv[i].x : ss == 1 ? wv[i].y : ss == 2 ? wv[i].z : wv[i].w;
-                            const float qq = ss == 0 ? qv[i].x : ss == 1 ? qv[i].y : ss == 2 ? qv[i].z : qv[i].w;
-                            ucur[i].x = __fsub_rn(__fadd_rn(ucur[i].x, __fmul_rn(w, xs.x)), __fmul_rn(qq, xq.x));
-                            ucur[i].y = __fsub_rn(__fadd_rn(ucur[i].y, __fmul_rn(w, xs.y)), __fmul_rn(qq, xq.y));
-                            ucur[i].z = __fsub_rn(__fadd_rn(ucur[i].z, __fmul_rn(w, xs.z)), __fmul_rn(qq, xq.z));
-                            ucur[i].w = __fsub_rn(__fadd_rn(ucur[i].w, __fmul_rn(w, xs.w)), __fmul_rn(qq, xq.w));
-                        }
-                    }
-                }
-                if (store_u) {
-                    const int64_t idx = u_index(q);
-#pragma unroll
-                    for (int i = 0; i < R; ++i) U4[idx + 32 * i] = ucur[i];
-                }
-                if (has_next) {
-#pragma unroll
-                    for (int s = 0; s < kB; ++s) {
-                        const float4 xn = *reinterpret_cast<const float4*>(sxn + s * kJS);
-#pragma unroll
-                        for (int i = 0; i < R; ++i) {
-                            float acc = P[i][s];
-                            acc = fmaf(ucur[i].x, xn.x, acc);
-                            acc = fmaf(ucur[i].y, xn.y, acc);
-                            acc = fmaf(ucur[i].z, xn.z, acc);
-                            acc = fmaf(ucur[i].w, xn.w, acc);
-                            P[i][s] = acc;
-                        }
-                    }
-                }
-                if (want_err) {
-#pragma unroll
-                    for (int i = 0; i < R; ++i) {
-                        float e = ucur[i].x * ucur[i].x;
-                        e = fmaf(ucur[i].y, ucur[i].y, e);
-                        e = fmaf(ucur[i].z, ucur[i].z, e);
-                        e = fmaf(ucur[i].w, ucur[i].w, e);
-                        esum[i] += (double)e;
-                    }
-                }
-                if (c == kChunksPerStage - 1) __syncthreads();
-#pragma unroll
-                for (int i = 0; i < R; ++i) ucur[i] = unext[i];
-            }
-            gs += (uint32_t)nst;
-            __syncthreads();
-
-            if (has_next) {
-                float* red = base;
-#pragma unroll
-                for (int i = 0; i < R; ++i)
-#pragma unroll
-                    for (int s = 0; s < kB; ++s) red[(warp * TN + lane + 32 * i) * kRedStride + s] = P[i][s];
-                __syncthreads();
-                for (int e = tid; e < TN * kB; e += kThreads) {
-                    const int n = e / kB, s = e % kB;
-                    double acc = 0.0;
-#pragma unroll
-                    for (int w = 0; w < kWarps; ++w) acc += (double)red[(w * TN + n) * kRedStride + s];
-                    a.part[((int64_t)jt * a.Npad + row0 + n) * kB + s] = acc;
-                }
-                __threadfence();
-                __syncthreads();
-                if (tid == 0) {
-                    const unsigned int ticket = atomicAdd(&tickets[ntile], 1u);
-                    s_last = (ticket == (unsigned)((blk + 1) * a.j_tiles - 1));
-                    __threadfence();
-                }
-                __syncthreads();
-                if (s_last) {   // every column range of this neuron tile has delivered its dots for block blk+1
-                    recur_tile<TN>(a, row0, blk + 1, Gs, Hs, ns, qstage);
-                    if (tid == 0) st_release_u32(&flags[ntile], (unsigned)(blk + 2));
-                }
-            }
-            if (want_err) {
-                __syncthreads();
-                double* red2 = reinterpret_cast<double*>(base);
-#pragma unroll
-                for (int i = 0; i < R; ++i) red2[warp * TN + lane + 32 * i] = esum[i];
-                __syncthreads();
-                for (int n = tid; n < TN; n += kThreads) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int w = 0; w < kWarps; ++w) acc += red2[w * TN + n];
-                    a.epart[(int64_t)jt * a.Npad + row0 + n] = acc;
-                }
-                __syncthreads();
-            }
-        }
-    }
-}
-
-template <int R>
-static size_t persistent_smem_bytes() {
-    constexpr int TN = 32 * R;
-    return 128 + (size_t)(2 * kStageFloats + 2 * kB * TN) * sizeof(float) + 4 * kB * kB * sizeof(double) +
-           (size_t)(kB + kB * TN) * sizeof(float) + 64;
-}
-
-
-// ==========================================================================================
 // Resident variant for small calibration sets (m_pad <= 768, e.g. every Linear layer at bs=256):
 // "each CTA owns a neuron slice of U, resident on chip" (BASELINE.json kernel (1)).  A CTA owns 32
 // neurons and ALL m columns, so nothing ever crosses CTAs: U lives in shared memory for the whole layer,
@@ -990,8 +613,8 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     double* P64 = Hs + 2 * kB * kB;                                            // [TN][kB + 1]
     float* wsm = reinterpret_cast<float*>(P64 + TN * (kB + 1));                // [2][kB/4][TN] float4
     float* qsm = wsm + 2 * kB * TN;                                            // [kB/4][TN] float4
-    float* ns = qsm + kB * TN;                                                 // [kB]
-    float* red = ns + kB;                                                      // [kWarps][TN][17]
+    float* ns = qsm + kB * TN;                                                 // [2 kB]: squared norms, their reciprocals
+    float* red = ns + 2 * kB;                                                  // [kWarps][TN][17]
     const int CS = a.cluster;
     // cluster: this CTA makes the decisions of OWN = TN / CS of the tile's neurons; P64 then holds the CS senders'
     // partial projections of those neurons, [CS][OWN][kB + 1]
@@ -1008,6 +631,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int nst = mc / kRJS;
     const int total_stages = a.nblk * nst;
     const float delta = *a.delta;
+    const float rdelta = recip_or_zero(delta);
 
     if (tid == 0) {
         for (int i = 0; i < S; ++i) mbar_init(&bars[i], 1);
@@ -1055,7 +679,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             cp_async16(Gs + r * 2 * kB + 2 * c2, g + 2 * e);
             cp_async16(Hs + r * 2 * kB + 2 * c2, h + 2 * e);
         }
-        if (tid < kB / 4) cp_async16(ns + 4 * tid, a.norm32 + (size_t)k * kB + 4 * tid);
+        if (tid < 2 * kB / 4) cp_async16(ns + 4 * tid, a.norm32 + (size_t)k * 2 * kB + 4 * tid);
     };
     // The kB decisions of block k.  Work item = neuron, one warp per neuron with lane = feature of the block (the
     // arithmetic of recur_kernel): lane s keeps p_s = <u, xq_s>; per step the current p_t and w_t are shuffled to
@@ -1100,10 +724,10 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     const double* h = Hs + t * (2 * kB) + t;
                     const double dot = fma((double)wt, g[0], p[0]);
                     const float nrm = ns[t];
-                    const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                    const float arg = (nrm > 0.f) ? div_by((float)dot, nrm, ns[kB + t]) : 0.f;
                     int lv;
                     const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
-                                                         (uint32_t)(a.n_base + row0 + n), (uint32_t)(t0 + t));
+                                                         (uint32_t)(a.n_base + row0 + n), (uint32_t)(t0 + t), rdelta);
                     qsm[((t >> 2) * TN + n) * 4 + (t & 3)] = q;
                     if (a.levels && row0 + n < a.n_rows) a.levels[(int64_t)(row0 + n) * a.ldl + t0 + t] = (int8_t)lv;
                     const double wd = (double)wt, qd = -(double)q;
@@ -1148,16 +772,16 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (cnt == 2) {
                 for (int t = 0; t < bvalid; ++t) {
                     const double gtt = Gs[t * (2 * kB) + t], gl = Gs[t * (2 * kB) + lane], hl = Hs[t * (2 * kB) + lane];
-                    const float nrm = ns[t];
+                    const float nrm = ns[t], rnrm = ns[kB + t];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const double pt = __shfl_sync(0xffffffffu, pr[i], t);
                         const float wt = __shfl_sync(0xffffffffu, wr[i], t);
                         const double dot = fma((double)wt, gtt, pt);
-                        const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                        const float arg = (nrm > 0.f) ? div_by((float)dot, nrm, rnrm) : 0.f;
                         int lv;
                         const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
-                                                             (uint32_t)(a.n_base + row0 + own0 + nl0 + i), (uint32_t)(t0 + t));
+                                                             (uint32_t)(a.n_base + row0 + own0 + nl0 + i), (uint32_t)(t0 + t), rdelta);
                         if (lane == t) {
                             q_mine[i] = q;
                             lv_mine[i] = lv;
@@ -1174,10 +798,10 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     const float wt = __shfl_sync(0xffffffffu, wr[0], t);
                     const double dot = fma((double)wt, Gs[t * (2 * kB) + t], pt);
                     const float nrm = ns[t];
-                    const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                    const float arg = (nrm > 0.f) ? div_by((float)dot, nrm, ns[kB + t]) : 0.f;
                     int lv;
                     const float q = alphabet_map_t<MODE>(arg, delta, a.Kf, a.lam, &lv, a.seed,
-                                                         (uint32_t)(a.n_base + row0 + own0 + nl0), (uint32_t)(t0 + t));
+                                                         (uint32_t)(a.n_base + row0 + own0 + nl0), (uint32_t)(t0 + t), rdelta);
                     if (lane == t) {
                         q_mine[0] = q;
                         lv_mine[0] = lv;
@@ -1347,7 +971,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 static size_t resident_smem_host(int64_t mc, int slots, int TN, int cluster) {
     (void)cluster;      // the cluster's hand-off slots reuse the P64 area
     return 128 + (size_t)slots * (3 * kB * kRJSHost) * sizeof(float) + (size_t)4 * kB * kB * sizeof(double) +
-           (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + kB) * sizeof(float) +
+           (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + 2 * kB) * sizeof(float) +
            (size_t)8 * TN * 17 * sizeof(float) + (size_t)mc * TN * sizeof(float);
 }
 
@@ -1356,7 +980,7 @@ static size_t resident_smem_bytes(int mc, int slots, int TN, int cluster = 1) {
     (void)cluster;
     return 128 + (size_t)slots * kRStageFloats * sizeof(float) + (size_t)2 * kB * kB * sizeof(double) +
            (size_t)2 * kB * kB * sizeof(double) /* zero padding of G, H rows */ +
-           (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + kB) * sizeof(float) +
+           (size_t)TN * (kB + 1) * sizeof(double) + (size_t)(3 * kB * TN + 2 * kB) * sizeof(float) +
            (size_t)kWarps * TN * 17 * sizeof(float) + (size_t)mc * TN * sizeof(float);
 }
 
@@ -1441,37 +1065,6 @@ static int launch_sweep(const DirectPlan& p, const CUtensorMap& tmX, const CUten
     return 0;
 }
 
-template <int R>
-static int launch_persistent(const DirectPlan& p, const CUtensorMap& tmX, const CUtensorMap& tmXq, PersistArgs& a,
-                             cudaStream_t stream) {
-    int max_ctas = 0;
-    const size_t smem = persistent_smem_bytes<R>();
-    if (int rc = ensure_dynamic_smem((const void*)persistent_kernel<R>, smem)) return rc;
-    {
-        int dev = 0, sms = 0, per_sm = 0;
-        GPFQ_CUDA_TRY(cudaGetDevice(&dev));
-        GPFQ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        GPFQ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel<R>, kThreads, smem));
-        GPFQ_REQUIRE(per_sm >= 1, "persistent_kernel does not fit on an SM");
-        max_ctas = sms * per_sm;
-    }
-    const int tiles = p.p_n_tiles * p.p_j_tiles;
-    const int grid = std::min(tiles, max_ctas);
-    void* params[] = {(void*)&tmX, (void*)&tmXq, (void*)&a};
-    profile_mark_begin(stream);
-    GPFQ_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)persistent_kernel<R>, dim3(grid), dim3(kThreads), params, smem,
-                                              stream));
-    if (profile_on()) {
-        const double nm = (double)a.n_rows * (double)a.mpad;
-        const double bytes = (2.0 * a.nblk - 1.0) * 4.0 * nm + 12.0 * kB * (double)a.mpad * a.nblk +
-                             8.0 * a.n_rows * kB * a.nblk + 8.0 * p.p_j_tiles * (double)a.n_rows * kB * a.nblk;
-        const double instr = nm * (4.0 * a.d + 1.0 * kB * (a.nblk - 1));
-        profile_mark_end(stream, bytes, instr);
-    }
-    count_launch();
-    return 0;
-}
-
 int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, int64_t ldx, int d, int m, int n_rows,
                  const float* delta, int K, int mode, float lam, unsigned long long seed, int n_base, float* Q, int64_t ldq,
                  int8_t* levels, double* row_err2, float* U_out, int64_t ldu, void* workspace, size_t workspace_bytes,
@@ -1551,37 +1144,13 @@ int direct_solve(const float* W, int64_t ldw, const float* X, const float* Xq, i
         return 0;
     }
 
-    if (p.use_persistent) {
-        unsigned int* sync = (unsigned int*)(ws + p.off_sync);
-        GPFQ_CUDA_TRY(cudaMemsetAsync(sync, 0, (size_t)2 * p.p_n_tiles * sizeof(unsigned int), stream));
-        PersistArgs a{};
-        a.W = W; a.ldw = ldw; a.Q = Q; a.ldq = ldq; a.levels = levels; a.ldl = d; a.U = U; a.part = part; a.epart = epart;
-        a.G = G; a.H = H; a.norm32 = norm32; a.delta = delta; a.sync = sync; a.Npad = p.Npad; a.mpad = p.mpad;
-        a.n_rows = n_rows; a.d = d; a.nblk = p.nblk; a.TJ = p.pTJ; a.j_tiles = p.p_j_tiles; a.n_tiles = p.p_n_tiles;
-        a.mode = mode; a.want_err = (row_err2 != nullptr); a.store_last_u = (U_out != nullptr);
-        a.Kf = (float)K; a.lam = lam; a.seed = seed; a.n_base = n_base;
-        int rc = p.pR == 2 ? launch_persistent<2>(p, tmX, tmXq, a, stream) : launch_persistent<1>(p, tmX, tmXq, a, stream);
-        if (rc) return rc;
-        if (row_err2) {
-            err_finish_kernel<<<(unsigned)ceil_div(n_rows, 128), 128, 0, stream>>>(epart, p.p_j_tiles, p.Npad, n_rows,
-                                                                                 row_err2);
-            GPFQ_CHECK_LAUNCH();
-        }
-        if (U_out) {
-            untile_kernel<<<dim3((unsigned)ceil_div(m, 256), (unsigned)std::min(n_rows, 65535)), 256, 0, stream>>>(U, p.Npad, n_rows, m,
-                                                                                                 U_out, ldu);
-            GPFQ_CHECK_LAUNCH();
-        }
-        return 0;
-    }
-
     for (int blk = 0; blk < p.nblk; ++blk) {
         const int t0 = blk * kB;
         const int bvalid = std::min(kB, d - t0);
         RecurArgs r{};
         r.W = W; r.ldw = ldw; r.Q = Q; r.ldq = ldq; r.levels = levels; r.ldl = d;
         r.part = part; r.G = G + (size_t)blk * kB * kB; r.H = H + (size_t)blk * kB * kB;
-        r.norm32 = norm32 + (size_t)blk * kB; r.delta = delta; r.Npad = p.Npad;
+        r.norm32 = norm32 + (size_t)blk * 2 * kB; r.delta = delta; r.Npad = p.Npad;
         r.n_rows = n_rows; r.d = d; r.t0 = t0; r.bvalid = bvalid; r.j_tiles = p.j_tiles;
         r.first = (blk == 0); r.mode = mode; r.Kf = (float)K; r.lam = lam; r.seed = seed; r.n_base = n_base;
         profile_mark_begin(stream);

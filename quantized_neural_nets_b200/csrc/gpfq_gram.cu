@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_base = blockIdx.x * kPathNeurons;
     const float delta = *a.delta;
+    const float rdelta = recip_or_zero(delta);
     const bool want_norms = a.row_err2 != nullptr || a.row_ref2 != nullptr;
 
     for (int e = tid; e < kPathNeurons * dpad32; e += blockDim.x) {
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
             const double gtt = M1[t * 33 + t], htt = M2[t * 33 + t], att = M3[t * 33 + t];
             const float root = sqrtf((float)htt);
             const float nrm = __fmul_rn(root, root);            // linalg.norm(.)**2, step_algorithm.py:142
+            const float rnrm = recip_or_zero(nrm);              // off the decision chain (depends on H only)
             const double gl = M1[t * 33 + lane], hl = M2[t * 33 + lane];
             const double al = M3[t * 33 + lane], gtl = M1[lane * 33 + t];      // A[t][s], GT[s][t]
 #pragma unroll
@@ -287,10 +289,10 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
                 const double pt = __shfl_sync(0xffffffffu, p[i], t);
                 const float wt = __shfl_sync(0xffffffffu, wl[i], t);
                 const double dot = fma((double)wt, gtt, pt);
-                const float arg = (nrm > 0.f) ? __fdiv_rn((float)dot, nrm) : 0.f;
+                const float arg = (nrm > 0.f) ? div_by((float)dot, nrm, rnrm) : 0.f;
                 int lv;
                 const float q = alphabet_map(arg, delta, a.Kf, a.mode, a.lam, &lv, a.seed,
-                                             (uint32_t)(a.n_base + n_base + warp * kNB + i), (uint32_t)(t0 + t));
+                                             (uint32_t)(a.n_base + n_base + warp * kNB + i), (uint32_t)(t0 + t), rdelta);
                 if (lane == t) {
                     qmine[i] = q;
                     lvmine[i] = lv;

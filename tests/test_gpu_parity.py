@@ -241,18 +241,18 @@ def test_gram_matrices_tcgen05_accuracy(qb):
             assert rel < tol, (solver, rel)
 
 
-@pytest.mark.parametrize("env", [{"GPFQ_RESIDENT": "1"}, {"GPFQ_PERSISTENT": "1", "GPFQ_RESIDENT": "0"},
-                                 {"GPFQ_RESIDENT": "0", "GPFQ_PERSISTENT": "0"},
+@pytest.mark.parametrize("env", [{"GPFQ_RESIDENT": "1"},
+                                 {"GPFQ_RESIDENT": "0"},
                                  {"GPFQ_RESIDENT": "1", "GPFQ_RESIDENT_CLUSTER": "1", "GPFQ_RESIDENT_TN": "32"},
                                  {"GPFQ_RESIDENT": "1", "GPFQ_RESIDENT_CLUSTER": "2", "GPFQ_RESIDENT_TN": "32"},
                                  {"GPFQ_RESIDENT": "1", "GPFQ_RESIDENT_CLUSTER": "4", "GPFQ_RESIDENT_TN": "16"},
                                  {"GPFQ_RESIDENT": "1", "GPFQ_RESIDENT_CLUSTER": "8", "GPFQ_RESIDENT_TN": "32"},
                                  {"GPFQ_RESIDENT": "1", "GPFQ_RESIDENT_CLUSTER": "16", "GPFQ_RESIDENT_TN": "16"}],
-                         ids=["resident", "persistent", "multi_launch", "resident_c1_t32_lane_neuron",
+                         ids=["resident", "multi_launch", "resident_c1_t32_lane_neuron",
                               "resident_c2_t32", "resident_c4_t16", "resident_c8_t32", "resident_c16_t16"])
 def test_direct_solver_variants_in_subprocess(env):
-    """The three launch structures of the direct solver (multi-launch sweep+recur, single-launch resident,
-    single-launch persistent) are selected per layer by a heuristic; force each one over the same small
+    """The launch structures of the direct solver (multi-launch sweep+recur, single-launch resident with 1-16 CTA
+    clusters) are selected per layer by a heuristic; force each one over the same small
     problems (oracle-checked inside tools/sanitize_smoke.py).  The switches are read once per process."""
     import os
     import subprocess

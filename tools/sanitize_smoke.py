@@ -1,5 +1,5 @@
 """Small end-to-end exercise of every kernel in libgpfq_b200 (for compute-sanitizer); checks results against the
-CPU oracle.  The direct-solver variant is chosen with GPFQ_RESIDENT / GPFQ_PERSISTENT in the environment."""
+CPU oracle.  The direct-solver variant is chosen with GPFQ_RESIDENT (and GPFQ_RESIDENT_CLUSTER / GPFQ_RESIDENT_TN) in the environment."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
