@@ -32,9 +32,12 @@ namespace gpfq {
 constexpr int kB = 32;            // greedy steps per block
 constexpr int kThreads = 256;     // sweep CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kJS = 128;          // calibration columns per smem stage
-constexpr int kColsPerWarp = kJS / kWarps;       // 16
-constexpr int kChunksPerStage = kColsPerWarp / 4;  // 4 column quads per warp per stage
+// Calibration columns per shared-memory stage = the granularity at which a layer's columns are dealt out to CTAs.
+// 128 in round 1: ncu showed 100 of 148 SMs busy on 256 x 1024 x 12800 (100 stages, 2 neuron tiles -> 2 x 50 CTAs of
+// two stages); with 64 the same layer runs as 2 x 67 CTAs of three half-size stages.
+constexpr int kJS = 64;
+constexpr int kColsPerWarp = kJS / kWarps;       // 8
+constexpr int kChunksPerStage = kColsPerWarp / 4;  // 2 column quads per warp per stage
 constexpr int kStageFloats = 3 * kB * kJS;       // x_prev | xq_prev | xq_next
 constexpr int kRedStride = kB + 1;
 constexpr int kMaxTJ = 4096;      // keeps every fp32 accumulation chain <= 512 terms

@@ -241,4 +241,5 @@ def test_pointwise_convs_as_gemm_match_cudnn_and_keep_hooks():
         got, got_b = model(x), conv(y)
     handle.remove()
     assert seen == [(8, 512, 28, 28)]
-    assert (got - want).norm() <= 1e-6 * want.norm() and torch.allclose(got_b, want_b, rtol=1e-5, atol=1e-6)
+    # the 1x1 layers now run on the tensor cores in split-TF32 (fp32-level, but not cuDNN's rounding): 50 layers deep
+    assert (got - want).norm() <= 1e-5 * want.norm() and torch.allclose(got_b, want_b, rtol=1e-4, atol=1e-5)
