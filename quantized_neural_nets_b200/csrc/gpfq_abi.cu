@@ -210,25 +210,28 @@ __global__ void unpack_levels_kernel(const uint8_t* __restrict__ in, int64_t n, 
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int k, int s, int p, int Ho, int Wo,
                float* __restrict__ out) {
-    const int64_t total = planes * Ho * Wo;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int xo = (int)(e % Wo);
-        const int yo = (int)((e / Wo) % Ho);
-        const int64_t pl = e / ((int64_t)Wo * Ho);
+    // blockIdx.y walks the planes, blockIdx.x / threadIdx.x the pixels of one plane: 32-bit index arithmetic only
+    const int HWo = Ho * Wo;
+    for (int64_t pl = blockIdx.y; pl < planes; pl += gridDim.y) {
         const float* src = in + pl * (int64_t)H * W;
-        const int y0 = yo * s - p, x0 = xo * s - p;
-        float m = -INFINITY;
-        for (int i = 0; i < k; ++i) {
-            const int y = y0 + i;
-            if (y < 0 || y >= H) continue;
-            for (int j = 0; j < k; ++j) {
-                const int x = x0 + j;
-                if (x < 0 || x >= W) continue;
-                const float v = __ldg(src + (int64_t)y * W + x);
-                m = (v > m || v != v) ? v : m;
+        float* dst = out + pl * (int64_t)HWo;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < HWo; e += gridDim.x * blockDim.x) {
+            const int yo = e / Wo, xo = e - yo * Wo;
+            const int y0 = yo * s - p, x0 = xo * s - p;
+            float m = -INFINITY;
+            for (int i = 0; i < k; ++i) {
+                const int y = y0 + i;
+                if (y < 0 || y >= H) continue;
+                const float* row = src + y * W;
+                for (int j = 0; j < k; ++j) {
+                    const int x = x0 + j;
+                    if (x < 0 || x >= W) continue;
+                    const float v = __ldg(row + x);
+                    m = (v > m || v != v) ? v : m;
+                }
             }
+            dst[e] = m;
         }
-        out[e] = m;
     }
 }
 
@@ -516,9 +519,9 @@ int gpfq_maxpool2d_f32(const float* in, int64_t planes, int32_t H, int32_t W, in
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     GPFQ_REQUIRE(Ho >= 1 && Wo >= 1 && in && out, "gpfq_maxpool2d_f32: empty output or null pointer");
     if (planes == 0) return 0;
-    const int64_t total = planes * Ho * Wo;
-    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-        in, planes, H, W, k, stride, pad, Ho, Wo, out);
+    GPFQ_REQUIRE((int64_t)H * W < (1ll << 31), "gpfq_maxpool2d_f32: plane too large");
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)Ho * Wo, 256), 64), (unsigned)std::min<int64_t>(planes, 65535));
+    maxpool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, planes, H, W, k, stride, pad, Ho, Wo, out);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }
