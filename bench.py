@@ -39,8 +39,10 @@ NCU_BN_ACT_TRAFFIC = {"dram_bytes_per_launch": 2440.1e6, "algorithmic_bytes_same
                       "launch": "BatchNorm + residual + ReLU of a (256, 256, 56, 56) activation",
                       "source": "profiles/r01_bn_act_kernel_ncu_full_summary.txt"}
 
-# dram bytes of one conv1x1_tc_kernel launch (ncu --set full; filled from profiles/r02_conv1x1_tc_kernel_ncu_full_summary.txt)
-NCU_CONV_TRAFFIC = {"dram_bytes_per_launch": None, "algorithmic_bytes_same_launch": None, "launch": "pending", "source": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv1x1_tc_kernel launch, from the committed ncu --set full capture
+NCU_CONV_TRAFFIC = {"dram_bytes_per_launch": 2118.3e6, "algorithmic_bytes_same_launch": 1849.7e6,
+                    "launch": "1x1 convolution 64 -> 256 + BatchNorm + residual + ReLU of a (256, 64, 56, 56) activation, 507 us",
+                    "source": "profiles/r02_conv_64_256_res_ncu_full_summary.txt"}
 
 L2_PEAK_GBS = 8300.0     # L2-resident read bandwidth measured by tools/microbench.cu on this pool's B200 (r01)
 
@@ -547,15 +549,44 @@ def fc6_variants(dev, direct_ms):
     return out
 
 
+def full_size_spot_check(kept):
+    """Parity at the bench's FULL layer sizes (bs = 256: m up to 200,960): the (W, X) sub-problems the CPU arm has just
+    run through the reference -- the first k features of one layer shape per class -- are handed to the CUDA solvers and
+    the levels compared.  GPFQ decides feature t from features <= t only, so the first k columns are a complete problem."""
+    from quantized_neural_nets_b200 import _lib, step_algorithm as sa
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows, worst = [], 1.0
+    for c in kept:
+        N, d, m = c["shape"]
+        W, X, K = c["W"].to(dev), c["X"].to(dev), c["K"]
+        delta = c["delta"].to(dev)
+        lv_ref = torch.round(c["Q"].double() / float(c["delta"])).to(torch.int32)
+        rec = {"shape": f"{N}x{d}x{m}", "features": c["k"]}
+        for name, solver in (("direct", _lib.SOLVER_DIRECT), ("gram_tcgen05", _lib.SOLVER_GRAM)):
+            if solver == _lib.SOLVER_GRAM and not sa.gram_eligible(N, c["k"], m):
+                continue
+            Q, _, _ = sa.quantize_layer_impl(W, X, X, m, 1.16 / K, K, 1, None, 0.1, 1, False, dev, solver=solver,
+                                             return_partials=True, delta=delta)
+            lv = torch.round(Q.double().cpu() / float(c["delta"])).to(torch.int32)
+            rec[name] = round(float((lv == lv_ref).float().mean()), 6)
+            worst = min(worst, rec[name])
+        rows.append(rec)
+    return {"what": "level agreement of the CUDA solvers with the reference's own decisions on the first k features of "
+                    "full-size (bs = 256) layer shapes, same (W, X)", "min": worst, "per_shape": rows}
+
+
 def cpu_baseline_leg(args, shapes, units):
     """``cpu_baseline`` of the CUDA arm's line (rank 0, N = 1): one bounded sample of the reference on the host cores
     (oracle/cpu_baseline.py) and, unless --no-validate-cpu, the measured-vs-extrapolated check against one complete
     real reference run (AlexNet)."""
     from oracle import cpu_baseline as cb
     cores = cb.host_threads()
-    step = cb.sample_step(args.model, args.batch, args.retain, args.bits, shapes, seconds_per_class=args.cpu_class_seconds)
+    kept = []
+    step = cb.sample_step(args.model, args.batch, args.retain, args.bits, shapes, seconds_per_class=args.cpu_class_seconds,
+                          keep=kept)
     out = {"value": units / step["seconds"], "unit": UNIT, "cores": cores, "kind": step["kind"],
            "solver_only_value": units / step["solver_s"], "sample": cb.describe(step, cores, len(shapes), args.batch)}
+    out["full_size_spot_check"] = full_size_spot_check(kept)
     if args.validate_cpu:
         out["validation"] = cb.validate(batch=args.batch, retain=args.retain)
     return out

@@ -109,9 +109,12 @@ def _quiet():
         yield
 
 
-def time_greedy_features(StepAlgorithm, N, d, m, k, gen, bits=4):
+def time_greedy_features(StepAlgorithm, N, d, m, k, gen, bits=4, keep=None):
     """Seconds the reference's loop takes for the first k features of an (N, d, m) layer: W, X are full width and the
-    loop runs on their first-k-column views, so columns are read with stride d as in the complete layer."""
+    loop runs on their first-k-column views, so columns are read with stride d as in the complete layer.  With a list
+    ``keep`` the problem and the reference's decisions are appended to it (W_k, X_k, Q_k, delta, K) so that the caller can
+    hand the same inputs to the CUDA solver (GPFQ decides feature t from features <= t only, so the first k columns of Q
+    are a complete sub-problem)."""
     K = 2 ** (bits - 1)
     W = torch.randn(N, d, generator=gen) * 0.05
     X = torch.relu(torch.randn(m, d, generator=gen))
@@ -125,10 +128,14 @@ def time_greedy_features(StepAlgorithm, N, d, m, k, gen, bits=4):
             StepAlgorithm._quantization(Wk, Qk, U, Xk, Xk, StepAlgorithm._msq, delta, K, 0.1)
         else:
             orc.greedy_path(Wk, Qk, U, Xk, Xk, orc.msq, delta, K, 0.0)
-        return time.perf_counter() - t0
+        dt = time.perf_counter() - t0
+    if keep is not None:
+        keep.append({"shape": (N, d, m), "k": k, "W": Wk.contiguous(), "X": Xk.contiguous(), "Q": Qk.contiguous().clone(),
+                     "delta": delta.clone(), "K": K})
+    return dt
 
 
-def sample_greedy(shapes, StepAlgorithm, seconds_per_class, bits=4, max_classes=9):
+def sample_greedy(shapes, StepAlgorithm, seconds_per_class, bits=4, max_classes=9, keep=None):
     """-> (extrapolated seconds for all layers, seconds spent, {class: units/s})."""
     gen = torch.Generator().manual_seed(3)
     rates, spent = {}, 0.0
@@ -136,7 +143,7 @@ def sample_greedy(shapes, StepAlgorithm, seconds_per_class, bits=4, max_classes=
         k0 = min(2, d)
         dt0 = time_greedy_features(StepAlgorithm, N, d, m, k0, gen, bits)       # also touches pages / warms caches
         k = int(min(d, max(k0, seconds_per_class / (dt0 / k0))))
-        dt = time_greedy_features(StepAlgorithm, N, d, m, k, gen, bits)
+        dt = time_greedy_features(StepAlgorithm, N, d, m, k, gen, bits, keep)
         spent += dt0 + dt
         rates[(N, m)] = float(N) * m * k / dt
     total = 0.0
@@ -220,11 +227,11 @@ def validate(model_name="alexnet", batch=256, retain=0.25, seconds_per_class=0.3
             "sampling_s": round(spent + fwd_spent, 2)}
 
 
-def sample_step(model_name, batch, retain, bits, shapes, seconds_per_class=0.3, forward_batch=64):
+def sample_step(model_name, batch, retain, bits, shapes, seconds_per_class=0.3, forward_batch=64, keep=None):
     """One bounded-sample "step" -> dict(seconds (extrapolated quantize_network() time), spent, solver_s, forward_s,
     full_forward_s, equiv, kind)."""
     StepAlgorithm, _, extract_layers, kind = reference_modules()
-    solver_s, spent, rates = sample_greedy(shapes, StepAlgorithm, seconds_per_class, bits)
+    solver_s, spent, rates = sample_greedy(shapes, StepAlgorithm, seconds_per_class, bits, keep=keep)
     fwd_s, fwd_spent, full, equiv = sample_forward(model_name, batch, extract_layers, sample_batch=forward_batch)
     return {"seconds": solver_s + fwd_s, "spent": spent + fwd_spent, "solver_s": solver_s, "forward_s": fwd_s,
             "full_forward_s": full, "equiv": equiv, "kind": kind, "classes": len(rates),

@@ -196,15 +196,16 @@ class QuantizeNeuralNet:
         if calibration not in ('fresh', 'reuse'):
             raise ValueError(f"calibration must be 'fresh' or 'reuse', not {calibration!r}")
         self.calibration = calibration
-        # Run the calibration forward passes through a torch.fx copy of each network in which every inference
-        # BatchNorm2d (+ residual add) (+ ReLU) is ONE elementwise CUDA launch (forward_fusion.py): same fp32
-        # arithmetic as PyTorch's CPU batch norm, a quarter less HBM traffic per pass.  The fused callables share all
-        # Conv2d / Linear modules with the networks, so hooks and weight updates behave as before.
+        # Run the calibration forward passes through a torch.fx copy of each network in which every 1x1 / strided
+        # Conv2d -> BatchNorm2d (-> + residual) (-> ReLU) site is ONE tensor-core kernel, every other inference BatchNorm2d
+        # (+ add) (+ ReLU) one elementwise launch and every MaxPool2d one pass (forward_fusion.py).
+        # The fused callables share all Conv2d / Linear modules with the networks, so hooks and weight updates behave as
+        # before.
         self.fuse_forward = fuse_forward
-        # Opt-in experiment, measured as a LOSS in r01 (forward_fusion.pointwise_convs_as_gemm): stride-1 1x1
-        # convolutions as torch.matmul.  In isolation cuBLAS beats cuDNN on every ResNet-50 shape (20 vs 27 ms per
-        # forward), but torch.bmm materialises the batch-broadcast weight (17 ms of copies per forward), so the
-        # full forward is 59.9 ms against 53.2 ms; needs a strided-batched GEMM with a zero weight stride.
+        # Stride-1 1x1 convolutions that are NOT part of a fused conv + BatchNorm site (fuse_forward) through
+        # gpfq_conv1x1_f32 -- the tensor-core kernel without an epilogue (one strided-batched SGEMM on 7 x 7 planes);
+        # the Conv2d modules stay in place, only their ``forward`` is overridden on the instance while quantize_network()
+        # runs (forward_fusion.pointwise_convs_as_gemm).
         self.pointwise_gemm = pointwise_gemm
         self._fused = {}
         if fuse_forward:
