@@ -111,15 +111,22 @@ def launch(fn, *args):
                 device = a.device
             elif a.device != device:
                 raise ValueError(f"libgpfq_b200: tensors on different devices ({device} and {a.device}) in one call")
-            conv.append(ctypes.c_void_p(a.data_ptr()))
+            conv.append(a.data_ptr())
         elif a is None:
-            conv.append(ctypes.c_void_p(0))
+            conv.append(None)
         else:
             conv.append(a)
     if device is None:
         raise ValueError("libgpfq_b200: a launch needs at least one tensor argument")
-    with torch.cuda.device(device):
-        check(fn(*conv, stream_ptr(device)))
+    # the device guard costs several microseconds of host time per call (the calibration forward makes ~10^4 calls per
+    # step and is host-bound at small per-GPU batches): enter it only when the tensors are NOT on the current device
+    if device.index == torch.cuda.current_device():
+        rc = fn(*conv, torch.cuda.current_stream().cuda_stream)
+    else:
+        with torch.cuda.device(device):
+            rc = fn(*conv, torch.cuda.current_stream(device).cuda_stream)
+    if rc != 0:
+        check(rc)
 
 
 def ptr(t):

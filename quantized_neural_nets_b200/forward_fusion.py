@@ -38,13 +38,13 @@ class FusedBNAct(nn.Module):
 
     def _coefficients(self):
         bn = self.bn
-        tag = (bn.running_mean._version, bn.running_var._version, bn.running_mean.data_ptr(), bn.eps,
-               None if bn.weight is None else (bn.weight._version, bn.weight.data_ptr()),
-               None if bn.bias is None else (bn.bias._version, bn.bias.data_ptr()))
+        w, b = bn.weight, bn.bias
+        tag = (bn.running_mean._version, bn.running_var._version, bn.eps, None if w is None else w._version,
+               None if b is None else b._version, bn.running_mean.device)
         if self._coeff is None or self._coeff[2] != tag:
             invstd = 1.0 / torch.sqrt(bn.running_var + bn.eps)
-            alpha = invstd if bn.weight is None else invstd * bn.weight.data
-            beta = -bn.running_mean * alpha if bn.bias is None else bn.bias.data - bn.running_mean * alpha
+            alpha = invstd if w is None else invstd * w.data
+            beta = -bn.running_mean * alpha if b is None else b.data - bn.running_mean * alpha
             self._coeff = (alpha.float().contiguous(), beta.float().contiguous(), tag)
         return self._coeff[0], self._coeff[1]
 
@@ -71,9 +71,19 @@ def _is_pointwise(mod):
             and mod.dilation == (1, 1) and mod.groups == 1 and mod.padding_mode == 'zeros')
 
 
+_TINY_WS = {}      # device -> 256-byte workspace (the kernel needs a real one only when the weight's row pitch is padded)
+
+
 def _conv_workspace(conv, device):
+    """Workspace of gpfq_conv1x1_bn_act_f32 (== gpfq_conv1x1_workspace_bytes(N, C*kh*kw), computed here: this runs ~10^4
+    times per step and a ctypes round trip plus an allocation per call is host time the small-batch forward does not have)."""
     k = conv.in_channels // conv.groups * conv.kernel_size[0] * conv.kernel_size[1]
-    return torch.empty(lib.gpfq_conv1x1_workspace_bytes(conv.out_channels, k), dtype=torch.uint8, device=device)
+    if k % 4 == 0:
+        ws = _TINY_WS.get(device)
+        if ws is None:
+            ws = _TINY_WS[device] = torch.empty(256, dtype=torch.uint8, device=device)
+        return ws
+    return torch.empty(conv.out_channels * ((k + 3) // 4 * 4) * 4 + 256, dtype=torch.uint8, device=device)
 
 
 def _tc_route(conv):
