@@ -69,8 +69,7 @@ int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, c
  *     it to gpfq_conv1x1_bn_act_f32 (x_ld = ld, C = C*kh*kw, HW = Ho*Wo) evaluates ANY convolution on the tensor
  *     cores; a 1x1 kernel with stride 2 is a strided gather, with stride 1 a copy that pads the row pitch to a
  *     multiple of 4 (7 x 7 planes).
- *   gpfq_conv1x1_f32: the plain stride-1 1x1 convolution; the same kernel when HW % 4 == 0 and a workspace is given, else
- *     ONE cublasSgemmStridedBatched with a zero batch stride for W (fp32 SIMT SGEMM, default math mode: no TF32). */
+ *   gpfq_conv1x1_f32: the plain stride-1 1x1 convolution of a contiguous tensor (HW % 4 == 0) through the same kernel. */
 size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C);
 int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW, int64_t x_ld);
 int gpfq_conv1x1_bn_act_f32(const float* x, int64_t x_ld, const float* W, const float* residual, const float* alpha,

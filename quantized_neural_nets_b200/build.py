@@ -10,9 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgpfq_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-# cuBLAS for the one plain library GEMM of the calibration forward (csrc/gpfq_conv1x1.cu); at run time the SONAME
-# resolves to the libcublas that torch has already loaded, the toolkit's copy is the fallback
-LINK_FLAGS = ["-lcublas", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+LINK_FLAGS = []      # no library dependencies besides the CUDA runtime (round 1 linked cuBLAS for one SGEMM call)
 
 
 def sources():

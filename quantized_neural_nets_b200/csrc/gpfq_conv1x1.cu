@@ -1,38 +1,16 @@
-// C ABI of the stride-1 1x1 convolution (calibration-forward helper): the tcgen05 split-TF32 kernel of
-// gpfq_conv1x1_tc.cu wherever it applies (HW % 4 == 0), and for the remaining shapes (the 7 x 7 planes of ResNet's last
-// stage) ONE strided-batched library SGEMM:
+// C ABI of the convolutions of the calibration forward: the tcgen05 split-TF32 kernel of gpfq_conv1x1_tc.cu and the
+// patch-matrix kernel that turns strided / k x k convolutions (and planes whose pixel pitch TMA cannot address) into its
+// input.  No library GEMM: round 1's cuBLAS call is gone.
 //
 // out[b] (N x HW) = W (N x C) @ x[b] (C x HW) for every image b.  PyTorch reaches cuBLAS for this product only through
 // torch.bmm, which first materialises the batch-broadcast weight (256 copies of W; measured 17 ms of copy kernels per
 // ResNet-50 forward); cublasSgemmStridedBatched takes the weight with a batch stride of ZERO.  Plain fp32 SIMT SGEMM
 // (no TF32): cuBLAS is used here as a library GEMM, nothing else.
-#include <cublas_v2.h>
 #include <math.h>
 
 #include <algorithm>
-#include <map>
-#include <mutex>
 
 #include "gpfq_common.cuh"
-
-namespace gpfq {
-
-static cublasHandle_t handle_for_current_device() {
-    static std::mutex mu;
-    static std::map<int, cublasHandle_t> handles;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = handles.find(dev);
-    if (it != handles.end()) return it->second;
-    cublasHandle_t h = nullptr;
-    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return nullptr;
-    // CUBLAS_DEFAULT_MATH: fp32 SGEMM keeps fp32 operands (TF32 needs CUBLAS_TF32_TENSOR_OP_MATH, never set here)
-    handles[dev] = h;
-    return h;
-}
-
-}  // namespace gpfq
 
 namespace gpfq {
 size_t conv1x1_tc_workspace_bytes(int N, int C);
@@ -77,20 +55,6 @@ conv_patches_kernel(const float* __restrict__ in, int C, int H, int W, int kh, i
 }  // namespace gpfq
 
 using namespace gpfq;
-
-static int conv1x1_cublas(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
-                          void* stream) {
-    cublasHandle_t h = handle_for_current_device();
-    GPFQ_REQUIRE(h != nullptr, "gpfq_conv1x1_f32: cublasCreate failed");
-    GPFQ_REQUIRE(cublasSetStream(h, (cudaStream_t)stream) == CUBLAS_STATUS_SUCCESS, "gpfq_conv1x1_f32: cublasSetStream failed");
-    // row-major out[b] (N x HW) = W (N x C) x[b] (C x HW)  <=>  column-major out[b]^T (HW x N) = x[b]^T (HW x C) W^T (C x N)
-    const float one = 1.f, zero = 0.f;
-    const cublasStatus_t st = cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, HW, N, C, &one, x, HW, (long long)C * HW,
-                                                        W, C, 0LL, &zero, out, HW, (long long)N * HW, B);
-    GPFQ_REQUIRE(st == CUBLAS_STATUS_SUCCESS, "gpfq_conv1x1_f32: cublasSgemmStridedBatched failed with status %d", (int)st);
-    count_launch();
-    return 0;
-}
 
 extern "C" size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C) {
     if (N < 1 || C < 1) return 0;
@@ -137,11 +101,11 @@ extern "C" int gpfq_conv1x1_bn_act_f32(const float* x, int64_t x_ld, const float
 extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
                                 void* workspace, size_t workspace_bytes, void* stream) {
     GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && HW >= 1, "gpfq_conv1x1_f32: bad shape");
-    GPFQ_REQUIRE(x && W && out, "gpfq_conv1x1_f32: null pointer");
+    GPFQ_REQUIRE(x && W && out && workspace, "gpfq_conv1x1_f32: null pointer");
+    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW, HW),
+                 "gpfq_conv1x1_f32: HW = %d is not a multiple of 4: pad the pixel pitch with gpfq_conv_patches_f32 (1x1 window, "
+                 "stride 1) and call gpfq_conv1x1_bn_act_f32 with x_ld", HW);
     if (B == 0) return 0;
-    static const bool force_cublas = getenv("GPFQ_CONV1X1_CUBLAS") && atoi(getenv("GPFQ_CONV1X1_CUBLAS")) == 1;
-    if (!force_cublas && workspace != nullptr && conv1x1_tc_supported(C, N, HW, HW))
-        return conv1x1_tc(x, HW, W, out, nullptr, nullptr, nullptr, -INFINITY, INFINITY, B, C, N, HW, workspace,
-                          workspace_bytes, (cudaStream_t)stream);
-    return conv1x1_cublas(x, W, out, B, C, N, HW, stream);       // 7 x 7 planes (HW % 4 != 0): plain library SGEMM
+    return conv1x1_tc(x, HW, W, out, nullptr, nullptr, nullptr, -INFINITY, INFINITY, B, C, N, HW, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
 }

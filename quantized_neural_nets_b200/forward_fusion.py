@@ -274,23 +274,28 @@ def fuse_inference_forward(network, fuse_pointwise=True):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# 1x1 convolutions as library GEMMs (QuantizeNeuralNet(pointwise_gemm=True)).
-# In ResNet-50 at bs=256 the stride-1 1x1 convolutions are 27 ms of the 61 ms forward through cuDNN's fp32
-# implicit-GEMM kernels (28-35 TFLOP/s); the same products as a batched cuBLAS SGEMM out[b] = W (N x C) @ x[b]
-# (C x HW) take 20 ms (40-53 TFLOP/s, bit-identical results on every ResNet-50 shape, tools/conv1x1_probe.py).
-# torch.matmul / torch.bmm cannot be used for it: they materialise the batch-broadcast weight first (66 copy kernels,
-# 17 ms per forward: tools/forward_probe2.py measured 59.9 ms against 53.2 ms), so the product goes through
-# gpfq_conv1x1_f32 = one cublasSgemmStridedBatched with a ZERO batch stride for W.
+# 1x1 convolutions outside a fused site (QuantizeNeuralNet(pointwise_gemm=True)).
+# Stride-1 1x1 convolutions that are not followed by a BatchNorm2d (so no FusedConvBNAct site), or whose site fell back to
+# the plain modules because of a hook, still go through the tensor-core kernel, without an epilogue (round 1 used one
+# strided-batched cuBLAS SGEMM here; cuDNN's fp32 implicit-GEMM kernels reach 28-35 TFLOP/s on these shapes).
 # The Conv2d MODULES stay in place -- only their ``forward`` is overridden, on the instance, for the duration of
 # quantize_network() -- so forward hooks, pre-hooks and weight updates behave as before.
 def _pointwise_forward(mod, x):
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and mod.bias is None
-            and mod.weight.is_contiguous()):
+            and mod.weight.is_contiguous() and x.shape[0] > 0):
         return nn.Conv2d.forward(mod, x)
     B, C, H, W = x.shape
+    HW = H * W
     out = torch.empty((B, mod.out_channels, H, W), dtype=torch.float32, device=x.device)
     ws = _conv_workspace(mod, x.device)
-    launch(lib.gpfq_conv1x1_f32, x, mod.weight, out, B, C, mod.out_channels, H * W, ws, ws.numel())
+    if HW % 4 == 0:
+        launch(lib.gpfq_conv1x1_f32, x, mod.weight, out, B, C, mod.out_channels, HW, ws, ws.numel())
+    else:                       # 7 x 7 planes: a copy with the pixel pitch padded to a multiple of 4 floats
+        ld = (HW + 3) // 4 * 4
+        xp = torch.empty((B, C, ld), dtype=torch.float32, device=x.device)
+        launch(lib.gpfq_conv_patches_f32, x, B, C, H, W, 1, 1, 1, 1, 0, 0, 1, 1, xp, ld)
+        launch(lib.gpfq_conv1x1_bn_act_f32, xp, ld, mod.weight, None, None, None, out, B, C, mod.out_channels, HW, -_INF, _INF,
+               ws, ws.numel())
     return out
 
 
