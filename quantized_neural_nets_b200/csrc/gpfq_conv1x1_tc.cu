@@ -186,16 +186,21 @@ struct ConvArgs {
     int C, N, HW, B;
     int n_tiles, p_tiles, total_tiles;
     int prefetch_residual;   // tmRes is valid
+    // k x k stride-1 "same" convolution as an implicit GEMM: taps = kh * kw k-block groups, tap (ki, kj) reads the
+    // activation shifted by (ki - pad_h) rows and (kj - pad_w) columns.  1x1: taps = kw = 1, pads 0.
+    int taps, kw, img_w, pad_h, pad_w, cblocks;
 };
 
-// copy of the (N x C) weight with its rows padded with zeros to Cp columns (only when C % 4 != 0: TMA needs row pitches
-// that are multiples of 16 bytes)
-__global__ void pad_weight_kernel(const float* __restrict__ W, int N, int C, int Cp, float* __restrict__ out) {
-    const int64_t n = (int64_t)N * Cp;
+// Weight (N, C, taps) -> out[tap][n][c], rows padded with zeros to Cp columns: one K-major (N x Cp) slab per tap.  Needed
+// when taps > 1 (the taps of a k x k kernel are interleaved in memory) or C % 4 != 0 (TMA needs row pitches that are
+// multiples of 16 bytes); a 1x1 weight with C % 4 == 0 is used in place.
+__global__ void arrange_weight_kernel(const float* __restrict__ W, int N, int C, int taps, int Cp, float* __restrict__ out) {
+    const int64_t n = (int64_t)taps * N * Cp;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / Cp;
         const int c = (int)(e % Cp);
-        out[e] = c < C ? W[r * C + c] : 0.f;
+        const int64_t rn = e / Cp;
+        const int nn = (int)(rn % N), tap = (int)(rn / N);
+        out[e] = c < C ? W[((int64_t)nn * C + c) * taps + tap] : 0.f;
     }
 }
 
@@ -216,7 +221,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccs);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = (a.C + kBK - 1) / kBK;
+    const int nkb = a.taps * a.cblocks;             // k-blocks per tile: (tap, 32-channel block)
     const int my_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
@@ -262,11 +267,16 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
                     float* st = tiles + (size_t)s * kStageFloats;
                     mbar_expect_tx(&full[s], (uint32_t)((kATile + kBTile) * sizeof(float)));
-                    const int c0 = kb * kBK;
-                    tma_load_2d(st, &tmW, c0, n0, &full[s]);
+                    const int tap = kb / a.cblocks;
+                    const int c0 = (kb - tap * a.cblocks) * kBK;
+                    // the tap's activation is the flattened image shifted by whole rows and columns: rows above / below
+                    // the image are TMA's out-of-bounds zeros, columns that would wrap into the neighbouring row are
+                    // zeroed by the split warps
+                    const int shift = (tap / a.kw - a.pad_h) * a.img_w + (tap % a.kw - a.pad_w);
+                    tma_load_3d(st, &tmW, c0, n0, tap, &full[s]);
 #pragma unroll
                     for (int j = 0; j < kTN / kPx; ++j)
-                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx, c0, img, &full[s]);
+                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx + shift, c0, img, &full[s]);
                 }
             }
         }
@@ -312,9 +322,26 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // nearest at 11 significant bits -- exactly representable in TF32 -- and lo = x - hi is exact; the tensor core
         // reads the leading 11 bits of lo (|lo| <= 2^-11 |x|, so what it drops is below 2^-21 |x|, of either sign).
         const int t = threadIdx.x - kFirstSplitWarp * 32;        // 0 .. 32 * kSplitWarps - 1
-        const int total = my_tiles * nkb;
-        for (int it = 0; it < total; ++it) {
+        constexpr int kSlots = kBTile / 4 / (32 * kSplitWarps);  // float4 slots of the activation tile per thread (16)
+        int it = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+          // column (x coordinate in the image) of the first pixel of each of this thread's float4 slots: slot i is float4
+          // t + 128 i of the tile = box i / 2, channel row (t >> 3) + 16 (i & 1), physical 16-byte unit t & 7 of the
+          // 128-byte row, whose 32-byte chunks SWIZZLE_128B_ATOM_32B permutes by (row & 3)
+          int xq[kSlots];
+          if (a.kw > 1) {
+              int img, p0, n0;
+              tile_coords(ti, img, p0, n0);
+#pragma unroll
+              for (int i = 0; i < kSlots; ++i) {
+                  const int r = (t >> 3) + 16 * (i & 1);
+                  const int lp = 32 * (i >> 1) + 8 * (((t & 7) >> 1) ^ (r & 3)) + 4 * (t & 1);
+                  xq[i] = (p0 + lp) % a.img_w;
+              }
+          }
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % kStages;
+            const int dx = (kb / a.cblocks) % a.kw - a.pad_w;       // this tap's column shift
             mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
             // the weight tile first (half the size), then the activation tile; both arrive RAW from TMA
             float4* whi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats);
@@ -332,9 +359,18 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
             float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats + 2 * kATile);
             float4* lo = hi + kBTile / 4;
-#pragma unroll 8
-            for (int i = 0; i < kBTile / 4 / (32 * kSplitWarps); ++i) {
-                const float4 v = hi[t + 32 * kSplitWarps * i];
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                float4 v = hi[t + 32 * kSplitWarps * i];
+                if (dx != 0) {                     // pixels whose shifted column leaves the image row are padding zeros
+                    int x0 = xq[i] + dx, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;      // a float4 may straddle a row end
+                    const int w = a.img_w;
+                    x1 -= (x1 - dx >= w) ? w : 0; x2 -= (x2 - dx >= w) ? w : 0; x3 -= (x3 - dx >= w) ? w : 0;
+                    v.x = (unsigned)x0 < (unsigned)w ? v.x : 0.f;
+                    v.y = (unsigned)x1 < (unsigned)w ? v.y : 0.f;
+                    v.z = (unsigned)x2 < (unsigned)w ? v.z : 0.f;
+                    v.w = (unsigned)x3 < (unsigned)w ? v.w : 0.f;
+                }
                 float4 h, l;
                 veltkamp_split(v.x, h.x, l.x);
                 veltkamp_split(v.y, h.y, l.y);
@@ -346,6 +382,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
+          }
         }
     } else if (warp >= kFirstDrainWarp) {
         // drain warps: warp (quad, half) owns TMEM lanes 32*quad .. +31 (a warp may only touch the lane quarter given by
@@ -516,39 +553,48 @@ int sm_count() {
 
 }  // namespace
 
-// only a zero-padded copy of W when its row pitch is not a multiple of 16 bytes
-size_t conv1x1_tc_workspace_bytes(int N, int C) { return (C % 4 == 0 ? 0 : (size_t)N * round_up(C, 4) * sizeof(float)) + 256; }
+// the re-arranged copy of W (see arrange_weight_kernel); nothing for a 1x1 weight with C % 4 == 0
+size_t conv1x1_tc_workspace_bytes(int N, int C, int taps) {
+    return ((taps == 1 && C % 4 == 0) ? 0 : (size_t)taps * N * round_up(C, 4) * sizeof(float)) + 256;
+}
 
 // x is read through TMA: its pixel pitch x_ld (floats between consecutive channels) must be a multiple of 4
 bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld) { return C >= 1 && N >= 1 && HW >= 1 && x_ld >= HW && x_ld % 4 == 0; }
 
+// kh x kw taps with padding (pad_h, pad_w), stride 1, on images img_w pixels wide: the output has the input's H x W
+// (2 * pad = k - 1); kh = kw = 1, pads 0 is the 1x1 convolution (img_w is then irrelevant).
 int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
                const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
-               cudaStream_t stream) {
+               cudaStream_t stream, int kh, int kw, int img_w, int pad_h, int pad_w) {
     GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW, x_ld), "conv1x1_tc: unsupported shape");
-    GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C), "conv1x1_tc: workspace too small");
+    const int taps = kh * kw;
+    GPFQ_REQUIRE(kh >= 1 && kw >= 1 && taps <= 121 && 2 * pad_h == kh - 1 && 2 * pad_w == kw - 1 &&
+                     (taps == 1 || (img_w >= 1 && HW % img_w == 0)),
+                 "conv1x1_tc: the implicit-GEMM path needs an odd kernel with 'same' padding");
+    GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C, taps), "conv1x1_tc: workspace too small");
     GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
                      ((uintptr_t)residual & 15) == 0,
                  "conv1x1_tc: workspace must be 256-byte aligned, tensors 16-byte aligned");
     GPFQ_REQUIRE((const void*)x != (const void*)out && (const void*)residual != (const void*)out, "conv1x1_tc: out must not alias an input");
     const float* w_src = W;
     int64_t w_ld = C;
-    if (C % 4 != 0) {
+    if (taps > 1 || C % 4 != 0) {
         w_ld = round_up(C, 4);
-        float* padded = (float*)workspace;
-        const int64_t n_w = (int64_t)N * w_ld;
-        pad_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, (int)w_ld, padded);
+        float* arranged = (float*)workspace;
+        const int64_t n_w = (int64_t)taps * N * w_ld;
+        arrange_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 8), 256, 0, stream>>>(W, N, C, taps, (int)w_ld,
+                                                                                                   arranged);
         GPFQ_CHECK_LAUNCH();
-        w_src = padded;
+        w_src = arranged;
     }
     GPFQ_REQUIRE(((uintptr_t)w_src & 15) == 0, "conv1x1_tc: W must be 16-byte aligned");
 
     CUtensorMap tmW, tmX, tmRes;
-    {   // the weight as it is (fp32, K-major): its TF32 planes are made in the kernel, one tile at a time
-        cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)N};
-        cuuint64_t strides[1] = {(cuuint64_t)w_ld * sizeof(float)};
-        cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTM};
-        if (int rc = make_map(&tmW, w_src, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    {   // the weight in fp32, one K-major (N x C) slab per tap: its TF32 planes are made in the kernel, a tile at a time
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)taps};
+        cuuint64_t strides[2] = {(cuuint64_t)w_ld * sizeof(float), (cuuint64_t)N * w_ld * sizeof(float)};
+        cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kTM, 1};
+        if (int rc = make_map(&tmW, w_src, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
@@ -564,6 +610,8 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     const int64_t total = (int64_t)a.n_tiles * a.p_tiles * B;
     GPFQ_REQUIRE(total < (1ll << 31), "conv1x1_tc: too many tiles");
     a.total_tiles = (int)total;
+    a.taps = taps; a.kw = kw; a.img_w = taps > 1 ? img_w : 1; a.pad_h = pad_h; a.pad_w = pad_w;
+    a.cblocks = (int)ceil_div(C, kBK);
     a.prefetch_residual = 0;
     tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
     if (residual != nullptr && HW % 4 == 0) {
@@ -583,7 +631,7 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     fn<<<grid, kThreads, kSmemBytes, stream>>>(tmW, tmX, tmRes, a);
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
-                         2.0 * B * (double)HW * C * N, 3);
+                         2.0 * B * (double)HW * C * N * taps, 3);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

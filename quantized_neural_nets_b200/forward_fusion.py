@@ -90,13 +90,19 @@ def _tc_route(conv):
     """How a Conv2d reaches the tensor-core kernel: 'direct' (stride-1 1x1: the activation is the B operand as it is),
     'patches' (gpfq_conv_patches_f32 writes the patch matrix first: 1x1 with a stride -- a strided gather -- and k x k
     kernels with stride >= 2, which cuDNN's fp32 kernels run at 25-35 TFLOP/s: ResNet's stem, its three stride-2 3x3
-    layers and its three stride-2 shortcuts), or None (grouped / depthwise, and stride-1 k x k layers, where cuDNN's
-    Winograd kernels beat a 9x larger patch matrix)."""
+    layers and its three stride-2 shortcuts), 'same' (stride-1 k x k layers with "same" padding as an implicit GEMM:
+    gpfq_conv_same_bn_act_f32 reads tap (ki, kj) as the flattened image shifted by whole rows and columns), or None
+    (grouped / depthwise and anything else: cuDNN)."""
     if type(conv) is not nn.Conv2d or conv.groups != 1 or conv.padding_mode != 'zeros' or isinstance(conv.padding, str):
         return None
     if conv.kernel_size == (1, 1):
         return 'direct' if conv.stride == (1, 1) and conv.padding == (0, 0) else 'patches'
-    return 'patches' if max(conv.stride) >= 2 else None
+    if max(conv.stride) >= 2:
+        return 'patches'
+    kh, kw = conv.kernel_size
+    if conv.dilation == (1, 1) and kh % 2 == 1 and kw % 2 == 1 and tuple(conv.padding) == (kh // 2, kw // 2):
+        return 'same'           # implicit GEMM: one shifted TMA load per tap, no patch matrix
+    return None
 
 
 class FusedConvBNAct(nn.Module):
@@ -137,6 +143,14 @@ class FusedConvBNAct(nn.Module):
         if conv.bias is not None:            # (W x + b) * alpha + beta  =  (W x) * alpha + (beta + alpha * b)
             beta = beta + alpha * conv.bias.data
         HW = Ho * Wo
+        if self.route == 'same':
+            if HW % 4 != 0 or (Ho, Wo) != (H, W):      # 7 x 7 planes: TMA cannot address the row pitch
+                return self.tail(conv(x), residual)
+            out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
+            ws = torch.empty(kh * kw * N * ((C + 3) // 4 * 4) * 4 + 256, dtype=torch.uint8, device=x.device)
+            launch(lib.gpfq_conv_same_bn_act_f32, x, conv.weight, residual, alpha, beta, out, B, C, N, H, W, kh, kw,
+                   self.tail.lo, self.tail.hi, ws, ws.numel())
+            return out
         if self.route == 'direct' and HW % 4 == 0:
             xin, x_ld, Ck = x, HW, C
         else:
