@@ -73,10 +73,12 @@ int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, c
 /*   gpfq_conv_same_bn_act_f32: a kh x kw convolution with stride 1 and "same" padding (odd kernel, pad = k / 2, dilation 1:
  *     ResNet's and VGG's 3x3 layers) through the SAME kernel as an implicit GEMM -- no patch matrix: tap (ki, kj) is the
  *     flattened image shifted by whole rows and columns (one TMA load; rows outside the image are TMA's out-of-bounds
- *     zeros, columns that would wrap into the neighbouring row are zeroed while the tile is split into its TF32 planes);
+ *     zeros, columns that would wrap into the neighbouring row are zeroed while the tile is split into its TF32 planes).
+ *     TMA boxes must start on 16-byte boundaries, so shifts that are not multiples of 4 pixels read from up to three
+ *     copies of the activation displaced by 1..3 pixels, written once per call into the workspace.
  *     W is the layer's (N, C, kh, kw) weight, x / out / residual contiguous (B, ., H, W) with H * W % 4 == 0.  Workspace:
- *     gpfq_conv_same_workspace_bytes(N, C, kh, kw) (the weight re-arranged into one K-major slab per tap). */
-size_t gpfq_conv_same_workspace_bytes(int32_t N, int32_t C, int32_t kh, int32_t kw);
+ *     gpfq_conv_same_workspace_bytes(N, C, kh, kw, B, H, W) (the weight as one K-major slab per tap + those copies). */
+size_t gpfq_conv_same_workspace_bytes(int32_t N, int32_t C, int32_t kh, int32_t kw, int32_t B, int32_t H, int32_t Wd);
 int gpfq_conv_same_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha, const float* beta,
                               float* out, int32_t B, int32_t C, int32_t N, int32_t H, int32_t Wd, int32_t kh, int32_t kw,
                               float lo, float hi, void* workspace, size_t workspace_bytes, void* stream);

@@ -14,6 +14,7 @@
 
 namespace gpfq {
 size_t conv1x1_tc_workspace_bytes(int N, int C, int taps = 1);
+size_t conv_same_workspace_bytes(int N, int C, int kh, int kw, int B, int H, int W);
 bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld);
 int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
                const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
@@ -65,9 +66,10 @@ extern "C" int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW
     return conv1x1_tc_supported(C, N, HW, x_ld) ? 1 : 0;
 }
 
-extern "C" size_t gpfq_conv_same_workspace_bytes(int32_t N, int32_t C, int32_t kh, int32_t kw) {
-    if (N < 1 || C < 1 || kh < 1 || kw < 1) return 0;
-    return conv1x1_tc_workspace_bytes(N, C, kh * kw);
+extern "C" size_t gpfq_conv_same_workspace_bytes(int32_t N, int32_t C, int32_t kh, int32_t kw, int32_t B, int32_t H,
+                                                 int32_t Wd) {
+    if (N < 1 || C < 1 || kh < 1 || kw < 1 || B < 0 || H < 1 || Wd < 1) return 0;
+    return conv_same_workspace_bytes(N, C, kh, kw, B, H, Wd);
 }
 
 extern "C" int gpfq_conv_same_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha,

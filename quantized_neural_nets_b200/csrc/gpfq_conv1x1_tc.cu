@@ -191,6 +191,29 @@ struct ConvArgs {
     int taps, kw, img_w, pad_h, pad_w, cblocks;
 };
 
+// copy_r[plane][p] = x[plane][p - r] for r = 1..3 (zero where p - r is outside [0, HW)), rows of ld = HW + 4 floats:
+// the displaced copies of the activation that make every tap's TMA box start on a 16-byte boundary.  `want` has bit r
+// set for the copies a layer needs (image widths that are multiples of 4 need r = 1 and 3 only).
+__global__ void __launch_bounds__(256)
+shift_copies_kernel(const float* __restrict__ x, int64_t planes, int HW, int ld, int want, float* __restrict__ c1,
+                    float* __restrict__ c2, float* __restrict__ c3) {
+    const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (p >= ld) return;
+    for (int64_t pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+        const float* src = x + pl * HW;
+        float v[7];                               // x[p - 3 .. p + 3]
+#pragma unroll
+        for (int e = 0; e < 7; ++e) {
+            const int q = p - 3 + e;
+            v[e] = (q >= 0 && q < HW) ? __ldg(src + q) : 0.f;
+        }
+        const int64_t o = pl * ld + p;
+        if (want & 2) *reinterpret_cast<float4*>(c1 + o) = make_float4(v[2], v[3], v[4], v[5]);
+        if (want & 4) *reinterpret_cast<float4*>(c2 + o) = make_float4(v[1], v[2], v[3], v[4]);
+        if (want & 8) *reinterpret_cast<float4*>(c3 + o) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 // Weight (N, C, taps) -> out[tap][n][c], rows padded with zeros to Cp columns: one K-major (N x Cp) slab per tap.  Needed
 // when taps > 1 (the taps of a k x k kernel are interleaved in memory) or C % 4 != 0 (TMA needs row pitches that are
 // multiples of 16 bytes); a 1x1 weight with C % 4 == 0 is used in place.
@@ -209,7 +232,8 @@ __global__ void arrange_weight_kernel(const float* __restrict__ W, int N, int C,
 template <bool AFFINE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                  const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
+                  const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                  const __grid_constant__ CUtensorMap tmX3, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     float* staging = tiles + (size_t)kStages * kStageFloats;
@@ -272,11 +296,17 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     // the tap's activation is the flattened image shifted by whole rows and columns: rows above / below
                     // the image are TMA's out-of-bounds zeros, columns that would wrap into the neighbouring row are
                     // zeroed by the split warps
+                    // A TMA box must start on a 16-byte boundary (measured: an inner coordinate that is not a multiple of 4
+                    // floats never completes), so a shift s is split into s = q - r with q a multiple of 4 and r in 0..3,
+                    // and the box is read at q from the copy of the activation that is displaced by r pixels
+                    // (copy_r[p] = x[p - r], written once per layer by shift_copies_kernel; r = 0 is x itself).
                     const int shift = (tap / a.kw - a.pad_h) * a.img_w + (tap % a.kw - a.pad_w);
+                    const int r = (-shift) & 3;
+                    const CUtensorMap* xm = r == 0 ? &tmX : r == 1 ? &tmX1 : r == 2 ? &tmX2 : &tmX3;
                     tma_load_3d(st, &tmW, c0, n0, tap, &full[s]);
 #pragma unroll
                     for (int j = 0; j < kTN / kPx; ++j)
-                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx + shift, c0, img, &full[s]);
+                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, xm, p0 + j * kPx + shift + r, c0, img, &full[s]);
                 }
             }
         }
@@ -554,8 +584,24 @@ int sm_count() {
 }  // namespace
 
 // the re-arranged copy of W (see arrange_weight_kernel); nothing for a 1x1 weight with C % 4 == 0
-size_t conv1x1_tc_workspace_bytes(int N, int C, int taps) {
-    return ((taps == 1 && C % 4 == 0) ? 0 : (size_t)taps * N * round_up(C, 4) * sizeof(float)) + 256;
+static size_t weight_bytes(int N, int C, int taps) {
+    const size_t b = (taps == 1 && C % 4 == 0) ? 0 : (size_t)taps * N * round_up(C, 4) * sizeof(float);
+    return (b + 255) & ~(size_t)255;
+}
+// bit r set: the copy displaced by r pixels is read by some tap of a kh x kw "same" convolution on images img_w wide
+static int copies_wanted(int kh, int kw, int img_w) {
+    int want = 0;
+    for (int ki = 0; ki < kh; ++ki)
+        for (int kj = 0; kj < kw; ++kj) want |= 1 << ((-((ki - kh / 2) * img_w + (kj - kw / 2))) & 3);
+    return want & ~1;
+}
+size_t conv1x1_tc_workspace_bytes(int N, int C, int taps) { return weight_bytes(N, C, taps) + 256; }
+// + the displaced copies of the activation ((B, C, HW + 4) each) for the implicit-GEMM path
+size_t conv_same_workspace_bytes(int N, int C, int kh, int kw, int B, int H, int W) {
+    const int want = copies_wanted(kh, kw, W);
+    const int n_copies = ((want >> 1) & 1) + ((want >> 2) & 1) + ((want >> 3) & 1);
+    const size_t copy = (((size_t)B * C * ((size_t)H * W + 4) * sizeof(float)) + 255) & ~(size_t)255;
+    return weight_bytes(N, C, kh * kw) + n_copies * copy + 256;
 }
 
 // x is read through TMA: its pixel pitch x_ld (floats between consecutive channels) must be a multiple of 4
@@ -571,7 +617,11 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     GPFQ_REQUIRE(kh >= 1 && kw >= 1 && taps <= 121 && 2 * pad_h == kh - 1 && 2 * pad_w == kw - 1 &&
                      (taps == 1 || (img_w >= 1 && HW % img_w == 0)),
                  "conv1x1_tc: the implicit-GEMM path needs an odd kernel with 'same' padding");
-    GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C, taps), "conv1x1_tc: workspace too small");
+    const int want = taps > 1 ? copies_wanted(kh, kw, img_w) : 0;
+    GPFQ_REQUIRE(workspace_bytes >= (taps > 1 ? conv_same_workspace_bytes(N, C, kh, kw, B, HW / std::max(img_w, 1), img_w)
+                                              : conv1x1_tc_workspace_bytes(N, C, taps)),
+                 "conv1x1_tc: workspace too small");
+    GPFQ_REQUIRE(taps == 1 || x_ld == HW, "conv1x1_tc: the implicit-GEMM path needs a contiguous activation");
     GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
                      ((uintptr_t)residual & 15) == 0,
                  "conv1x1_tc: workspace must be 256-byte aligned, tensors 16-byte aligned");
@@ -589,7 +639,7 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     }
     GPFQ_REQUIRE(((uintptr_t)w_src & 15) == 0, "conv1x1_tc: W must be 16-byte aligned");
 
-    CUtensorMap tmW, tmX, tmRes;
+    CUtensorMap tmW, tmX, tmXr[4], tmRes;
     {   // the weight in fp32, one K-major (N x C) slab per tap: its TF32 planes are made in the kernel, a tile at a time
         cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)taps};
         cuuint64_t strides[2] = {(cuuint64_t)w_ld * sizeof(float), (cuuint64_t)N * w_ld * sizeof(float)};
@@ -601,6 +651,25 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         cuuint64_t strides[2] = {(cuuint64_t)x_ld * sizeof(float), (cuuint64_t)C * x_ld * sizeof(float)};
         cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kBK, 1};
         if (int rc = make_map(&tmX, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+    }
+    for (int r = 1; r < 4; ++r) tmXr[r] = tmX;          // valid maps in any case; only the wanted ones are dereferenced
+    if (want) {
+        const int ld = HW + 4;
+        const size_t copy = (((size_t)B * C * ld * sizeof(float)) + 255) & ~(size_t)255;
+        unsigned char* base = (unsigned char*)workspace + weight_bytes(N, C, taps);
+        float* cp[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int r = 1; r < 4; ++r)
+            if (want & (1 << r)) {
+                cp[r] = (float*)base;
+                base += copy;
+                cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)C, (cuuint64_t)B};
+                cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)C * ld * sizeof(float)};
+                cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kBK, 1};
+                if (int rc = make_map(&tmXr[r], cp[r], 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+            }
+        dim3 grid((unsigned)ceil_div(ld, 1024), (unsigned)std::min<int64_t>((int64_t)B * C, 65535));
+        shift_copies_kernel<<<grid, 256, 0, stream>>>(x, (int64_t)B * C, HW, ld, want, cp[1], cp[2], cp[3]);
+        GPFQ_CHECK_LAUNCH();
     }
     ConvArgs a{};
     a.out = out; a.residual = residual; a.alpha = alpha; a.beta = beta; a.lo = lo; a.hi = hi;
@@ -621,14 +690,15 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
         a.prefetch_residual = 1;
     }
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const ConvArgs);
     static const KernelFn table[2][2] = {{conv1x1_tc_kernel<false, false>, conv1x1_tc_kernel<false, true>},
                                          {conv1x1_tc_kernel<true, false>, conv1x1_tc_kernel<true, true>}};
     const KernelFn fn = table[alpha != nullptr][residual != nullptr];
     if (int rc = ensure_dynamic_smem((const void*)fn, kSmemBytes)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
     profile_mark_begin(stream);
-    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmW, tmX, tmRes, a);
+    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmW, tmX, tmXr[1], tmXr[2], tmXr[3], tmRes, a);
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
                          2.0 * B * (double)HW * C * N * taps, 3);

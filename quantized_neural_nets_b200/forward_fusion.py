@@ -147,7 +147,7 @@ class FusedConvBNAct(nn.Module):
             if HW % 4 != 0 or (Ho, Wo) != (H, W):      # 7 x 7 planes: TMA cannot address the row pitch
                 return self.tail(conv(x), residual)
             out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
-            ws = torch.empty(kh * kw * N * ((C + 3) // 4 * 4) * 4 + 256, dtype=torch.uint8, device=x.device)
+            ws = torch.empty(lib.gpfq_conv_same_workspace_bytes(N, C, kh, kw, B, H, W), dtype=torch.uint8, device=x.device)
             launch(lib.gpfq_conv_same_bn_act_f32, x, conv.weight, residual, alpha, beta, out, B, C, N, H, W, kh, kw,
                    self.tail.lo, self.tail.hi, ws, ws.numel())
             return out

@@ -38,7 +38,7 @@ def same_probe():
         beta = torch.randn(c, device=dev, generator=g) * 0.1
         out = torch.empty(B, c, h, h, device=dev)
         tmp = torch.empty_like(out)
-        ws = torch.empty(lib.gpfq_conv_same_workspace_bytes(c, c, 3, 3), dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.gpfq_conv_same_workspace_bytes(c, c, 3, 3, B, h, h), dtype=torch.uint8, device=dev)
 
         def cudnn():
             y = F.conv2d(x, w, padding=1)
