@@ -70,18 +70,6 @@ int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, c
  *     cores; a 1x1 kernel with stride 2 is a strided gather, with stride 1 a copy that pads the row pitch to a
  *     multiple of 4 (7 x 7 planes).
  *   gpfq_conv1x1_f32: the plain stride-1 1x1 convolution of a contiguous tensor (HW % 4 == 0) through the same kernel. */
-/*   gpfq_conv_same_bn_act_f32: a kh x kw convolution with stride 1 and "same" padding (odd kernel, pad = k / 2, dilation 1:
- *     ResNet's and VGG's 3x3 layers) through the SAME kernel as an implicit GEMM -- no patch matrix: tap (ki, kj) is the
- *     flattened image shifted by whole rows and columns (one TMA load; rows outside the image are TMA's out-of-bounds
- *     zeros, columns that would wrap into the neighbouring row are zeroed while the tile is split into its TF32 planes).
- *     TMA boxes must start on 16-byte boundaries, so shifts that are not multiples of 4 pixels read from up to three
- *     copies of the activation displaced by 1..3 pixels, written once per call into the workspace.
- *     W is the layer's (N, C, kh, kw) weight, x / out / residual contiguous (B, ., H, W) with H * W % 4 == 0.  Workspace:
- *     gpfq_conv_same_workspace_bytes(N, C, kh, kw, B, H, W) (the weight as one K-major slab per tap + those copies). */
-size_t gpfq_conv_same_workspace_bytes(int32_t N, int32_t C, int32_t kh, int32_t kw, int32_t B, int32_t H, int32_t Wd);
-int gpfq_conv_same_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha, const float* beta,
-                              float* out, int32_t B, int32_t C, int32_t N, int32_t H, int32_t Wd, int32_t kh, int32_t kw,
-                              float lo, float hi, void* workspace, size_t workspace_bytes, void* stream);
 size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C);
 int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW, int64_t x_ld);
 int gpfq_conv1x1_bn_act_f32(const float* x, int64_t x_ld, const float* W, const float* residual, const float* alpha,

@@ -13,12 +13,11 @@
 #include "gpfq_common.cuh"
 
 namespace gpfq {
-size_t conv1x1_tc_workspace_bytes(int N, int C, int taps = 1);
-size_t conv_same_workspace_bytes(int N, int C, int kh, int kw, int B, int H, int W);
+size_t conv1x1_tc_workspace_bytes(int N, int C);
 bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld);
 int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
                const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
-               cudaStream_t stream, int kh = 1, int kw = 1, int img_w = 1, int pad_h = 0, int pad_w = 0);
+               cudaStream_t stream);
 
 // Patch matrix of a convolution with ITS OWN stride (not the stride = kernel unfold of the calibration capture):
 // out[b][(c, ki, kj)][yo * Wo + xo] = in[b][c][yo * sh - ph + ki * dh][xo * sw - pw + kj * dw] (0 outside the image),
@@ -64,26 +63,6 @@ extern "C" size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C) {
 
 extern "C" int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW, int64_t x_ld) {
     return conv1x1_tc_supported(C, N, HW, x_ld) ? 1 : 0;
-}
-
-extern "C" size_t gpfq_conv_same_workspace_bytes(int32_t N, int32_t C, int32_t kh, int32_t kw, int32_t B, int32_t H,
-                                                 int32_t Wd) {
-    if (N < 1 || C < 1 || kh < 1 || kw < 1 || B < 0 || H < 1 || Wd < 1) return 0;
-    return conv_same_workspace_bytes(N, C, kh, kw, B, H, Wd);
-}
-
-extern "C" int gpfq_conv_same_bn_act_f32(const float* x, const float* W, const float* residual, const float* alpha,
-                                         const float* beta, float* out, int32_t B, int32_t C, int32_t N, int32_t H,
-                                         int32_t Wd, int32_t kh, int32_t kw, float lo, float hi, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
-    GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && H >= 1 && Wd >= 1, "gpfq_conv_same_bn_act_f32: bad shape");
-    GPFQ_REQUIRE(kh >= 1 && kw >= 1 && (kh & 1) && (kw & 1), "gpfq_conv_same_bn_act_f32: odd kernel sizes only");
-    GPFQ_REQUIRE(x && W && out && workspace, "gpfq_conv_same_bn_act_f32: null pointer");
-    GPFQ_REQUIRE((alpha == nullptr) == (beta == nullptr), "gpfq_conv_same_bn_act_f32: alpha and beta go together");
-    GPFQ_REQUIRE(((int64_t)H * Wd) % 4 == 0, "gpfq_conv_same_bn_act_f32: H * W must be a multiple of 4 (TMA row pitch)");
-    if (B == 0) return 0;
-    return conv1x1_tc(x, (int64_t)H * Wd, W, out, residual, alpha, beta, lo, hi, B, C, N, H * Wd, workspace, workspace_bytes,
-                      (cudaStream_t)stream, kh, kw, Wd, kh / 2, kw / 2);
 }
 
 extern "C" int gpfq_conv_patches_f32(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,

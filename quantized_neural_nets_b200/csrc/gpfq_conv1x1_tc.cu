@@ -10,11 +10,11 @@
 // accumulator per 32-channel k-block that the epilogue warps add up in registers with round-to-nearest.
 //
 // Structure (one persistent CTA per SM, 512 threads, tiles of 128 output channels x 128 pixels of one image):
-//   warp 0      TMA producer: per k-block the RAW fp32 weight tile (box [128][32], SWIZZLE_128B, K-major) and the
+//   warp 0      TMA producer: per k-block the weight planes w_hi / w_lo (boxes [128][32], SWIZZLE_128B, K-major) and the
 //               RAW fp32 activation (four boxes [32 channels][32 pixels], SWIZZLE_128B_ATOM_32B: the B operand is
 //               MN-major -- the pixel index is the contiguous one in NCHW), 3-stage ring that runs on across tiles; one
 //               bulk L2 prefetch of the tile's residual when there is one;
-//   warps 4-7   split: turn the raw weight and activation tiles into their hi planes in place and the lo planes next to them (an
+//   warps 4-7   split: turn the raw activation tile into its hi plane in place and the lo plane next to it (an
 //               elementwise map, so the swizzled layout is untouched; Veltkamp's split on the FMA pipe, see below),
 //               fence.proxy.async, release the MMA warp -- the activation is read from HBM exactly once;
 //   warp 1      single-thread tcgen05.mma issue, 12 MMAs (M = N = 128, K = 8, kind::tf32) per k-block into one of FOUR
@@ -186,44 +186,19 @@ struct ConvArgs {
     int C, N, HW, B;
     int n_tiles, p_tiles, total_tiles;
     int prefetch_residual;   // tmRes is valid
-    // k x k stride-1 "same" convolution as an implicit GEMM: taps = kh * kw k-block groups, tap (ki, kj) reads the
-    // activation shifted by (ki - pad_h) rows and (kj - pad_w) columns.  1x1: taps = kw = 1, pads 0.
-    int taps, kw, img_w, pad_h, pad_w, cblocks;
 };
 
-// copy_r[plane][p] = x[plane][p - r] for r = 1..3 (zero where p - r is outside [0, HW)), rows of ld = HW + 4 floats:
-// the displaced copies of the activation that make every tap's TMA box start on a 16-byte boundary.  `want` has bit r
-// set for the copies a layer needs (image widths that are multiples of 4 need r = 1 and 3 only).
-__global__ void __launch_bounds__(256)
-shift_copies_kernel(const float* __restrict__ x, int64_t planes, int HW, int ld, int want, float* __restrict__ c1,
-                    float* __restrict__ c2, float* __restrict__ c3) {
-    const int p = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (p >= ld) return;
-    for (int64_t pl = blockIdx.y; pl < planes; pl += gridDim.y) {
-        const float* src = x + pl * HW;
-        float v[7];                               // x[p - 3 .. p + 3]
-#pragma unroll
-        for (int e = 0; e < 7; ++e) {
-            const int q = p - 3 + e;
-            v[e] = (q >= 0 && q < HW) ? __ldg(src + q) : 0.f;
-        }
-        const int64_t o = pl * ld + p;
-        if (want & 2) *reinterpret_cast<float4*>(c1 + o) = make_float4(v[2], v[3], v[4], v[5]);
-        if (want & 4) *reinterpret_cast<float4*>(c2 + o) = make_float4(v[1], v[2], v[3], v[4]);
-        if (want & 8) *reinterpret_cast<float4*>(c3 + o) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-}
-
-// Weight (N, C, taps) -> out[tap][n][c], rows padded with zeros to Cp columns: one K-major (N x Cp) slab per tap.  Needed
-// when taps > 1 (the taps of a k x k kernel are interleaved in memory) or C % 4 != 0 (TMA needs row pitches that are
-// multiples of 16 bytes); a 1x1 weight with C % 4 == 0 is used in place.
-__global__ void arrange_weight_kernel(const float* __restrict__ W, int N, int C, int taps, int Cp, float* __restrict__ out) {
-    const int64_t n = (int64_t)taps * N * Cp;
+// hi = rna_tf32(w), lo = rna_tf32(w - hi) of the (N x C) weight, rows padded with zeros to Cp columns
+__global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, int Cp, float* __restrict__ hi,
+                                    float* __restrict__ lo) {
+    const int64_t n = (int64_t)N * Cp;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / Cp;
         const int c = (int)(e % Cp);
-        const int64_t rn = e / Cp;
-        const int nn = (int)(rn % N), tap = (int)(rn / N);
-        out[e] = c < C ? W[((int64_t)nn * C + c) * taps + tap] : 0.f;
+        const float v = c < C ? W[r * C + c] : 0.f;
+        const float h = to_tf32(v);
+        hi[e] = h;
+        lo[e] = to_tf32(v - h);
     }
 }
 
@@ -231,9 +206,8 @@ __global__ void arrange_weight_kernel(const float* __restrict__ W, int N, int C,
 // SWIZZLE_128B_ATOM_32B; channels beyond C and pixels beyond HW arrive as zeros.
 template <bool AFFINE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
-conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
-                  const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
-                  const __grid_constant__ CUtensorMap tmX3, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
+conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     float* staging = tiles + (size_t)kStages * kStageFloats;
@@ -245,7 +219,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccs);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = a.taps * a.cblocks;             // k-blocks per tile: (tap, 32-channel block)
+    const int nkb = (a.C + kBK - 1) / kBK;
     const int my_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
@@ -290,23 +264,13 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                     const int s = it % kStages;
                     mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
                     float* st = tiles + (size_t)s * kStageFloats;
-                    mbar_expect_tx(&full[s], (uint32_t)((kATile + kBTile) * sizeof(float)));
-                    const int tap = kb / a.cblocks;
-                    const int c0 = (kb - tap * a.cblocks) * kBK;
-                    // the tap's activation is the flattened image shifted by whole rows and columns: rows above / below
-                    // the image are TMA's out-of-bounds zeros, columns that would wrap into the neighbouring row are
-                    // zeroed by the split warps
-                    // A TMA box must start on a 16-byte boundary (measured: an inner coordinate that is not a multiple of 4
-                    // floats never completes), so a shift s is split into s = q - r with q a multiple of 4 and r in 0..3,
-                    // and the box is read at q from the copy of the activation that is displaced by r pixels
-                    // (copy_r[p] = x[p - r], written once per layer by shift_copies_kernel; r = 0 is x itself).
-                    const int shift = (tap / a.kw - a.pad_h) * a.img_w + (tap % a.kw - a.pad_w);
-                    const int r = (-shift) & 3;
-                    const CUtensorMap* xm = r == 0 ? &tmX : r == 1 ? &tmX1 : r == 2 ? &tmX2 : &tmX3;
-                    tma_load_3d(st, &tmW, c0, n0, tap, &full[s]);
+                    mbar_expect_tx(&full[s], (uint32_t)((2 * kATile + kBTile) * sizeof(float)));
+                    const int c0 = kb * kBK;
+                    tma_load_2d(st, &tmWh, c0, n0, &full[s]);
+                    tma_load_2d(st + kATile, &tmWl, c0, n0, &full[s]);
 #pragma unroll
                     for (int j = 0; j < kTN / kPx; ++j)
-                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, xm, p0 + j * kPx + shift + r, c0, img, &full[s]);
+                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx, c0, img, &full[s]);
                 }
             }
         }
@@ -318,7 +282,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 const uint32_t ph = (uint32_t)((it / kStages) & 1);
                 const int b = it % kAccs;
                 mbar_wait(&acc_empty[b], (uint32_t)(((it / kAccs) & 1) ^ 1));
-                mbar_wait(&split[s], ph);      // both operands split into their hi / lo planes
+                mbar_wait(&full[s], ph);       // weight planes (TMA)
+                mbar_wait(&split[s], ph);      // activation planes (split warps)
                 tc_fence_after();
                 const float* st = tiles + (size_t)s * kStageFloats;
                 const uint64_t d_wh = desc_k_major(st), d_wl = desc_k_major(st + kATile);
@@ -352,55 +317,15 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         // nearest at 11 significant bits -- exactly representable in TF32 -- and lo = x - hi is exact; the tensor core
         // reads the leading 11 bits of lo (|lo| <= 2^-11 |x|, so what it drops is below 2^-21 |x|, of either sign).
         const int t = threadIdx.x - kFirstSplitWarp * 32;        // 0 .. 32 * kSplitWarps - 1
-        constexpr int kSlots = kBTile / 4 / (32 * kSplitWarps);  // float4 slots of the activation tile per thread (16)
-        int it = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-          // column (x coordinate in the image) of the first pixel of each of this thread's float4 slots: slot i is float4
-          // t + 128 i of the tile = box i / 2, channel row (t >> 3) + 16 (i & 1), physical 16-byte unit t & 7 of the
-          // 128-byte row, whose 32-byte chunks SWIZZLE_128B_ATOM_32B permutes by (row & 3)
-          int xq[kSlots];
-          if (a.kw > 1) {
-              int img, p0, n0;
-              tile_coords(ti, img, p0, n0);
-#pragma unroll
-              for (int i = 0; i < kSlots; ++i) {
-                  const int r = (t >> 3) + 16 * (i & 1);
-                  const int lp = 32 * (i >> 1) + 8 * (((t & 7) >> 1) ^ (r & 3)) + 4 * (t & 1);
-                  xq[i] = (p0 + lp) % a.img_w;
-              }
-          }
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int total = my_tiles * nkb;
+        for (int it = 0; it < total; ++it) {
             const int s = it % kStages;
-            const int dx = (kb / a.cblocks) % a.kw - a.pad_w;       // this tap's column shift
             mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
-            // the weight tile first (half the size), then the activation tile; both arrive RAW from TMA
-            float4* whi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats);
-            float4* wlo = whi + kATile / 4;
-#pragma unroll 8
-            for (int i = 0; i < kATile / 4 / (32 * kSplitWarps); ++i) {
-                const float4 v = whi[t + 32 * kSplitWarps * i];
-                float4 h, l;
-                veltkamp_split(v.x, h.x, l.x);
-                veltkamp_split(v.y, h.y, l.y);
-                veltkamp_split(v.z, h.z, l.z);
-                veltkamp_split(v.w, h.w, l.w);
-                whi[t + 32 * kSplitWarps * i] = h;
-                wlo[t + 32 * kSplitWarps * i] = l;
-            }
             float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats + 2 * kATile);
             float4* lo = hi + kBTile / 4;
-#pragma unroll
-            for (int i = 0; i < kSlots; ++i) {
-                float4 v = hi[t + 32 * kSplitWarps * i];
-                if (dx != 0) {                     // pixels whose shifted column leaves the image row are padding zeros
-                    int x0 = xq[i] + dx, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;      // a float4 may straddle a row end
-                    const int w = a.img_w;
-                    x1 -= (x1 - dx >= w) ? w : 0; x2 -= (x2 - dx >= w) ? w : 0; x3 -= (x3 - dx >= w) ? w : 0;
-                    v.x = (unsigned)x0 < (unsigned)w ? v.x : 0.f;
-                    v.y = (unsigned)x1 < (unsigned)w ? v.y : 0.f;
-                    v.z = (unsigned)x2 < (unsigned)w ? v.z : 0.f;
-                    v.w = (unsigned)x3 < (unsigned)w ? v.w : 0.f;
-                }
+#pragma unroll 8
+            for (int i = 0; i < kBTile / 4 / (32 * kSplitWarps); ++i) {
+                const float4 v = hi[t + 32 * kSplitWarps * i];
                 float4 h, l;
                 veltkamp_split(v.x, h.x, l.x);
                 veltkamp_split(v.y, h.y, l.y);
@@ -412,7 +337,6 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
-          }
         }
     } else if (warp >= kFirstDrainWarp) {
         // drain warps: warp (quad, half) owns TMEM lanes 32*quad .. +31 (a warp may only touch the lane quarter given by
@@ -583,93 +507,40 @@ int sm_count() {
 
 }  // namespace
 
-// the re-arranged copy of W (see arrange_weight_kernel); nothing for a 1x1 weight with C % 4 == 0
-static size_t weight_bytes(int N, int C, int taps) {
-    const size_t b = (taps == 1 && C % 4 == 0) ? 0 : (size_t)taps * N * round_up(C, 4) * sizeof(float);
-    return (b + 255) & ~(size_t)255;
-}
-// bit r set: the copy displaced by r pixels is read by some tap of a kh x kw "same" convolution on images img_w wide
-static int copies_wanted(int kh, int kw, int img_w) {
-    int want = 0;
-    for (int ki = 0; ki < kh; ++ki)
-        for (int kj = 0; kj < kw; ++kj) want |= 1 << ((-((ki - kh / 2) * img_w + (kj - kw / 2))) & 3);
-    return want & ~1;
-}
-size_t conv1x1_tc_workspace_bytes(int N, int C, int taps) { return weight_bytes(N, C, taps) + 256; }
-// + the displaced copies of the activation ((B, C, HW + 4) each) for the implicit-GEMM path
-size_t conv_same_workspace_bytes(int N, int C, int kh, int kw, int B, int H, int W) {
-    const int want = copies_wanted(kh, kw, W);
-    const int n_copies = ((want >> 1) & 1) + ((want >> 2) & 1) + ((want >> 3) & 1);
-    const size_t copy = (((size_t)B * C * ((size_t)H * W + 4) * sizeof(float)) + 255) & ~(size_t)255;
-    return weight_bytes(N, C, kh * kw) + n_copies * copy + 256;
-}
+size_t conv1x1_tc_workspace_bytes(int N, int C) { return (size_t)2 * N * round_up(C, kBK) * sizeof(float) + 256; }
 
 // x is read through TMA: its pixel pitch x_ld (floats between consecutive channels) must be a multiple of 4
 bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld) { return C >= 1 && N >= 1 && HW >= 1 && x_ld >= HW && x_ld % 4 == 0; }
 
-// kh x kw taps with padding (pad_h, pad_w), stride 1, on images img_w pixels wide: the output has the input's H x W
-// (2 * pad = k - 1); kh = kw = 1, pads 0 is the 1x1 convolution (img_w is then irrelevant).
 int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
                const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
-               cudaStream_t stream, int kh, int kw, int img_w, int pad_h, int pad_w) {
+               cudaStream_t stream) {
     GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW, x_ld), "conv1x1_tc: unsupported shape");
-    const int taps = kh * kw;
-    GPFQ_REQUIRE(kh >= 1 && kw >= 1 && taps <= 121 && 2 * pad_h == kh - 1 && 2 * pad_w == kw - 1 &&
-                     (taps == 1 || (img_w >= 1 && HW % img_w == 0)),
-                 "conv1x1_tc: the implicit-GEMM path needs an odd kernel with 'same' padding");
-    const int want = taps > 1 ? copies_wanted(kh, kw, img_w) : 0;
-    GPFQ_REQUIRE(workspace_bytes >= (taps > 1 ? conv_same_workspace_bytes(N, C, kh, kw, B, HW / std::max(img_w, 1), img_w)
-                                              : conv1x1_tc_workspace_bytes(N, C, taps)),
-                 "conv1x1_tc: workspace too small");
-    GPFQ_REQUIRE(taps == 1 || x_ld == HW, "conv1x1_tc: the implicit-GEMM path needs a contiguous activation");
+    GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C), "conv1x1_tc: workspace too small");
     GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
                      ((uintptr_t)residual & 15) == 0,
                  "conv1x1_tc: workspace must be 256-byte aligned, tensors 16-byte aligned");
     GPFQ_REQUIRE((const void*)x != (const void*)out && (const void*)residual != (const void*)out, "conv1x1_tc: out must not alias an input");
-    const float* w_src = W;
-    int64_t w_ld = C;
-    if (taps > 1 || C % 4 != 0) {
-        w_ld = round_up(C, 4);
-        float* arranged = (float*)workspace;
-        const int64_t n_w = (int64_t)taps * N * w_ld;
-        arrange_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 8), 256, 0, stream>>>(W, N, C, taps, (int)w_ld,
-                                                                                                   arranged);
-        GPFQ_CHECK_LAUNCH();
-        w_src = arranged;
-    }
-    GPFQ_REQUIRE(((uintptr_t)w_src & 15) == 0, "conv1x1_tc: W must be 16-byte aligned");
+    const int Cp = (int)round_up(C, kBK);
+    float* w_hi = (float*)workspace;
+    float* w_lo = w_hi + (size_t)N * Cp;
+    const int64_t n_w = (int64_t)N * Cp;
+    split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
+    GPFQ_CHECK_LAUNCH();
 
-    CUtensorMap tmW, tmX, tmXr[4], tmRes;
-    {   // the weight in fp32, one K-major (N x C) slab per tap: its TF32 planes are made in the kernel, a tile at a time
-        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)taps};
-        cuuint64_t strides[2] = {(cuuint64_t)w_ld * sizeof(float), (cuuint64_t)N * w_ld * sizeof(float)};
-        cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kTM, 1};
-        if (int rc = make_map(&tmW, w_src, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    CUtensorMap tmWh, tmWl, tmX, tmRes;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cp, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)Cp * sizeof(float)};
+        cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTM};
+        if (int rc = make_map(&tmWh, w_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        if (int rc = make_map(&tmWl, w_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
         cuuint64_t strides[2] = {(cuuint64_t)x_ld * sizeof(float), (cuuint64_t)C * x_ld * sizeof(float)};
         cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kBK, 1};
         if (int rc = make_map(&tmX, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-    }
-    for (int r = 1; r < 4; ++r) tmXr[r] = tmX;          // valid maps in any case; only the wanted ones are dereferenced
-    if (want) {
-        const int ld = HW + 4;
-        const size_t copy = (((size_t)B * C * ld * sizeof(float)) + 255) & ~(size_t)255;
-        unsigned char* base = (unsigned char*)workspace + weight_bytes(N, C, taps);
-        float* cp[4] = {nullptr, nullptr, nullptr, nullptr};
-        for (int r = 1; r < 4; ++r)
-            if (want & (1 << r)) {
-                cp[r] = (float*)base;
-                base += copy;
-                cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)C, (cuuint64_t)B};
-                cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)C * ld * sizeof(float)};
-                cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kBK, 1};
-                if (int rc = make_map(&tmXr[r], cp[r], 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-            }
-        dim3 grid((unsigned)ceil_div(ld, 1024), (unsigned)std::min<int64_t>((int64_t)B * C, 65535));
-        shift_copies_kernel<<<grid, 256, 0, stream>>>(x, (int64_t)B * C, HW, ld, want, cp[1], cp[2], cp[3]);
-        GPFQ_CHECK_LAUNCH();
     }
     ConvArgs a{};
     a.out = out; a.residual = residual; a.alpha = alpha; a.beta = beta; a.lo = lo; a.hi = hi;
@@ -679,8 +550,6 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     const int64_t total = (int64_t)a.n_tiles * a.p_tiles * B;
     GPFQ_REQUIRE(total < (1ll << 31), "conv1x1_tc: too many tiles");
     a.total_tiles = (int)total;
-    a.taps = taps; a.kw = kw; a.img_w = taps > 1 ? img_w : 1; a.pad_h = pad_h; a.pad_w = pad_w;
-    a.cblocks = (int)ceil_div(C, kBK);
     a.prefetch_residual = 0;
     tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
     if (residual != nullptr && HW % 4 == 0) {
@@ -690,18 +559,17 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
         a.prefetch_residual = 1;
     }
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
-                             const CUtensorMap, const ConvArgs);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
     static const KernelFn table[2][2] = {{conv1x1_tc_kernel<false, false>, conv1x1_tc_kernel<false, true>},
                                          {conv1x1_tc_kernel<true, false>, conv1x1_tc_kernel<true, true>}};
     const KernelFn fn = table[alpha != nullptr][residual != nullptr];
     if (int rc = ensure_dynamic_smem((const void*)fn, kSmemBytes)) return rc;
     const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
     profile_mark_begin(stream);
-    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmW, tmX, tmXr[1], tmXr[2], tmXr[3], tmRes, a);
+    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, tmRes, a);
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
-                         2.0 * B * (double)HW * C * N * taps, 3);
+                         2.0 * B * (double)HW * C * N, 3);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

@@ -71,38 +71,27 @@ def _is_pointwise(mod):
             and mod.dilation == (1, 1) and mod.groups == 1 and mod.padding_mode == 'zeros')
 
 
-_TINY_WS = {}      # device -> 256-byte workspace (the kernel needs a real one only when the weight's row pitch is padded)
-
-
 def _conv_workspace(conv, device):
-    """Workspace of gpfq_conv1x1_bn_act_f32 (== gpfq_conv1x1_workspace_bytes(N, C*kh*kw), computed here: this runs ~10^4
-    times per step and a ctypes round trip plus an allocation per call is host time the small-batch forward does not have)."""
+    """Workspace of gpfq_conv1x1_bn_act_f32: the TF32 hi / lo planes of the weight, rows padded to a multiple of 32
+    (== gpfq_conv1x1_workspace_bytes(N, C*kh*kw), computed here: this runs ~10^4 times per step and the small-batch
+    forward has no host time to spare for a ctypes round trip)."""
     k = conv.in_channels // conv.groups * conv.kernel_size[0] * conv.kernel_size[1]
-    if k % 4 == 0:
-        ws = _TINY_WS.get(device)
-        if ws is None:
-            ws = _TINY_WS[device] = torch.empty(256, dtype=torch.uint8, device=device)
-        return ws
-    return torch.empty(conv.out_channels * ((k + 3) // 4 * 4) * 4 + 256, dtype=torch.uint8, device=device)
+    return torch.empty(2 * conv.out_channels * ((k + 31) // 32 * 32) * 4 + 256, dtype=torch.uint8, device=device)
 
 
 def _tc_route(conv):
     """How a Conv2d reaches the tensor-core kernel: 'direct' (stride-1 1x1: the activation is the B operand as it is),
     'patches' (gpfq_conv_patches_f32 writes the patch matrix first: 1x1 with a stride -- a strided gather -- and k x k
     kernels with stride >= 2, which cuDNN's fp32 kernels run at 25-35 TFLOP/s: ResNet's stem, its three stride-2 3x3
-    layers and its three stride-2 shortcuts), 'same' (stride-1 k x k layers with "same" padding as an implicit GEMM:
-    gpfq_conv_same_bn_act_f32 reads tap (ki, kj) as the flattened image shifted by whole rows and columns), or None
-    (grouped / depthwise and anything else: cuDNN)."""
+    layers and its three stride-2 shortcuts), or None (grouped / depthwise, and stride-1 k x k layers: cuDNN's Winograd
+    kernels beat both a 9x larger patch matrix and an implicit-GEMM variant of this kernel that was built and measured
+    in round 2 -- shifted TMA loads per tap from 16-byte-displaced copies of the activation: 1.07 / 0.60 / 0.65 ms
+    against cuDNN + bn_act 0.68 / 0.49 / 0.46 ms on ResNet-50's 56 / 28 / 14 pixel 3x3 layers -- and removed again)."""
     if type(conv) is not nn.Conv2d or conv.groups != 1 or conv.padding_mode != 'zeros' or isinstance(conv.padding, str):
         return None
     if conv.kernel_size == (1, 1):
         return 'direct' if conv.stride == (1, 1) and conv.padding == (0, 0) else 'patches'
-    if max(conv.stride) >= 2:
-        return 'patches'
-    kh, kw = conv.kernel_size
-    if conv.dilation == (1, 1) and kh % 2 == 1 and kw % 2 == 1 and tuple(conv.padding) == (kh // 2, kw // 2):
-        return 'same'           # implicit GEMM: one shifted TMA load per tap, no patch matrix
-    return None
+    return 'patches' if max(conv.stride) >= 2 else None
 
 
 class FusedConvBNAct(nn.Module):
@@ -143,14 +132,6 @@ class FusedConvBNAct(nn.Module):
         if conv.bias is not None:            # (W x + b) * alpha + beta  =  (W x) * alpha + (beta + alpha * b)
             beta = beta + alpha * conv.bias.data
         HW = Ho * Wo
-        if self.route == 'same':
-            if HW % 4 != 0 or (Ho, Wo) != (H, W):      # 7 x 7 planes: TMA cannot address the row pitch
-                return self.tail(conv(x), residual)
-            out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
-            ws = torch.empty(lib.gpfq_conv_same_workspace_bytes(N, C, kh, kw, B, H, W), dtype=torch.uint8, device=x.device)
-            launch(lib.gpfq_conv_same_bn_act_f32, x, conv.weight, residual, alpha, beta, out, B, C, N, H, W, kh, kw,
-                   self.tail.lo, self.tail.hi, ws, ws.numel())
-            return out
         if self.route == 'direct' and HW % 4 == 0:
             xin, x_ld, Ck = x, HW, C
         else:

@@ -29,37 +29,8 @@ def t(fn, n=5):
 
 B = 256
 g = torch.Generator(device=dev).manual_seed(0)
-def same_probe():
-    """stride-1 3x3 layers: cuDNN (Winograd) + bn_act against the implicit-GEMM tensor-core path"""
-    for (c, h) in ((64, 56), (128, 28), (256, 14), (512, 14)):
-        x = torch.relu(torch.randn(B, c, h, h, device=dev, generator=g))
-        w = torch.randn(c, c, 3, 3, device=dev, generator=g) * 0.05
-        alpha = torch.rand(c, device=dev, generator=g) + 0.5
-        beta = torch.randn(c, device=dev, generator=g) * 0.1
-        out = torch.empty(B, c, h, h, device=dev)
-        tmp = torch.empty_like(out)
-        ws = torch.empty(lib.gpfq_conv_same_workspace_bytes(c, c, 3, 3, B, h, h), dtype=torch.uint8, device=dev)
-
-        def cudnn():
-            y = F.conv2d(x, w, padding=1)
-            launch(lib.gpfq_bn_act_f32, y, None, alpha, beta, tmp, B * c, c, h * h, 0.0, float("inf"))
-
-        def ours():
-            launch(lib.gpfq_conv_same_bn_act_f32, x, w, None, alpha, beta, out, B, c, c, h, h, 3, 3, 0.0, float("inf"), ws,
-                   ws.numel())
-
-        with torch.no_grad():
-            tc, to = t(cudnn), t(ours)
-            cudnn(); ours()
-            err = ((out - tmp).norm() / tmp.norm()).item()
-        fl = 2.0 * B * h * h * c * c * 9
-        print(f"3x3 s1 {c:4d}->{c:4d} @{h:3d}: cuDNN+bn_act {tc:.3f} ms | implicit GEMM {to:.3f} ms ({fl / to / 1e9:.0f} TF/s algorithmic)"
-              f"   rel diff {err:.1e}", flush=True)
-
-
 B = 256
 g = torch.Generator(device=dev).manual_seed(0)
-same_probe()
 for (cin, cout, h, k, s, p) in ((3, 64, 224, 7, 2, 3), (128, 128, 56, 3, 2, 1), (256, 512, 56, 1, 2, 0), (256, 256, 28, 3, 2, 1),
                                 (512, 1024, 28, 1, 2, 0), (512, 512, 14, 3, 2, 1), (1024, 2048, 14, 1, 2, 0),
                                 (512, 2048, 7, 1, 1, 0), (2048, 512, 7, 1, 1, 0)):
