@@ -162,6 +162,37 @@ __device__ __forceinline__ float min_nan(float a, float b) {
     asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
+// 2-D tiled TMA load delivered to the same shared-memory offset (and signalling the same-offset mbarrier) in every CTA
+// of the cluster whose bit is set in `mask`
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                      uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// arrive on the mbarrier at the same offset in another CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(dsmem_addr(bar, cta_rank)) : "memory");
+}
+// wait on a local mbarrier whose arrivals come from another CTA (cluster-scope acquire); bounded like mbar_wait
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (spins > (1u << 28)) __trap();
+    }
+}
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
@@ -184,7 +215,7 @@ struct ConvArgs {
     const float* beta;       // (N)
     float lo, hi;
     int C, N, HW, B;
-    int n_tiles, p_tiles, total_tiles;
+    int n_tiles, p_tiles, total_units;      // units = tiles, or pairs of tiles (PAIR)
     int prefetch_residual;   // tmRes is valid
 };
 
@@ -204,7 +235,14 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, i
 
 // tmWh / tmWl: (N x Cp) planes, box [128][32], SWIZZLE_128B.  tmX: RAW activation as (HW, C, B), box (32, 32, 1),
 // SWIZZLE_128B_ATOM_32B; channels beyond C and pixels beyond HW arrive as zeros.
-template <bool AFFINE, bool RES>
+//
+// PAIR: the kernel is launched as clusters of two CTAs that work on two activation tiles of the SAME channel tile in
+// lockstep and share the weight planes: each CTA fetches half of the 128 weight rows (boxes [64][32]) and TMA-multicasts
+// them into both CTAs' shared memory, so the weight costs a CTA 16 KB of L2 -> SM traffic per k-block instead of 32 KB
+// (the large-C layers run at the L2 roofline).  A stage may be refilled only when BOTH tensor cores are done with it:
+// after its own `empty` barrier a producer relays "my stage s is free" to its peer's `peer_free` barrier (remote
+// mbarrier arrive over DSMEM) and waits for the peer's relay.
+template <bool AFFINE, bool RES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
@@ -216,17 +254,24 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
     uint64_t* empty = split + kStages;
     uint64_t* acc_full = empty + kStages;
     uint64_t* acc_empty = acc_full + kAccs;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccs);
+    uint64_t* peer_free = acc_empty + kAccs;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_free + kStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (a.C + kBK - 1) / kBK;
-    const int my_tiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // work units: a tile (PAIR = false) or a pair of tiles with the same channel tile (PAIR = true), dealt out round
+    // robin to the CTAs / clusters
+    const int crank = PAIR ? (int)(blockIdx.x & 1) : 0;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int my_tiles = (a.total_units - worker + n_workers - 1) / n_workers;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&split[s], kSplitWarps);       // one arrival per split warp
             mbar_init(&empty[s], 1);
+            mbar_init(&peer_free[s], 1);
         }
         for (int b = 0; b < kAccs; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -237,15 +282,18 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
     if (warp == 1) tmem_alloc(tmem_slot, kAccs * kTN);
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile index -> (image, pixel tile, channel tile): channel tiles of one activation tile are adjacent in the
-    // schedule, so CTAs that run side by side share the activation tile through L2
+    // unit index -> (image, pixel tile, channel tile): channel tiles of one activation tile are adjacent in the
+    // schedule, so CTAs that run side by side share the activation tile through L2.  In a pair the two CTAs take
+    // consecutive (image, pixel tile) positions of the same channel tile; a position past the end is a dummy tile
+    // (img = B: every load is out of bounds = zeros, and the epilogue stores nothing).
     auto tile_coords = [&](int i, int& img, int& p0, int& n0) {
-        const int t = (int)blockIdx.x + i * (int)gridDim.x;
+        const int t = worker + i * n_workers;
         const int nt = t % a.n_tiles;
-        const int rest = t / a.n_tiles;
+        const int rest = (t / a.n_tiles) * (PAIR ? 2 : 1) + crank;
         n0 = nt * kTM;
         p0 = (rest % a.p_tiles) * kTN;
         img = rest / a.p_tiles;
@@ -259,15 +307,25 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 tile_coords(i, img, p0, n0);
                 // the residual tile is only needed by the epilogue, several microseconds from now: pull it into L2 with
                 // one bulk prefetch so that the epilogue's loads do not each pay an HBM round trip
-                if (a.prefetch_residual) tma_prefetch_3d(&tmRes, p0, n0, img);
+                if (a.prefetch_residual && img < a.B) tma_prefetch_3d(&tmRes, p0, n0, img);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
+                    if (PAIR) {            // my tensor core is done with stage s: tell the peer, wait for the peer's word
+                        mbar_arrive_remote(&peer_free[s], (uint32_t)(crank ^ 1));
+                        mbar_wait_cluster(&peer_free[s], (uint32_t)((it / kStages) & 1));
+                    }
                     float* st = tiles + (size_t)s * kStageFloats;
                     mbar_expect_tx(&full[s], (uint32_t)((2 * kATile + kBTile) * sizeof(float)));
                     const int c0 = kb * kBK;
-                    tma_load_2d(st, &tmWh, c0, n0, &full[s]);
-                    tma_load_2d(st + kATile, &tmWl, c0, n0, &full[s]);
+                    if (PAIR) {            // my half of the weight rows, into both CTAs' stage s
+                        const int half = crank * (kTM / 2);
+                        tma_load_2d_multicast(st + half * kBK, &tmWh, c0, n0 + half, &full[s], (uint16_t)3);
+                        tma_load_2d_multicast(st + kATile + half * kBK, &tmWl, c0, n0 + half, &full[s], (uint16_t)3);
+                    } else {
+                        tma_load_2d(st, &tmWh, c0, n0, &full[s]);
+                        tma_load_2d(st + kATile, &tmWl, c0, n0, &full[s]);
+                    }
 #pragma unroll
                     for (int j = 0; j < kTN / kPx; ++j)
                         tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx, c0, img, &full[s]);
@@ -394,7 +452,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             for (int k = 0; k < 4; ++k) {
                 al4[k] = __shfl_sync(0xffffffffu, al_mine, 8 * k + rq);
                 be4[k] = __shfl_sync(0xffffffffu, be_mine, 8 * k + rq);
-                rv[k] = n0 + quad * 32 + 8 * k + rq < a.N;
+                rv[k] = img < a.B && n0 + quad * 32 + 8 * k + rq < a.N;
             }
             const size_t row_base = ((size_t)img * a.N + n0 + quad * 32 + rq) * a.HW + pw0 + 4 * cq;
             const size_t kstride = (size_t)8 * a.HW;
@@ -448,7 +506,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                         float v = stg[r * kStgStride + c];
                         const float al = __shfl_sync(0xffffffffu, al_mine, r), be = __shfl_sync(0xffffffffu, be_mine, r);
                         const int n = n0 + quad * 32 + r, p = pw0 + c0 + c;
-                        if (n < a.N && p < a.HW) {
+                        if (img < a.B && n < a.N && p < a.HW) {
                             const size_t off = ((size_t)img * a.N + n) * a.HW + p;
                             if (AFFINE) v = __fadd_rn(__fmul_rn(v, al), be);
                             if (RES) v = __fadd_rn(v, __ldg(a.residual + off));
@@ -463,6 +521,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         }
     }
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kAccs * kTN);
@@ -528,11 +587,14 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
     GPFQ_CHECK_LAUNCH();
 
+    // pairs of CTAs sharing the weight planes through TMA multicast (see the kernel); GPFQ_CONV_PAIR=0 switches it off
+    static const bool pair_env = !(getenv("GPFQ_CONV_PAIR") && atoi(getenv("GPFQ_CONV_PAIR")) == 0);
+    const bool pair = pair_env && (int64_t)B * ceil_div(HW, kTN) >= 2;
     CUtensorMap tmWh, tmWl, tmX, tmRes;
     {
         cuuint64_t dims[2] = {(cuuint64_t)Cp, (cuuint64_t)N};
         cuuint64_t strides[1] = {(cuuint64_t)Cp * sizeof(float)};
-        cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kTM};
+        cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(pair ? kTM / 2 : kTM)};
         if (int rc = make_map(&tmWh, w_hi, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
         if (int rc = make_map(&tmWl, w_lo, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
     }
@@ -547,9 +609,10 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     a.C = C; a.N = N; a.HW = HW; a.B = B;
     a.n_tiles = (int)ceil_div(N, kTM);
     a.p_tiles = (int)ceil_div(HW, kTN);
-    const int64_t total = (int64_t)a.n_tiles * a.p_tiles * B;
-    GPFQ_REQUIRE(total < (1ll << 31), "conv1x1_tc: too many tiles");
-    a.total_tiles = (int)total;
+    const int64_t positions = (int64_t)a.p_tiles * B;                          // (image, pixel tile) positions per channel tile
+    const int64_t total = (int64_t)a.n_tiles * (pair ? ceil_div(positions, 2) : positions);
+    GPFQ_REQUIRE(total < (1ll << 30), "conv1x1_tc: too many tiles");
+    a.total_units = (int)total;
     a.prefetch_residual = 0;
     tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
     if (residual != nullptr && HW % 4 == 0) {
@@ -560,13 +623,40 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         a.prefetch_residual = 1;
     }
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
-    static const KernelFn table[2][2] = {{conv1x1_tc_kernel<false, false>, conv1x1_tc_kernel<false, true>},
-                                         {conv1x1_tc_kernel<true, false>, conv1x1_tc_kernel<true, true>}};
-    const KernelFn fn = table[alpha != nullptr][residual != nullptr];
+    static const KernelFn table[2][2][2] = {
+        {{conv1x1_tc_kernel<false, false, false>, conv1x1_tc_kernel<false, false, true>},
+         {conv1x1_tc_kernel<false, true, false>, conv1x1_tc_kernel<false, true, true>}},
+        {{conv1x1_tc_kernel<true, false, false>, conv1x1_tc_kernel<true, false, true>},
+         {conv1x1_tc_kernel<true, true, false>, conv1x1_tc_kernel<true, true, true>}}};
+    const KernelFn fn = table[alpha != nullptr][residual != nullptr][pair];
     if (int rc = ensure_dynamic_smem((const void*)fn, kSmemBytes)) return rc;
-    const unsigned grid = (unsigned)std::min<int64_t>(total, sm_count());
+    cudaLaunchConfig_t cfg{};
+    const int sms = sm_count();
+    cfg.gridDim = pair ? dim3(2 * (unsigned)std::min<int64_t>(total, sms / 2)) : dim3((unsigned)std::min<int64_t>(total, sms));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+    if (pair) {
+        // persistent clusters: never launch more than can be resident at once (a GPC with an odd number of free SMs
+        // leaves one out), or the last cluster would run after all the others
+        static int max_clusters[2][2] = {{0, 0}, {0, 0}};
+        int& mc = max_clusters[alpha != nullptr][residual != nullptr];
+        if (mc == 0) {
+            cudaLaunchConfig_t q = cfg;
+            q.gridDim = dim3(2 * (unsigned)(sms / 2));
+            if (cudaOccupancyMaxActiveClusters(&mc, fn, &q) != cudaSuccess || mc < 1) mc = sms / 2 - 2;
+        }
+        cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(total, mc));
+    }
     profile_mark_begin(stream);
-    fn<<<grid, kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, tmRes, a);
+    GPFQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, tmWh, tmWl, tmX, tmRes, a));
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
                          2.0 * B * (double)HW * C * N, 3);
