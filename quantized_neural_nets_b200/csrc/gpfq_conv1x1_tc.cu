@@ -587,8 +587,11 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
     GPFQ_CHECK_LAUNCH();
 
-    // pairs of CTAs sharing the weight planes through TMA multicast (see the kernel); GPFQ_CONV_PAIR=0 switches it off
-    static const bool pair_env = !(getenv("GPFQ_CONV_PAIR") && atoi(getenv("GPFQ_CONV_PAIR")) == 0);
+    // pairs of CTAs sharing the weight planes through TMA multicast (see the kernel): correct (the same tests pass), but
+    // measured SLOWER on every ResNet-50 shape (all 33 layers 8.24 -> 9.35 ms; 1024 -> 512 @ 14: 0.373 -> 0.472 ms): the
+    // 3-stage ring is bound by the latency of a stage's TMA -> split -> MMA -> free cycle, not by L2 bandwidth, and the
+    // cross-CTA hand-shake lengthens that cycle.  Opt-in with GPFQ_CONV_PAIR=1.
+    static const bool pair_env = getenv("GPFQ_CONV_PAIR") && atoi(getenv("GPFQ_CONV_PAIR")) == 1;
     const bool pair = pair_env && (int64_t)B * ceil_div(HW, kTN) >= 2;
     CUtensorMap tmWh, tmWl, tmX, tmRes;
     {
