@@ -448,3 +448,29 @@ def test_maxpool_kernel_matches_pytorch(shape, k, s, p):
     assert got.shape == want.shape
     assert torch.equal(torch.nan_to_num(got, nan=7.0), torch.nan_to_num(want, nan=7.0))
     assert torch.isnan(got).sum() == torch.isnan(want).sum() > 0
+
+
+@pytest.mark.parametrize("name,min_conv_sites", [("mobilenet_v2", 30), ("resnet18", 4), ("googlenet", 20)])
+def test_fused_forward_of_other_model_families(name, min_conv_sites):
+    """The fused calibration forward on the other families the reference's CLI whitelists: MobileNetV2 (1x1 layers with
+    C = 16 ... 960 -- channel tails of a k-block --, ReLU6 clamps, depthwise layers left to cuDNN), ResNet-18 (only the
+    stem and the shortcuts are 1x1 / strided), GoogLeNet (BasicConv2d: functional ReLU, eps = 1e-3)."""
+    from quantized_neural_nets_b200.forward_fusion import fuse_inference_forward
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    kw = dict(weights=None)
+    if name == "googlenet":
+        kw.update(aux_logits=False, init_weights=True)
+    model = getattr(torchvision.models, name)(**kw).eval().to(DEV)
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+    fused, sites = fuse_inference_forward(model)
+    assert fused.fused_conv_sites >= min_conv_sites, fused.fused_conv_sites
+    x = torch.randn(4, 3, 224, 224, device=DEV)
+    with torch.no_grad():
+        want, got = model(x), fused(x)
+    assert torch.isfinite(got).all()
+    assert (got - want).norm() <= 5e-5 * want.norm(), ((got - want).norm() / want.norm()).item()
