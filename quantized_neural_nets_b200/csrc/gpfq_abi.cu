@@ -207,10 +207,15 @@ __global__ void unpack_levels_kernel(const uint8_t* __restrict__ in, int64_t n, 
 // Calibration-forward helper: MaxPool2d (square window, padding with -inf, floor mode) of an NCHW tensor.  One thread per
 // output pixel, consecutive threads along the row; the k x k windows of neighbouring outputs overlap, so the input is
 // read from HBM once and re-read through L1.  NaN propagates as in PyTorch (a NaN in the window wins).
+// KT > 0 fixes the window at compile time: the KT*KT loads are issued unconditionally from clamped coordinates (taps in
+// the padding are replaced by -inf afterwards), so every thread has KT*KT loads in flight instead of one behind a branch
+// -- with one outstanding 128-byte request per warp the kernel sat at a quarter of the HBM rate.
+template <int KT>
 __global__ void __launch_bounds__(256)
-maxpool_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int k, int s, int p, int Ho, int Wo,
+maxpool_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int k_rt, int s, int p, int Ho, int Wo,
                float* __restrict__ out) {
     // blockIdx.y walks the planes, blockIdx.x / threadIdx.x the pixels of one plane: 32-bit index arithmetic only
+    const int k = KT > 0 ? KT : k_rt;
     const int HWo = Ho * Wo;
     for (int64_t pl = blockIdx.y; pl < planes; pl += gridDim.y) {
         const float* src = in + pl * (int64_t)H * W;
@@ -219,18 +224,84 @@ maxpool_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int k
             const int yo = e / Wo, xo = e - yo * Wo;
             const int y0 = yo * s - p, x0 = xo * s - p;
             float m = -INFINITY;
-            for (int i = 0; i < k; ++i) {
-                const int y = y0 + i;
-                if (y < 0 || y >= H) continue;
-                const float* row = src + y * W;
-                for (int j = 0; j < k; ++j) {
-                    const int x = x0 + j;
-                    if (x < 0 || x >= W) continue;
-                    const float v = __ldg(row + x);
-                    m = (v > m || v != v) ? v : m;
+            if (KT > 0) {
+                float v[KT > 0 ? KT * KT : 1];
+#pragma unroll
+                for (int i = 0; i < KT; ++i) {
+                    const int y = min(max(y0 + i, 0), H - 1);
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) v[i * KT + j] = __ldg(src + y * W + min(max(x0 + j, 0), W - 1));
+                }
+#pragma unroll
+                for (int i = 0; i < KT; ++i) {
+                    const bool row_in = (unsigned)(y0 + i) < (unsigned)H;
+#pragma unroll
+                    for (int j = 0; j < KT; ++j) {
+                        const float t = (row_in && (unsigned)(x0 + j) < (unsigned)W) ? v[i * KT + j] : -INFINITY;
+                        m = (t > m || t != t) ? t : m;
+                    }
+                }
+            } else {
+                for (int i = 0; i < k; ++i) {
+                    const int y = y0 + i;
+                    if (y < 0 || y >= H) continue;
+                    const float* row = src + y * W;
+                    for (int j = 0; j < k; ++j) {
+                        const int x = x0 + j;
+                        if (x < 0 || x >= W) continue;
+                        const float t = __ldg(row + x);
+                        m = (t > m || t != t) ? t : m;
+                    }
                 }
             }
             dst[e] = m;
+        }
+    }
+}
+
+// The ResNet / GoogLeNet stem pool (3 x 3 window, stride 2, padding 1) on planes whose width is a multiple of 4: the
+// one-output-per-thread kernel above issues 9 stride-2 scalar loads per output and is bound by L1 wavefronts (0.65 ms
+// for 256 x 64 x 112 x 112, a quarter of the HBM rate).  Here a thread produces TWO neighbouring outputs from one aligned
+// float4 per input row (columns 4j .. 4j+3) plus column 4j-1, which is the .w of the lane to its left (one shuffle;
+// lane 0 loads it): 3 LDG.128 per two outputs instead of 18 LDG.32, a float2 store.
+__global__ void __launch_bounds__(256)
+maxpool_3s2p1_kernel(const float* __restrict__ in, int64_t planes, int H, int W, int Ho, int Wo, float* __restrict__ out) {
+    const int pairs_per_row = Wo >> 1;               // Wo == W / 2 is even
+    const int pairs = Ho * pairs_per_row;
+    const int lane = threadIdx.x & 31;
+    for (int64_t pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+        const float* src = in + pl * (int64_t)H * W;
+        float* dst = out + pl * (int64_t)Ho * Wo;
+        // whole warps stay in the loop (the shuffle needs every lane); a lane past the end computes a clamped pair and skips the store
+        for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < pairs; base += gridDim.x * blockDim.x) {
+            const int e = min(base + lane, pairs - 1);
+            const int yo = e / pairs_per_row, j = e - yo * pairs_per_row;      // outputs (yo, 2j) and (yo, 2j+1)
+            const int y0 = 2 * yo - 1;
+            float4 v[3];
+            float left[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int y = min(max(y0 + i, 0), H - 1);
+                v[i] = __ldg(reinterpret_cast<const float4*>(src + y * W) + j);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                left[i] = __shfl_up_sync(0xffffffffu, v[i].w, 1);
+                if (lane == 0 && j > 0) left[i] = __ldg(src + min(max(y0 + i, 0), H - 1) * W + 4 * j - 1);
+            }
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                if ((unsigned)(y0 + i) >= (unsigned)H) continue;          // a padding row
+                const float l = j > 0 ? left[i] : -INFINITY;              // column -1 is padding
+                m0 = (l > m0 || l != l) ? l : m0;
+                m0 = (v[i].x > m0 || v[i].x != v[i].x) ? v[i].x : m0;
+                m0 = (v[i].y > m0 || v[i].y != v[i].y) ? v[i].y : m0;
+                m1 = (v[i].y > m1 || v[i].y != v[i].y) ? v[i].y : m1;
+                m1 = (v[i].z > m1 || v[i].z != v[i].z) ? v[i].z : m1;
+                m1 = (v[i].w > m1 || v[i].w != v[i].w) ? v[i].w : m1;
+            }
+            if (base + lane < pairs) *reinterpret_cast<float2*>(dst + yo * Wo + 2 * j) = make_float2(m0, m1);
         }
     }
 }
@@ -521,7 +592,15 @@ int gpfq_maxpool2d_f32(const float* in, int64_t planes, int32_t H, int32_t W, in
     if (planes == 0) return 0;
     GPFQ_REQUIRE((int64_t)H * W < (1ll << 31), "gpfq_maxpool2d_f32: plane too large");
     dim3 grid((unsigned)std::min<int64_t>(ceil_div((int64_t)Ho * Wo, 256), 64), (unsigned)std::min<int64_t>(planes, 65535));
-    maxpool_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, planes, H, W, k, stride, pad, Ho, Wo, out);
+    if (k == 3 && stride == 2 && pad == 1 && W % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0 && (H * W) % 4 == 0) {
+        // Wo = (W + 2 - 3) / 2 + 1 = W / 2, even; rows of both tensors stay 16 / 8-byte aligned
+        dim3 g2((unsigned)std::min<int64_t>(ceil_div((int64_t)Ho * (Wo / 2), 256), 64), grid.y);
+        maxpool_3s2p1_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(in, planes, H, W, Ho, Wo, out);
+        GPFQ_CHECK_LAUNCH();
+        return 0;
+    }
+    auto kernel = k == 3 ? maxpool_kernel<3> : k == 2 ? maxpool_kernel<2> : maxpool_kernel<0>;
+    kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, planes, H, W, k, stride, pad, Ho, Wo, out);
     GPFQ_CHECK_LAUNCH();
     return 0;
 }

@@ -217,7 +217,20 @@ struct ConvArgs {
     int C, N, HW, B;
     int n_tiles, p_tiles, total_units;      // units = tiles, or pairs of tiles (PAIR)
     int prefetch_residual;   // tmRes is valid
+    int experiment;          // only read under -DGPFQ_CONV_EXPERIMENT (timing experiments that give WRONG results)
 };
+
+// Timing experiments, compiled in only with -DGPFQ_CONV_EXPERIMENT and selected by the bit mask GPFQ_CONV_EXPERIMENT=<n>
+// in the environment; each one removes part of a stage's work to show which resource bounds the stage cycle (results
+// are wrong by construction):  1 = the split warps do not store the lo plane (-16 KB of shared-memory writes per
+// k-block), 2 = only the hi*hi products are issued (a third of the tensor work and of its operand reads), 4 = the drain
+// warps read half of their accumulator columns (half of the TMEM reads and fp32 adds), 8 = the split warps neither
+// load nor store (the stage goes from TMA straight to the tensor core).
+#ifdef GPFQ_CONV_EXPERIMENT
+#define CONV_EXPERIMENT(bit) ((a.experiment & (bit)) != 0)
+#else
+#define CONV_EXPERIMENT(bit) false
+#endif
 
 // hi = rna_tf32(w), lo = rna_tf32(w - hi) of the (N x C) weight, rows padded with zeros to Cp columns
 __global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, int Cp, float* __restrict__ hi,
@@ -351,18 +364,21 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 // the eight small products (lo*hi, hi*lo) first, the four hi*hi products last: the tensor core adds into
                 // the fp32 accumulator with truncation, so only the additions made at full magnitude matter (measured:
                 // interleaved order 2.2e-7 relative bias toward zero, this order see the tests)
+                const bool small_products = !CONV_EXPERIMENT(2);
+                if (small_products) {
 #pragma unroll
-                for (int k8 = 0; k8 < kBK / 8; ++k8) {
-                    const uint64_t adv_a = (uint64_t)((k8 * 8 * sizeof(float)) >> 4);     // 32 bytes along K
-                    const uint64_t adv_b = (uint64_t)((k8 * 1024) >> 4);                  // 8 channel rows
-                    umma_tf32(d_tmem, d_wl + adv_a, d_xh + adv_b, kIdesc, k8 > 0);
-                    umma_tf32(d_tmem, d_wh + adv_a, d_xl + adv_b, kIdesc, 1);
+                    for (int k8 = 0; k8 < kBK / 8; ++k8) {
+                        const uint64_t adv_a = (uint64_t)((k8 * 8 * sizeof(float)) >> 4);     // 32 bytes along K
+                        const uint64_t adv_b = (uint64_t)((k8 * 1024) >> 4);                  // 8 channel rows
+                        umma_tf32(d_tmem, d_wl + adv_a, d_xh + adv_b, kIdesc, k8 > 0);
+                        umma_tf32(d_tmem, d_wh + adv_a, d_xl + adv_b, kIdesc, 1);
+                    }
                 }
 #pragma unroll
                 for (int k8 = 0; k8 < kBK / 8; ++k8) {
                     const uint64_t adv_a = (uint64_t)((k8 * 8 * sizeof(float)) >> 4);
                     const uint64_t adv_b = (uint64_t)((k8 * 1024) >> 4);
-                    umma_tf32(d_tmem, d_wh + adv_a, d_xh + adv_b, kIdesc, 1);
+                    umma_tf32(d_tmem, d_wh + adv_a, d_xh + adv_b, kIdesc, small_products || k8 > 0);
                 }
                 umma_commit(&empty[s]);
                 umma_commit(&acc_full[b]);
@@ -383,6 +399,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             float4* lo = hi + kBTile / 4;
 #pragma unroll 8
             for (int i = 0; i < kBTile / 4 / (32 * kSplitWarps); ++i) {
+                if (CONV_EXPERIMENT(8)) break;
                 const float4 v = hi[t + 32 * kSplitWarps * i];
                 float4 h, l;
                 veltkamp_split(v.x, h.x, l.x);
@@ -390,7 +407,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 veltkamp_split(v.z, h.z, l.z);
                 veltkamp_split(v.w, h.w, l.w);
                 hi[t + 32 * kSplitWarps * i] = h;
-                lo[t + 32 * kSplitWarps * i] = l;
+                if (!CONV_EXPERIMENT(1)) lo[t + 32 * kSplitWarps * i] = l;
             }
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
@@ -426,6 +443,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 tc_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < kCols; c0 += 16) {
+                    if (CONV_EXPERIMENT(4) && c0 >= kCols / 2) break;
                     float v[16];
                     tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + half * kCols + c0), v);
 #pragma unroll
@@ -617,6 +635,9 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     GPFQ_REQUIRE(total < (1ll << 30), "conv1x1_tc: too many tiles");
     a.total_units = (int)total;
     a.prefetch_residual = 0;
+#ifdef GPFQ_CONV_EXPERIMENT
+    a.experiment = getenv("GPFQ_CONV_EXPERIMENT") ? atoi(getenv("GPFQ_CONV_EXPERIMENT")) : 0;
+#endif
     tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
     if (residual != nullptr && HW % 4 == 0) {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)N, (cuuint64_t)B};

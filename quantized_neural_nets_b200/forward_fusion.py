@@ -94,6 +94,39 @@ def _tc_route(conv):
     return 'patches' if max(conv.stride) >= 2 else None
 
 
+class _SharedPatches:
+    """Patch matrices of ONE designated tensor, kept between consecutive forward passes.
+
+    The analog and the quantized network of a layer's calibration read the SAME image batch, so the patch matrix of the
+    stem convolution (the 7 x 7 stride-2 stem of a ResNet: 2 GB for 256 images) is identical in the two passes;
+    QuantizeNeuralNet designates the batch before the analog pass and releases it after the quantized one."""
+    source = None
+    store = {}
+
+
+def share_patches_of(x):
+    _SharedPatches.source, _SharedPatches.store = x, {}
+
+
+def release_shared_patches():
+    _SharedPatches.source, _SharedPatches.store = None, {}
+
+
+def _patch_matrix(x, geometry, x_ld):
+    """[B, C*kh*kw, x_ld] patch matrix of ``x`` (gpfq_conv_patches_f32), shared when ``x`` is the designated tensor."""
+    B, C, H, W = x.shape
+    kh, kw, sh, sw, ph, pw, dh, dw = geometry
+    shared = x is _SharedPatches.source
+    key = (x._version, geometry, x_ld)
+    if shared and key in _SharedPatches.store:
+        return _SharedPatches.store[key]
+    xin = torch.empty((B, C * kh * kw, x_ld), dtype=torch.float32, device=x.device)
+    launch(lib.gpfq_conv_patches_f32, x, B, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, xin, x_ld)
+    if shared:
+        _SharedPatches.store[key] = xin
+    return xin
+
+
 class FusedConvBNAct(nn.Module):
     """Conv2d -> inference BatchNorm2d (-> + residual) (-> clamp to [lo, hi]) as ONE tensor-core kernel
     (gpfq_conv1x1_bn_act_f32: tcgen05 split-TF32 GEMM whose epilogue applies the batch norm, the residual add and the
@@ -136,8 +169,7 @@ class FusedConvBNAct(nn.Module):
             xin, x_ld, Ck = x, HW, C
         else:
             x_ld, Ck = (HW + 3) // 4 * 4, C * kh * kw
-            xin = torch.empty((B, Ck, x_ld), dtype=torch.float32, device=x.device)
-            launch(lib.gpfq_conv_patches_f32, x, B, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, xin, x_ld)
+            xin = _patch_matrix(x, (kh, kw, sh, sw, ph, pw, dh, dw), x_ld)
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=x.device)
         ws = _conv_workspace(conv, x.device)
         launch(lib.gpfq_conv1x1_bn_act_f32, xin, x_ld, conv.weight, residual, alpha, beta, out, B, Ck, N, HW, self.tail.lo,

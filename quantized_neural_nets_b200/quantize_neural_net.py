@@ -24,6 +24,7 @@ from . import step_algorithm as _sa
 from .step_algorithm import (quantize_layer_impl, reduce_errors, row_radius, delta_from_radii,
                              gram_reduce_eligible, feature_major)
 from .utils import InterruptException, extract_layers
+from .forward_fusion import share_patches_of, release_shared_patches
 
 LINEAR_MODULE_TYPE = nn.Linear
 CONV2D_MODULE_TYPE = nn.Conv2d
@@ -516,14 +517,18 @@ class QuantizeNeuralNet:
         """Draw the layer's batch, copy it to the device and run the ANALOG network up to the layer."""
         images, sharded, shard_range, full_batch = self._next_images()
         save_input = self._make_saver(self.analog_network_layers[layer_idx], sharded, shard_range, full_batch)
+        share_patches_of(images)              # the quantized pass reads the same batch: one stem patch matrix for both
         self._run_to_hook('forward_analog', self.analog_network, self.analog_network_layers, layer_idx, save_input, images)
         return layer_idx, save_input, images, sharded
 
     def _end_capture(self, capture):
         """Run the (partially) QUANTIZED network up to the layer on the same batch; returns (X, X~)."""
         layer_idx, save_input, images, sharded = capture
-        self._run_to_hook('forward_quantized', self.quantized_network, self.quantized_network_layers, layer_idx,
-                          save_input, images)
+        try:
+            self._run_to_hook('forward_quantized', self.quantized_network, self.quantized_network_layers, layer_idx,
+                              save_input, images)
+        finally:
+            release_shared_patches()
         return self._exchange_inputs(layer_idx, save_input.inputs[0], save_input.inputs[1], sharded)
 
     def _exchange_inputs(self, layer_idx, X, Xq, sharded):

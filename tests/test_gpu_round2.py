@@ -438,11 +438,13 @@ def test_slice_exchange_kernels_round_trip(reg, lam, groups):
 
 
 @pytest.mark.parametrize("shape,k,s,p", [((3, 5, 17, 23), 3, 2, 1), ((2, 4, 8, 8), 2, 2, 0), ((1, 3, 9, 9), 3, 1, 1),
-                                         ((2, 64, 112, 112), 3, 2, 1)])
+                                         ((2, 64, 112, 112), 3, 2, 1), ((2, 3, 30, 31), 5, 3, 2),
+                                         ((1, 2, 3, 3), 3, 2, 1), ((2, 3, 15, 24), 3, 2, 1), ((3, 2, 4, 4), 3, 2, 1)])
 def test_maxpool_kernel_matches_pytorch(shape, k, s, p):
     from quantized_neural_nets_b200.forward_fusion import FastMaxPool
     x = torch.randn(shape, generator=torch.Generator().manual_seed(11)).to(DEV)
     x[0, 0, 1, 1] = float("nan")
+    x[-1, -1, -1, -1] = float("nan")
     pool = torch.nn.MaxPool2d(k, s, p)
     got, want = FastMaxPool(pool)(x), pool(x)
     assert got.shape == want.shape
@@ -474,3 +476,32 @@ def test_fused_forward_of_other_model_families(name, min_conv_sites):
         want, got = model(x), fused(x)
     assert torch.isfinite(got).all()
     assert (got - want).norm() <= 5e-5 * want.norm(), ((got - want).norm() / want.norm()).item()
+
+
+def test_stem_patch_matrix_is_shared_between_the_two_passes():
+    """The analog and the quantized pass of a layer read the same image batch: the designated batch's patch matrix is
+    built once (forward_fusion.share_patches_of) and the second pass gives the same bits as an unshared one."""
+    from quantized_neural_nets_b200 import forward_fusion as ff
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).to(DEV)
+    bn = torch.nn.BatchNorm2d(64).eval().to(DEV)
+    bn.running_mean.normal_(0, 0.1), bn.running_var.uniform_(0.5, 1.5)
+    site = ff.FusedConvBNAct(conv, bn, 0.0, float("inf"))
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    with torch.no_grad():
+        plain = site(x)
+        ff.share_patches_of(x)
+        try:
+            first = site(x)
+            assert len(ff._SharedPatches.store) == 1
+            cached = next(iter(ff._SharedPatches.store.values()))
+            second = site(x)
+            assert len(ff._SharedPatches.store) == 1 and next(iter(ff._SharedPatches.store.values())) is cached
+            x.add_(1.0)                                    # an in-place change of the batch must not hit the cache
+            third = site(x)
+            assert len(ff._SharedPatches.store) == 2
+        finally:
+            ff.release_shared_patches()
+        assert ff._SharedPatches.source is None and not ff._SharedPatches.store
+        assert torch.equal(plain, first) and torch.equal(plain, second)
+        assert torch.equal(third, site(x)) and not torch.equal(third, plain)

@@ -35,13 +35,15 @@ records = {}     # module name -> [events]
 order = []
 
 
-fused_types = ("FusedConvBNAct", "FusedBNAct")
+fused_types = ("FusedConvBNAct", "FusedBNAct", "FastMaxPool")
 owned = set()       # modules that live inside a fused site: a hook on them would make the site fall back
 for n, c in net.named_modules():
     if type(c).__name__ == "FusedConvBNAct":
         owned |= {id(c.conv), id(c.tail), id(c.tail.bn)}
     elif type(c).__name__ == "FusedBNAct":
         owned.add(id(c.bn))
+    elif type(c).__name__ == "FastMaxPool":
+        owned.add(id(c.pool))
 timed = [(n, c) for n, c in net.named_modules()
          if id(c) not in owned and (type(c).__name__ in fused_types or not list(c.children()))]
 # a FusedBNAct that is the tail of a FusedConvBNAct is in `owned`; stand-alone ones are timed
