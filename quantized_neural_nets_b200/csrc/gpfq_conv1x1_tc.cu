@@ -144,6 +144,25 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same load without the wait: several of them are issued back to back and waited for once (tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Register budgets per warpgroup (setmaxnreg): the kernel starts with 128 registers per thread (512 threads); the TMA /
+// MMA warpgroup and the split warpgroup hand registers to the two drain warpgroups, which then hold their 64 running
+// sums AND a whole accumulator's worth of TMEM loads (or the tile's residual) in flight.  56 + 88 + 184 + 184 = 512.
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <uint32_t kRegs>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+constexpr uint32_t kRegsControl = 56, kRegsSplit = 88, kRegsDrain = 184;
 // Veltkamp split at 13 bits: hi = x rounded to nearest at 11 significant bits, lo = x - hi exactly (three roundings, none
 // of them contracted)
 __device__ __forceinline__ void veltkamp_split(float x, float& hi, float& lo) {
@@ -217,6 +236,7 @@ struct ConvArgs {
     int C, N, HW, B;
     int n_tiles, p_tiles, total_units;      // units = tiles, or pairs of tiles (PAIR)
     int prefetch_residual;   // tmRes is valid
+    int prefetch_tiles;      // the producer pulls the activation of its tile i + prefetch_tiles into L2 (0 = off)
     int experiment;          // only read under -DGPFQ_CONV_EXPERIMENT (timing experiments that give WRONG results)
 };
 
@@ -258,7 +278,8 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, i
 template <bool AFFINE, bool RES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes,
+                  const __grid_constant__ CUtensorMap tmXpf, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     float* staging = tiles + (size_t)kStages * kStageFloats;
@@ -312,12 +333,27 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         img = rest / a.p_tiles;
     };
 
-    if (warp == 0) {
+    if (warp < kFirstSplitWarp) {
+      reg_dealloc<kRegsControl>();
+      if (warp == 0) {
         if (lane == 0) {
             int it = 0;
+            int next_pf = 1;
             for (int i = 0; i < my_tiles; ++i) {
                 int img, p0, n0;
                 tile_coords(i, img, p0, n0);
+                // The shared-memory ring holds at most three k-blocks (48 KB of raw activation) and a stage is busy with
+                // its split and its MMAs for most of its cycle, so the ring alone keeps too few bytes in flight to cover
+                // the HBM latency (the 56 x 56 layers ran at 0.41-0.57 of the HBM peak).  The activation of the tile this
+                // CTA will work on `prefetch_tiles` tiles from now is therefore pulled into L2 by bulk prefetches (boxes of
+                // 128 pixels x 128 channels); the ring's own loads then hit L2.  An activation tile is shared by the
+                // n_tiles channel tiles that sit side by side in the schedule: the CTA that owns channel tile 0 fetches it.
+                for (; next_pf <= i + a.prefetch_tiles && next_pf < my_tiles; ++next_pf) {
+                    int pimg, pp0, pn0;
+                    tile_coords(next_pf, pimg, pp0, pn0);
+                    if (pn0 == 0 && pimg < a.B)
+                        for (int c = 0; c < a.C; c += 128) tma_prefetch_3d(&tmXpf, pp0, c, pimg);
+                }
                 // the residual tile is only needed by the epilogue, several microseconds from now: pull it into L2 with
                 // one bulk prefetch so that the epilogue's loads do not each pay an HBM round trip
                 if (a.prefetch_residual && img < a.B) tma_prefetch_3d(&tmRes, p0, n0, img);
@@ -345,7 +381,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         if (lane == 0) {
             const int total = my_tiles * nkb;
             for (int it = 0; it < total; ++it) {
@@ -384,7 +420,9 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 umma_commit(&acc_full[b]);
             }
         }
-    } else if (warp >= kFirstSplitWarp && warp < kFirstSplitWarp + kSplitWarps) {
+      }
+    } else if (warp < kFirstDrainWarp) {
+        reg_dealloc<kRegsSplit>();
         // split warps: raw fp32 (written by TMA) -> hi in place, lo next to it.  cvt.rna.tf32 runs on the XU pipe (16
         // lanes per SM: an ncu capture of the first version showed it 59 % busy and everything else idle), so the split
         // is Veltkamp's, three fp32 operations on the FMA pipe: p = x * (2^13 + 1), hi = p - (p - x) is x rounded to
@@ -413,7 +451,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
-    } else if (warp >= kFirstDrainWarp) {
+    } else {
+        reg_alloc<kRegsDrain>();
         // drain warps: warp (quad, half) owns TMEM lanes 32*quad .. +31 (a warp may only touch the lane quarter given by
         // its index mod 4) and columns 64*half .. +63 of every accumulator
         const int quad = warp & 3;
@@ -441,13 +480,20 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 const int b = it % kAccs;
                 mbar_wait(&acc_full[b], (uint32_t)((it / kAccs) & 1));
                 tc_fence_after();
+                // all four 16-column loads of this warp's half accumulator go out back to back and are waited for once
+                // (one TMEM round trip per k-block instead of four)
+                uint32_t v[kCols];
+                const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + half * kCols);
 #pragma unroll
                 for (int c0 = 0; c0 < kCols; c0 += 16) {
                     if (CONV_EXPERIMENT(4) && c0 >= kCols / 2) break;
-                    float v[16];
-                    tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kTN + half * kCols + c0), v);
+                    tmem_ld_32x16_issue(t0 + (uint32_t)c0, v + c0);
+                }
+                tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) run[c0 + e] = __fadd_rn(run[c0 + e], v[e]);
+                for (int c = 0; c < kCols; ++c) {
+                    if (CONV_EXPERIMENT(4) && c >= kCols / 2) break;
+                    run[c] = __fadd_rn(run[c], __uint_as_float(v[c]));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -477,19 +523,25 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             float* optr = a.out + row_base;
             const float* rptr = RES ? a.residual + row_base : nullptr;
             const float* sread = stg + rq * kStgStride + 4 * cq;
+            // the tile's sixteen residual loads (4 column blocks x 4 row groups, L2 hits after the bulk prefetch) all go
+            // out before the first block is transposed: one L2 round trip per tile instead of one per block (the drain
+            // warpgroups have the registers for it, see kRegsDrain)
+            float4 rr[kCols / 16][4];
+            if (RES && vec) {
+#pragma unroll
+                for (int cb = 0; cb < kCols / 16; ++cb) {
+                    const bool pv = pw0 + 16 * cb + 4 * cq < a.HW;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        rr[cb][k] = (rv[k] && pv) ? __ldg(reinterpret_cast<const float4*>(rptr + k * kstride + 16 * cb))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
 #pragma unroll
             for (int c0 = 0; c0 < kCols; c0 += 16) {
                 if (pw0 + c0 >= a.HW) break;       // uniform over the warp
                 if (vec) {
                     const bool pv = pw0 + c0 + 4 * cq < a.HW;      // HW % 4 == 0: a float4 is entirely inside or outside
-                    // the block's four residual loads go out before the transposition (L2 hits after the bulk prefetch)
-                    float4 rr[4];
-                    if (RES) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            rr[k] = (rv[k] && pv) ? __ldg(reinterpret_cast<const float4*>(rptr + k * kstride + c0))
-                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<float4*>(stg + lane * kStgStride + 4 * j) =
@@ -505,8 +557,9 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                             v.w = __fadd_rn(__fmul_rn(v.w, al4[k]), be4[k]);
                         }
                         if (RES) {
-                            v.x = __fadd_rn(v.x, rr[k].x); v.y = __fadd_rn(v.y, rr[k].y);
-                            v.z = __fadd_rn(v.z, rr[k].z); v.w = __fadd_rn(v.w, rr[k].w);
+                            const float4 r = rr[c0 / 16][k];
+                            v.x = __fadd_rn(v.x, r.x); v.y = __fadd_rn(v.y, r.y);
+                            v.z = __fadd_rn(v.z, r.z); v.w = __fadd_rn(v.w, r.w);
                         }
                         if (clamp_lo) { v.x = max_nan(v.x, lo); v.y = max_nan(v.y, lo); v.z = max_nan(v.z, lo); v.w = max_nan(v.w, lo); }
                         if (clamp_hi) { v.x = min_nan(v.x, hi); v.y = min_nan(v.y, hi); v.z = min_nan(v.z, hi); v.w = min_nan(v.w, hi); }
@@ -639,6 +692,17 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     a.experiment = getenv("GPFQ_CONV_EXPERIMENT") ? atoi(getenv("GPFQ_CONV_EXPERIMENT")) : 0;
 #endif
     tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
+    CUtensorMap tmXpf = tmX;
+    {
+        const int pf_env = getenv("GPFQ_CONV_PREFETCH") ? atoi(getenv("GPFQ_CONV_PREFETCH")) : 0;
+        a.prefetch_tiles = pair ? 0 : std::max(0, std::min(pf_env, 8));
+        if (a.prefetch_tiles > 0) {
+            cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+            cuuint64_t strides[2] = {(cuuint64_t)x_ld * sizeof(float), (cuuint64_t)C * x_ld * sizeof(float)};
+            cuuint32_t box[3] = {(cuuint32_t)kTN, 128, 1};
+            if (int rc = make_map(&tmXpf, x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        }
+    }
     if (residual != nullptr && HW % 4 == 0) {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)N, (cuuint64_t)B};
         cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)N * HW * sizeof(float)};
@@ -646,7 +710,8 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
         a.prefetch_residual = 1;
     }
-    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
+    typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const ConvArgs);
     static const KernelFn table[2][2][2] = {
         {{conv1x1_tc_kernel<false, false, false>, conv1x1_tc_kernel<false, false, true>},
          {conv1x1_tc_kernel<false, true, false>, conv1x1_tc_kernel<false, true, true>}},
@@ -680,7 +745,7 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(total, mc));
     }
     profile_mark_begin(stream);
-    GPFQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, tmWh, tmWl, tmX, tmRes, a));
+    GPFQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, tmWh, tmWl, tmX, tmRes, tmXpf, a));
     if (profile_on())
         profile_mark_end(stream, 4.0 * B * (double)HW * ((double)C + N * (residual ? 2.0 : 1.0)),
                          2.0 * B * (double)HW * C * N, 3);
