@@ -236,7 +236,12 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int N, int C, i
 
 // tmWh / tmWl: (N x Cp) planes, box [128][32], SWIZZLE_128B.  tmX: RAW activation as (HW, C, B), box (32, 32, 1),
 // SWIZZLE_128B_ATOM_32B; channels beyond C and pixels beyond HW arrive as zeros.
-template <bool AFFINE, bool RES>
+//
+// HWC > 0 is a specialisation for planes of exactly HWC pixels and channel counts that are multiples of 32 (every
+// ResNet / MobileNet layer): the epilogue's row offsets become immediates of its loads and stores and its per-channel
+// predicates disappear -- the drain warps are bound by their own instruction stream (see the epilogue).  HWC = 0 is the
+// general kernel.
+template <bool AFFINE, bool RES, int HWC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmRes, const ConvArgs a) {
@@ -427,12 +432,14 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             const size_t base = ((size_t)img * a.N + nb) * a.HW + p;
             char* optr = reinterpret_cast<char*>(a.out + base);
             const char* rptr = RES ? reinterpret_cast<const char*>(a.residual + base) : nullptr;
-            const uint32_t row_bytes = (uint32_t)a.HW * 4u;    // bytes between consecutive channels of one pixel
+            const uint32_t row_bytes = HWC > 0 ? (uint32_t)HWC * 4u : (uint32_t)a.HW * 4u;    // between channels of one pixel
+            constexpr bool kWhole = HWC > 0;                   // N % 32 == 0: a round's 16 channels all exist
             // the residual of one 16-channel round (L2 hits after the bulk prefetch); `left` = channels that exist
             auto load_residual = [&](float* r, const char* ptr, int left) {
+                const bool ok = pvalid && left > 0;
 #pragma unroll
                 for (int e = 0; e < kGroup; ++e)
-                    r[e] = (pvalid && e < left) ? __ldg(reinterpret_cast<const float*>(ptr + (size_t)((uint32_t)e * row_bytes)))
+                    r[e] = (ok && (kWhole || e < left)) ? __ldg(reinterpret_cast<const float*>(ptr + (size_t)((uint32_t)e * row_bytes)))
                                                 : 0.f;
             };
             float r[kGroup];
@@ -496,7 +503,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                         if (RES) v = __fadd_rn(v, rcur[e]);
                         if (clamp_lo) v = max_nan(v, lo);
                         if (clamp_hi) v = min_nan(v, hi);
-                        if (pvalid && e < left) *reinterpret_cast<float*>(optr + (size_t)((uint32_t)e * row_bytes)) = v;
+                        if (pvalid && (kWhole || e < left)) *reinterpret_cast<float*>(optr + (size_t)((uint32_t)e * row_bytes)) = v;
                     }
                 }
                 optr += (size_t)(kGroup * row_bytes);
@@ -513,7 +520,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                     rptr += (size_t)(kGroup * row_bytes);
                     load_residual(r, rptr, nvalid - c0 - 2 * kGroup);
                 }
-                round(c0 + kGroup, run + kGroup, r2);
+                if (c0 + kGroup < nvalid) round(c0 + kGroup, run + kGroup, r2);
 #pragma unroll
                 for (int j = 0; j < kCols - 2 * kGroup; ++j) run[j] = run[j + 2 * kGroup];
             }
@@ -620,9 +627,19 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         a.prefetch_residual = getenv("GPFQ_CONV_RESPF") ? atoi(getenv("GPFQ_CONV_RESPF")) : 1;
     }
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
-    static const KernelFn table[2][2] = {{conv1x1_tc_kernel<false, false>, conv1x1_tc_kernel<false, true>},
-                                         {conv1x1_tc_kernel<true, false>, conv1x1_tc_kernel<true, true>}};
-    const KernelFn fn = table[alpha != nullptr][residual != nullptr];
+#define GPFQ_CONV_ROW(HWC)                                                                                         \
+    {{conv1x1_tc_kernel<false, false, HWC>, conv1x1_tc_kernel<false, true, HWC>},                                  \
+     {conv1x1_tc_kernel<true, false, HWC>, conv1x1_tc_kernel<true, true, HWC>}}
+    // plane sizes with a specialised epilogue: 112^2 (the ResNet stem), 56^2, 28^2, 14^2; index 0 = general kernel
+    static const int plane[5] = {0, 12544, 3136, 784, 196};
+    static const KernelFn table[5][2][2] = {GPFQ_CONV_ROW(0), GPFQ_CONV_ROW(12544), GPFQ_CONV_ROW(3136), GPFQ_CONV_ROW(784),
+                                            GPFQ_CONV_ROW(196)};
+#undef GPFQ_CONV_ROW
+    int special = 0;
+    if (N % 32 == 0)
+        for (int k = 1; k < 5; ++k)
+            if (HW == plane[k]) special = k;
+    const KernelFn fn = table[special][alpha != nullptr][residual != nullptr];
     if (int rc = ensure_dynamic_smem((const void*)fn, kSmemBytes)) return rc;
     profile_mark_begin(stream);
     fn<<<(unsigned)std::min<int64_t>(total, sm_count()), kThreads, kSmemBytes, stream>>>(tmWh, tmWl, tmX, tmRes, a);
