@@ -203,7 +203,7 @@ struct ConvArgs {
     const float* beta;       // (N)
     float lo, hi;
     int C, N, HW, B;
-    int n_tiles, p_tiles, total_tiles;
+    int n_tiles, cpi, total_chunks, total_tiles;   // cpi = 32-pixel chunks per image
     int prefetch_residual;   // tmRes is valid
     int experiment;          // only read under -DGPFQ_CONV_EXPERIMENT (timing experiments that give WRONG results)
 };
@@ -279,15 +279,19 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile index -> (image, pixel tile, channel tile): channel tiles of one activation tile are adjacent in the
-    // schedule, so CTAs that run side by side share the activation tile through L2
-    auto tile_coords = [&](int i, int& img, int& p0, int& n0) {
+    // A tile is FOUR 32-pixel chunks x one channel tile.  The chunks of all images form one sequence (image-major; the
+    // last chunk of an image may be partly empty), a tile takes four consecutive ones -- so a tile may straddle images and
+    // small planes (28 x 28, 14 x 14, 7 x 7) do not leave most of their last tile empty.  Channel tiles of one pixel tile
+    // are adjacent in the schedule, so CTAs that run side by side share the activation through L2.
+    auto tile_coords = [&](int i, int& q0, int& n0) {
         const int t = worker + i * n_workers;
-        const int nt = t % a.n_tiles;
-        const int rest = t / a.n_tiles;
-        n0 = nt * kTM;
-        p0 = (rest % a.p_tiles) * kTN;
-        img = rest / a.p_tiles;
+        n0 = (t % a.n_tiles) * kTM;
+        q0 = (t / a.n_tiles) * (kTN / kPx);
+    };
+    // chunk index -> (image, first pixel); a chunk past the end belongs to image B (loads are zero-filled, nothing is stored)
+    auto chunk_coords = [&](int q, int& img, int& p0) {
+        img = q / a.cpi;
+        p0 = (q - img * a.cpi) * kPx;
     };
     // channels of the tile that starts at channel n0, rounded up to 32: the N of the tile's MMAs (the weight rows beyond
     // a.N arrive as zeros) and twice the number of accumulator columns one drain warp owns
@@ -299,11 +303,17 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         if (lane == 0) {
             int it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                int img, p0, n0;
-                tile_coords(i, img, p0, n0);
+                int q0, n0, img[kTN / kPx], p0[kTN / kPx];
+                tile_coords(i, q0, n0);
+#pragma unroll
+                for (int j = 0; j < kTN / kPx; ++j) chunk_coords(q0 + j, img[j], p0[j]);
                 // the residual tile is only needed by the epilogue, several microseconds from now: pull it into L2 with
-                // one bulk prefetch so that the epilogue's loads do not each pay an HBM round trip
-                if (a.prefetch_residual) tma_prefetch_3d(&tmRes, p0, n0, img);
+                // bulk prefetches so that the epilogue's loads do not each pay an HBM round trip
+                if (a.prefetch_residual) {
+#pragma unroll
+                    for (int j = 0; j < kTN / kPx; ++j)
+                        if (img[j] < a.B) tma_prefetch_3d(&tmRes, p0[j], n0, img[j]);
+                }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
@@ -314,7 +324,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                     tma_load_2d(st + kATile, &tmWl, c0, n0, &full[s]);
 #pragma unroll
                     for (int j = 0; j < kTN / kPx; ++j)
-                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0 + j * kPx, c0, img, &full[s]);
+                        tma_load_3d(st + 2 * kATile + j * kBK * kPx, &tmX, p0[j], c0, img[j], &full[s]);
                 }
             }
         }
@@ -322,8 +332,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         if (lane == 0) {
             int it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                int img, p0, n0;
-                tile_coords(i, img, p0, n0);
+                int q0, n0;
+                tile_coords(i, q0, n0);
                 const uint32_t idesc = kIdescBase | ((uint32_t)(tile_channels(n0) >> 3) << 17);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
@@ -411,8 +421,9 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         int nb_loaded = -1;
         int it = 0;
         for (int i = 0; i < my_tiles; ++i) {
-            int img, p0, n0;
-            tile_coords(i, img, p0, n0);
+            int q0, n0, img, p0;
+            tile_coords(i, q0, n0);
+            chunk_coords(q0 + quad, img, p0);                  // this warp's TMEM lane quarter = chunk `quad` of the tile
             const int cols_w = tile_channels(n0) >> 1;         // columns of this warp: a multiple of 16
             const int nb = n0 + half * cols_w;                 // this warp's first channel
             if (AFFINE && nb != nb_loaded) {
@@ -426,8 +437,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 __syncwarp();
                 nb_loaded = nb;
             }
-            const int p = p0 + quad * 32 + lane;
-            const bool pvalid = p < a.HW;
+            const int p = p0 + lane;
+            const bool pvalid = img < a.B && p < a.HW;
             const int nvalid = min(cols_w, a.N - nb);          // channels of this warp that exist (<= 0: none)
             const size_t base = ((size_t)img * a.N + nb) * a.HW + p;
             char* optr = reinterpret_cast<char*>(a.out + base);
@@ -610,9 +621,11 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     a.out = out; a.residual = residual; a.alpha = alpha; a.beta = beta; a.lo = lo; a.hi = hi;
     a.C = C; a.N = N; a.HW = HW; a.B = B;
     a.n_tiles = (int)ceil_div(N, kTM);
-    a.p_tiles = (int)ceil_div(HW, kTN);
-    const int64_t total = (int64_t)a.n_tiles * a.p_tiles * B;
-    GPFQ_REQUIRE(total < (1ll << 30), "conv1x1_tc: too many tiles");
+    a.cpi = (int)ceil_div(HW, kPx);
+    const int64_t chunks = (int64_t)a.cpi * B;
+    const int64_t total = (int64_t)a.n_tiles * ceil_div(chunks, kTN / kPx);
+    GPFQ_REQUIRE(chunks < (1ll << 30) && total < (1ll << 30), "conv1x1_tc: too many tiles");
+    a.total_chunks = (int)chunks;
     a.total_tiles = (int)total;
     a.prefetch_residual = 0;
 #ifdef GPFQ_CONV_EXPERIMENT
@@ -622,7 +635,7 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     if (residual != nullptr && HW % 4 == 0) {
         cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)N, (cuuint64_t)B};
         cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)N * HW * sizeof(float)};
-        cuuint32_t box[3] = {(cuuint32_t)kTN, (cuuint32_t)kTM, 1};
+        cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kTM, 1};
         if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
         a.prefetch_residual = getenv("GPFQ_CONV_RESPF") ? atoi(getenv("GPFQ_CONV_RESPF")) : 1;
     }
