@@ -456,7 +456,11 @@ class QuantizeNeuralNet:
         return self._end_capture(self._begin_capture(layer_idx))
 
     def _run_to_hook(self, name, network, layers, layer_idx, save_input, images):
-        handle = layers[layer_idx].register_forward_hook(save_input)
+        # The reference registers SaveInput* as a forward hook (quantize_neural_net.py:256-269): the layer's own forward
+        # runs, then the hook stores the INPUT and interrupts the pass -- the output is never used.  The same object is
+        # registered here as a forward PRE-hook: identical captured input, but the captured layer's convolution (as much
+        # as a tenth of a prefix pass) is not computed just to be thrown away.
+        handle = layers[layer_idx].register_forward_pre_hook(lambda module, module_in: save_input(module, module_in, None))
         with torch.no_grad(), self._Phase(self, layer_idx, name):
             try:
                 self._fused.get(id(network), network)(images)
