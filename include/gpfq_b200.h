@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GPFQ_ABI_VERSION 6
+#define GPFQ_ABI_VERSION 7
 
 /* alphabet maps: step_algorithm.py:38-56 (MSQ), :84-104 (SOFT, reg='L1'), :59-81 (HARD, reg='L0'),
  * :7-35 (STOCHASTIC, SGPFQ: stochastic rounding to the two neighbouring grid points, then clipping; the
@@ -69,7 +69,10 @@ int gpfq_bn_act_f32(const float* x, const float* residual, const float* alpha, c
  *     it to gpfq_conv1x1_bn_act_f32 (x_ld = ld, C = C*kh*kw, HW = Ho*Wo) evaluates ANY convolution on the tensor
  *     cores; a 1x1 kernel with stride 2 is a strided gather, with stride 1 a copy that pads the row pitch to a
  *     multiple of 4 (7 x 7 planes).
- *   gpfq_conv1x1_f32: the plain stride-1 1x1 convolution of a contiguous tensor (HW % 4 == 0) through the same kernel. */
+ *   gpfq_conv1x1_f32: the plain stride-1 1x1 convolution of a contiguous tensor (HW % 4 == 0) through the same kernel.
+ *   gpfq_conv1x1_split_weight_f32 + gpfq_conv1x1_bn_act_planes_f32: the same convolution in two calls for weights that are
+ *     used many times (the calibration forward re-runs a layer in up to 106 prefix passes per step): the first writes the
+ *     TF32 planes of W into `workspace`, the second takes them as `planes` and launches the tensor-core kernel only. */
 size_t gpfq_conv1x1_workspace_bytes(int32_t N, int32_t C);
 int32_t gpfq_conv1x1_fused_supported(int32_t C, int32_t N, int32_t HW, int64_t x_ld);
 int gpfq_conv1x1_bn_act_f32(const float* x, int64_t x_ld, const float* W, const float* residual, const float* alpha,
@@ -79,6 +82,10 @@ int gpfq_conv_patches_f32(const float* in, int32_t B, int32_t C, int32_t H, int3
                           int32_t sw, int32_t ph, int32_t pw, int32_t dh, int32_t dw, float* out, int64_t ld, void* stream);
 int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
                      void* workspace, size_t workspace_bytes, void* stream);
+int gpfq_conv1x1_split_weight_f32(const float* W, int32_t N, int32_t C, void* workspace, size_t workspace_bytes, void* stream);
+int gpfq_conv1x1_bn_act_planes_f32(const float* x, int64_t x_ld, const float* residual, const float* alpha, const float* beta,
+                                   float* out, int32_t B, int32_t C, int32_t N, int32_t HW, float lo, float hi,
+                                   const void* planes, size_t planes_bytes, void* stream);
 
 /* Calibration-forward helper: MaxPool2d with a square k x k window, stride, implicit -inf padding (2*pad <= k), floor mode,
  * dilation 1, of `planes` = B*C contiguous H x W planes; out is planes x Ho x Wo, Ho = (H + 2*pad - k) / stride + 1.

@@ -35,6 +35,9 @@ SIGNATURES = {
     "gpfq_conv1x1_fused_supported": (c_i32, [c_i32, c_i32, c_i32, c_i64]),
     "gpfq_conv1x1_bn_act_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_f32,
                                         c_f32, c_ptr, ctypes.c_size_t, c_ptr]),
+    "gpfq_conv1x1_split_weight_f32": (c_i32, [c_ptr, c_i32, c_i32, c_ptr, ctypes.c_size_t, c_ptr]),
+    "gpfq_conv1x1_bn_act_planes_f32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_f32,
+                                               c_f32, c_ptr, ctypes.c_size_t, c_ptr]),
     "gpfq_conv_patches_f32": (c_i32, [c_ptr] + [c_i32] * 12 + [c_ptr, c_i64, c_ptr]),
     "gpfq_maxpool2d_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "gpfq_packed_bits": (c_i32, [c_i32, c_i32]),

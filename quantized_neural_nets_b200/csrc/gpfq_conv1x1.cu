@@ -15,9 +15,10 @@
 namespace gpfq {
 size_t conv1x1_tc_workspace_bytes(int N, int C);
 bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld);
+int conv1x1_tc_split_weight(const float* W, int N, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
                const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
-               cudaStream_t stream);
+               cudaStream_t stream, bool planes_ready);
 
 // Patch matrix of a convolution with ITS OWN stride (not the stride = kernel unfold of the calibration capture):
 // out[b][(c, ki, kj)][yo * Wo + xo] = in[b][c][yo * sh - ph + ki * dh][xo * sw - pw + kj * dw] (0 outside the image),
@@ -95,7 +96,26 @@ extern "C" int gpfq_conv1x1_bn_act_f32(const float* x, int64_t x_ld, const float
                  "gpfq_conv_patches_f32; ask gpfq_conv1x1_fused_supported first)", (long long)x_ld);
     if (B == 0) return 0;
     return conv1x1_tc(x, x_ld, W, out, residual, alpha, beta, lo, hi, B, C, N, HW, workspace, workspace_bytes,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, false);
+}
+
+extern "C" int gpfq_conv1x1_split_weight_f32(const float* W, int32_t N, int32_t C, void* workspace, size_t workspace_bytes,
+                                             void* stream) {
+    GPFQ_REQUIRE(C >= 1 && N >= 1 && W && workspace, "gpfq_conv1x1_split_weight_f32: bad arguments");
+    return conv1x1_tc_split_weight(W, N, C, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gpfq_conv1x1_bn_act_planes_f32(const float* x, int64_t x_ld, const float* residual, const float* alpha,
+                                              const float* beta, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
+                                              float lo, float hi, const void* planes, size_t planes_bytes, void* stream) {
+    GPFQ_REQUIRE(B >= 0 && C >= 1 && N >= 1 && HW >= 1, "gpfq_conv1x1_bn_act_planes_f32: bad shape");
+    GPFQ_REQUIRE(x && out && planes, "gpfq_conv1x1_bn_act_planes_f32: null pointer");
+    GPFQ_REQUIRE((alpha == nullptr) == (beta == nullptr), "gpfq_conv1x1_bn_act_planes_f32: alpha and beta go together");
+    GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW, x_ld),
+                 "gpfq_conv1x1_bn_act_planes_f32: the pixel pitch x_ld = %lld must be >= HW and a multiple of 4", (long long)x_ld);
+    if (B == 0) return 0;
+    return conv1x1_tc(x, x_ld, nullptr, out, residual, alpha, beta, lo, hi, B, C, N, HW, const_cast<void*>(planes), planes_bytes,
+                      (cudaStream_t)stream, true);
 }
 
 extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int32_t B, int32_t C, int32_t N, int32_t HW,
@@ -107,5 +127,5 @@ extern "C" int gpfq_conv1x1_f32(const float* x, const float* W, float* out, int3
                  "stride 1) and call gpfq_conv1x1_bn_act_f32 with x_ld", HW);
     if (B == 0) return 0;
     return conv1x1_tc(x, HW, W, out, nullptr, nullptr, nullptr, -INFINITY, INFINITY, B, C, N, HW, workspace, workspace_bytes,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, false);
 }

@@ -587,9 +587,22 @@ size_t conv1x1_tc_workspace_bytes(int N, int C) { return (size_t)2 * N * round_u
 // x is read through TMA: its pixel pitch x_ld (floats between consecutive channels) must be a multiple of 4
 bool conv1x1_tc_supported(int C, int N, int HW, int64_t x_ld) { return C >= 1 && N >= 1 && HW >= 1 && x_ld >= HW && x_ld % 4 == 0; }
 
+// the TF32 planes of W into the workspace (what conv1x1_tc does first unless it is told they are there already)
+int conv1x1_tc_split_weight(const float* W, int N, int C, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C), "conv1x1_tc: workspace too small");
+    GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "conv1x1_tc: workspace must be 256-byte aligned");
+    const int Cp = (int)round_up(C, kBK);
+    float* w_hi = (float*)workspace;
+    float* w_lo = w_hi + (size_t)N * Cp;
+    const int64_t n_w = (int64_t)N * Cp;
+    split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
+    GPFQ_CHECK_LAUNCH();
+    return 0;
+}
+
 int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const float* residual, const float* alpha,
                const float* beta, float lo, float hi, int B, int C, int N, int HW, void* workspace, size_t workspace_bytes,
-               cudaStream_t stream) {
+               cudaStream_t stream, bool planes_ready) {
     GPFQ_REQUIRE(conv1x1_tc_supported(C, N, HW, x_ld), "conv1x1_tc: unsupported shape");
     GPFQ_REQUIRE(workspace_bytes >= conv1x1_tc_workspace_bytes(N, C), "conv1x1_tc: workspace too small");
     GPFQ_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
@@ -599,9 +612,8 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     const int Cp = (int)round_up(C, kBK);
     float* w_hi = (float*)workspace;
     float* w_lo = w_hi + (size_t)N * Cp;
-    const int64_t n_w = (int64_t)N * Cp;
-    split_weight_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_w, 256), 148 * 4), 256, 0, stream>>>(W, N, C, Cp, w_hi, w_lo);
-    GPFQ_CHECK_LAUNCH();
+    if (!planes_ready)
+        if (int rc = conv1x1_tc_split_weight(W, N, C, workspace, workspace_bytes, stream)) return rc;
 
     CUtensorMap tmWh, tmWl, tmX, tmRes;
     {

@@ -141,6 +141,19 @@ class FusedConvBNAct(nn.Module):
         self.conv = conv
         self.tail = FusedBNAct(bn, lo, hi)
         self.route = _tc_route(conv)
+        self._planes = None     # (TF32 planes of the weight, tag of the weight they were made from)
+
+    def _weight_planes(self, device, Ck):
+        """TF32 hi / lo planes of the weight (gpfq_conv1x1_split_weight_f32), made once per weight VALUE: a layer runs in
+        up to 106 prefix passes of a step with the same weight (the analog network's never changes, a quantized layer's
+        changes once), so the split is not repeated in front of every convolution launch."""
+        w = self.conv.weight
+        tag = (w.data_ptr(), w._version, tuple(w.shape), device)
+        if self._planes is None or self._planes[1] != tag:
+            ws = _conv_workspace(self.conv, device)
+            launch(lib.gpfq_conv1x1_split_weight_f32, w, self.conv.out_channels, Ck, ws, ws.numel())
+            self._planes = (ws, tag)
+        return self._planes[0]
 
     def forward(self, x, residual=None):
         conv, bn = self.conv, self.tail.bn
@@ -171,8 +184,8 @@ class FusedConvBNAct(nn.Module):
             x_ld, Ck = (HW + 3) // 4 * 4, C * kh * kw
             xin = _patch_matrix(x, (kh, kw, sh, sw, ph, pw, dh, dw), x_ld)
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=x.device)
-        ws = _conv_workspace(conv, x.device)
-        launch(lib.gpfq_conv1x1_bn_act_f32, xin, x_ld, conv.weight, residual, alpha, beta, out, B, Ck, N, HW, self.tail.lo,
+        ws = self._weight_planes(x.device, Ck)
+        launch(lib.gpfq_conv1x1_bn_act_planes_f32, xin, x_ld, residual, alpha, beta, out, B, Ck, N, HW, self.tail.lo,
                self.tail.hi, ws, ws.numel())
         return out
 

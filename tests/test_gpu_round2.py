@@ -334,6 +334,51 @@ def test_conv1x1_tensor_core_kernel(B, C, N, H, W, with_res, lo, hi):
     assert (plain - cud).norm() <= 2e-6 * cud.norm()
 
 
+def test_conv1x1_two_call_route_and_plane_cache():
+    """gpfq_conv1x1_split_weight_f32 + gpfq_conv1x1_bn_act_planes_f32 give the bits of the one-call route, tiles that
+    straddle images included (B * ceil(HW / 32) chunks not a multiple of 4), and FusedConvBNAct re-splits a weight whose
+    value changed (in place or by assignment) and only then."""
+    from quantized_neural_nets_b200 import _lib
+    from quantized_neural_nets_b200._lib import lib, launch
+    from quantized_neural_nets_b200.forward_fusion import FusedConvBNAct
+    g = torch.Generator().manual_seed(7)
+    B, C, N, H, W = 7, 96, 160, 14, 14          # 7 chunks per image, 49 chunks: tiles straddle images, last tile 1 chunk
+    x = torch.relu(torch.randn(B, C, H, W, generator=g)).to(DEV)
+    w = (torch.randn(N, C, generator=g) * 0.1).to(DEV)
+    alpha = (torch.rand(N, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(N, generator=g) * 0.1).to(DEV)
+    res = torch.randn(B, N, H, W, generator=g).to(DEV)
+    ws = torch.empty(lib.gpfq_conv1x1_workspace_bytes(N, C), dtype=torch.uint8, device=DEV)
+    one = torch.full((B, N, H, W), float("nan"), device=DEV)
+    launch(lib.gpfq_conv1x1_bn_act_f32, x, H * W, w, res, alpha, beta, one, B, C, N, H * W, 0.0, float("inf"), ws, ws.numel())
+    planes = torch.empty_like(ws)
+    launch(lib.gpfq_conv1x1_split_weight_f32, w, N, C, planes, planes.numel())
+    two = torch.full((B, N, H, W), float("nan"), device=DEV)
+    launch(lib.gpfq_conv1x1_bn_act_planes_f32, x, H * W, res, alpha, beta, two, B, C, N, H * W, 0.0, float("inf"), planes,
+           planes.numel())
+    assert torch.equal(one, two)
+    ref = torch.relu(torch.einsum("nc,bchw->bnhw", w.double(), x.double()) * alpha.double()[None, :, None, None]
+                     + beta.double()[None, :, None, None] + res.double())
+    assert (one.double() - ref).norm() <= 2e-7 * ref.norm()
+    # the module's cache
+    conv = torch.nn.Conv2d(C, N, 1, bias=False).to(DEV)
+    bn = torch.nn.BatchNorm2d(N).eval().to(DEV)
+    mod = FusedConvBNAct(conv, bn, 0.0, float("inf"))
+    with torch.no_grad():
+        y0 = mod(x)
+        n0 = _lib.launch_count()
+        y1 = mod(x)
+        assert _lib.launch_count() - n0 == 1 and torch.equal(y0, y1)        # planes reused: one launch
+        conv.weight.mul_(2.0)                                                # in-place change
+        y2 = mod(x)
+        assert torch.allclose(y2, torch.relu(bn(conv(x))), rtol=1e-5, atol=1e-5)
+        conv.weight.data = torch.randn(N, C, 1, 1, device=DEV) * 0.1        # assignment (what quantize_network does)
+        n0 = _lib.launch_count()
+        y3 = mod(x)
+        assert _lib.launch_count() - n0 == 2
+        assert torch.allclose(y3, torch.relu(bn(conv(x))), rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("C,N,H,W,k,stride,pad,bias", [(3, 64, 40, 40, 7, 2, 3, False),      # ResNet stem
                                                       (32, 48, 28, 28, 3, 2, 1, False),    # stride-2 3x3
                                                       (64, 96, 14, 14, 1, 2, 0, False),    # stride-2 shortcut, 7 x 7 output

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(dll, name), f"{name} declared in gpfq_b200.h but not exported"
     assert declared == set(L.SIGNATURES), "ctypes binding and header disagree"
-    assert L.lib.gpfq_abi_version() == 6
+    assert L.lib.gpfq_abi_version() == 7
 
 
 def test_workspace_and_argument_validation_without_gpu():
