@@ -40,9 +40,9 @@ NCU_BN_ACT_TRAFFIC = {"dram_bytes_per_launch": 2440.1e6, "algorithmic_bytes_same
                       "source": "profiles/r01_bn_act_kernel_ncu_full_summary.txt"}
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one conv1x1_tc_kernel launch, from the committed ncu --set full capture
-NCU_CONV_TRAFFIC = {"dram_bytes_per_launch": 2118.3e6, "algorithmic_bytes_same_launch": 1849.7e6,
-                    "launch": "1x1 convolution 64 -> 256 + BatchNorm + residual + ReLU of a (256, 64, 56, 56) activation, 507 us",
-                    "source": "profiles/r02_conv_64_256_res_ncu_full_summary.txt"}
+NCU_CONV_TRAFFIC = {"dram_bytes_per_launch": 2104.2e6, "algorithmic_bytes_same_launch": 1849.7e6,
+                    "launch": "1x1 convolution 64 -> 256 + BatchNorm + residual + ReLU of a (256, 64, 56, 56) activation, 443 us",
+                    "source": "profiles/r02b_conv_64_256_res_ncu_full_summary.txt"}
 
 L2_PEAK_GBS = 8300.0     # L2-resident read bandwidth measured by tools/microbench.cu on this pool's B200 (r01)
 
@@ -115,7 +115,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "500", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None

@@ -9,25 +9,40 @@
 // product (lo*hi, hi*lo, hi*hi), and -- because the tensor core accumulates fp32 with truncation -- a FRESH TMEM
 // accumulator per 32-channel k-block that the epilogue warps add up in registers with round-to-nearest.
 //
-// Structure (one persistent CTA per SM, 512 threads, tiles of 128 output channels x 128 pixels of one image):
-//   warp 0      TMA producer: per k-block the weight planes w_hi / w_lo (boxes [128][32], SWIZZLE_128B, K-major) and the
-//               RAW fp32 activation (four boxes [32 channels][32 pixels], SWIZZLE_128B_ATOM_32B: the B operand is
-//               MN-major -- the pixel index is the contiguous one in NCHW), 3-stage ring that runs on across tiles; one
-//               bulk L2 prefetch of the tile's residual when there is one;
+// Operands: D (pixel x channel) = X^T (pixel x C) . W^T (C x channel).  The ACTIVATION is the A operand: M = 128 pixels
+// = the 128 TMEM lanes, MN-major in shared memory (the pixel index is the contiguous one in NCHW); the weight is the B
+// operand, K-major, N = the tile's channel count rounded up to 32 (<= 128).  So a drain thread owns ONE pixel and up to 64
+// channels, consecutive lanes own consecutive pixels, and a warp's store of one channel is one whole 128-byte line of the
+// NCHW output: the epilogue needs no transposition (the first version of this kernel had channels on the lanes and moved
+// every tile through shared memory; its 64-channel layers also issued half-empty M = 128 MMAs).
+//
+// Structure (one persistent CTA per SM, 512 threads = four warpgroups with their own register budgets, setmaxnreg
+// 40 / 72 / 200 / 200).  A tile is FOUR 32-pixel chunks x one channel tile; the chunks of all images form one image-major
+// sequence and a tile takes four consecutive ones, so tiles straddle images and small planes (28 x 28, 14 x 14, 7 x 7)
+// do not leave 12 / 23 / 62 % of their last tile empty:
+//   warp 0      TMA producer: per k-block the weight planes w_hi / w_lo (boxes [128][32], SWIZZLE_128B, K-major; made once
+//               per weight VALUE by split_weight_kernel) and the RAW fp32 activation (four boxes [32 channels][32 pixels],
+//               one per chunk, SWIZZLE_128B_ATOM_32B), 3-stage ring that runs on across tiles; bulk L2 prefetches of the
+//               tile's residual when there is one;
 //   warps 4-7   split: turn the raw activation tile into its hi plane in place and the lo plane next to it (an
 //               elementwise map, so the swizzled layout is untouched; Veltkamp's split on the FMA pipe, see below),
 //               fence.proxy.async, release the MMA warp -- the activation is read from HBM exactly once;
-//   warp 1      single-thread tcgen05.mma issue, 12 MMAs (M = N = 128, K = 8, kind::tf32) per k-block into one of FOUR
-//               128-column TMEM accumulators (all 512 columns): the MMAs run up to four k-blocks ahead of the drain;
-//   warps 8-15  drain each finished accumulator (tcgen05.ld 32x32b) into 64 fp32 registers per thread (thread = output
-//               channel, register = pixel) and, after the tile's last k-block, transpose 32 x 16 blocks through shared
-//               memory, apply alpha / beta / residual / clamp and store whole row segments.  While they store, the MMA
-//               warp is already working on the next tile.
+//   warp 1      single-thread tcgen05.mma issue, 12 MMAs (M = 128, N <= 128, K = 8, kind::tf32) per k-block into one of
+//               FOUR 128-column TMEM accumulators (all 512 columns): the MMAs run up to four k-blocks ahead of the drain;
+//   warps 8-15  drain: warp (quad, half) owns chunk `quad` of the tile (its TMEM lane quarter) and one half of the
+//               tile's channel columns; per k-block ALL its tcgen05.ld go out back to back and are waited for once, then
+//               64 round-to-nearest adds into the running sums; after the tile's last k-block alpha / beta / residual /
+//               clamp and one coalesced store per channel.  While they store, the MMA warp works on the next tiles.
 //
-// The MN-major recipe (validated on B200 in round 1, experimental/conv1x1_tf32x3.cu): for 32-bit operands the only
-// MN-major shared-memory layout UMMA accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1), written by TMA with
-// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; LBO = bytes between 32-pixel chunks (one box, 4096), SBO = 512 (a swizzle
-// atom is 4 channel rows of 128 bytes), +1024 bytes per K = 8 step, instruction-descriptor bit 16 (B is MN-major).
+// What bounds it (ncu, profiles/r02b_conv_*): the drain warps' own instruction stream on the 56 x 56 layers -- hence the
+// plane-size specialisations below (row offsets as immediates, no per-channel predicates), the residual requested rounds
+// ahead, alpha / beta as shared-memory broadcasts -- and the L2 -> SM traffic of a stage (48 KB per k-block and SM, of which
+// 32 KB are weight planes) on the large-C layers.
+//
+// The MN-major recipe (validated on B200 in round 1): for 32-bit operands the only MN-major shared-memory layout UMMA
+// accepts is SWIZZLE_128B_BASE32B (descriptor layout type 1), written by TMA with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+// LBO = bytes between 32-pixel chunks (one box, 4096), SBO = 512 (a swizzle atom is 4 channel rows of 128 bytes), +1024
+// bytes per K = 8 step, instruction-descriptor bit 15 (A is MN-major; bit 16 when it was the B operand).
 //
 // Shapes: the activation's pixel pitch must be a multiple of 4 floats (TMA global strides are multiples of 16 bytes;
 // gpfq_conv_patches_f32 pads it when it is not); any C (the channel tail of a k-block is zero-filled by TMA on both
@@ -52,9 +67,8 @@ constexpr int kAccs = 4;            // TMEM accumulators of kTN columns
 constexpr int kATile = kTM * kBK;   // floats per weight plane tile (16 KB)
 constexpr int kBTile = kBK * kTN;   // floats per activation plane tile (16 KB) = 4 boxes [32 ch][32 px]
 constexpr int kStageFloats = 2 * kATile + 2 * kBTile;      // w_hi | w_lo | x_hi (raw on arrival) | x_lo
-// 16 warps = 4 per SM sub-partition (128 registers each): warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-7 split, warps
-// 8-15 drain (two per TMEM lane quarter, 64 accumulator columns each).  Ten warps with 128-column drains were tried first:
-// three warps on a sub-partition cap the allocation at 168 registers and the 128 running sums spill.
+// 16 warps = 4 per SM sub-partition: warp 0 TMA, warp 1 MMA, warps 2-3 idle, warps 4-7 split, warps 8-15 drain (two per
+// TMEM lane quarter, up to 64 accumulator columns each).
 constexpr int kThreads = 512;
 constexpr int kFirstSplitWarp = 4, kSplitWarps = 4;
 constexpr int kFirstDrainWarp = 8, kDrainWarps = 8;
@@ -115,36 +129,7 @@ __device__ __forceinline__ uint64_t desc_mn_major(const void* tile) {
     desc |= (uint64_t)1 << 61;
     return desc;
 }
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// the same load without the wait: several of them are issued back to back and waited for once (tmem_ld_wait)
+// one 16-column accumulator load WITHOUT the wait: several of them are issued back to back and waited for once (tmem_ld_wait)
 __device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -649,7 +634,7 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
         cuuint64_t strides[2] = {(cuuint64_t)HW * sizeof(float), (cuuint64_t)N * HW * sizeof(float)};
         cuuint32_t box[3] = {(cuuint32_t)kPx, (cuuint32_t)kTM, 1};
         if (int rc = make_map(&tmRes, residual, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-        a.prefetch_residual = getenv("GPFQ_CONV_RESPF") ? atoi(getenv("GPFQ_CONV_RESPF")) : 1;
+        a.prefetch_residual = 1;
     }
     typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvArgs);
 #define GPFQ_CONV_ROW(HWC)                                                                                         \

@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(256) recur_kernel(RecurArgs a) {
     const float rdelta = recip_or_zero(delta);
     float q_mine = 0.f;
     int lv_mine = 0;
+#pragma unroll 4      // lets the loads / conversions of later decisions move off the chain of the current one
     for (int t = 0; t < a.bvalid; ++t) {
         const double pt = __shfl_sync(0xffffffffu, p, t);
         const float wt = __shfl_sync(0xffffffffu, w, t);
@@ -773,6 +774,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 wr[i] = wblk[qoff + 4 * (own0 + nl)];
             }
             if (cnt == 2) {
+#pragma unroll 4
                 for (int t = 0; t < bvalid; ++t) {
                     const double gtt = Gs[t * (2 * kB) + t], gl = Gs[t * (2 * kB) + lane], hl = Hs[t * (2 * kB) + lane];
                     const float nrm = ns[t], rnrm = ns[kB + t];
@@ -796,6 +798,7 @@ resident_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     }
                 }
             } else {
+#pragma unroll 4
                 for (int t = 0; t < bvalid; ++t) {
                     const double pt = __shfl_sync(0xffffffffu, pr[0], t);
                     const float wt = __shfl_sync(0xffffffffu, wr[0], t);

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(kPathWarps * 32) gram_path_kernel(GramPathArgs
             qmine[i] = 0.f;
             lvmine[i] = 0;
         }
+#pragma unroll 4      // the norm / reciprocal / tile loads of later decisions move off the chain of the current one
         for (int t = 0; t < bvalid; ++t) {
             const double gtt = M1[t * 33 + t], htt = M2[t * 33 + t], att = M3[t * 33 + t];
             const float root = sqrtf((float)htt);
