@@ -191,6 +191,7 @@ struct ConvArgs {
     int n_tiles, cpi, total_chunks, total_tiles;   // cpi = 32-pixel chunks per image
     int prefetch_residual;   // tmRes is valid
     int experiment;          // only read under -DGPFQ_CONV_EXPERIMENT (timing experiments that give WRONG results)
+    long long* trace;        // only under -DGPFQ_CONV_TRACE: clock64() stamps of CTA 0's roles, [event][k-block]
 };
 
 // Timing experiments, compiled in only with -DGPFQ_CONV_EXPERIMENT and selected by the bit mask GPFQ_CONV_EXPERIMENT=<n>
@@ -199,6 +200,16 @@ struct ConvArgs {
 // k-block), 2 = only the hi*hi products are issued (a third of the tensor work and of its operand reads), 4 = the drain
 // warps read half of their accumulator columns (half of the TMEM reads and fp32 adds), 8 = the split warps neither
 // load nor store (the stage goes from TMA straight to the tensor core).
+// -DGPFQ_CONV_TRACE: CTA 0 stamps clock64() at the hand-over points of its first kTraceLen k-blocks into ConvArgs::trace
+// (address in the environment variable GPFQ_CONV_TRACE_PTR, see tools/conv_trace.py): 0 stage free (producer), 1 tile
+// landed (split warp), 2 split done, 3 MMA warp ready to issue, 4 MMAs issued, 5 accumulator complete (drain warp), 6
+// accumulator drained, 7 tile's epilogue done.
+constexpr int kTraceLen = 256;
+#ifdef GPFQ_CONV_TRACE
+#define CONV_TRACE(ev, it) do { if (blockIdx.x == 0 && a.trace && (it) < kTraceLen) a.trace[(ev) * kTraceLen + (it)] = clock64(); } while (0)
+#else
+#define CONV_TRACE(ev, it) do { } while (0)
+#endif
 #ifdef GPFQ_CONV_EXPERIMENT
 #define CONV_EXPERIMENT(bit) ((a.experiment & (bit)) != 0)
 #else
@@ -302,6 +313,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
+                    CONV_TRACE(0, it);
                     float* st = tiles + (size_t)s * kStageFloats;
                     mbar_expect_tx(&full[s], (uint32_t)((2 * kATile + kBTile) * sizeof(float)));
                     const int c0 = kb * kBK;
@@ -327,6 +339,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                     mbar_wait(&acc_empty[b], (uint32_t)(((it / kAccs) & 1) ^ 1));
                     mbar_wait(&full[s], ph);       // weight planes (TMA)
                     mbar_wait(&split[s], ph);      // activation planes (split warps)
+                    CONV_TRACE(3, it);
                     tc_fence_after();
                     const float* st = tiles + (size_t)s * kStageFloats;
                     const uint64_t d_wh = desc_k_major(st), d_wl = desc_k_major(st + kATile);
@@ -354,6 +367,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                     }
                     umma_commit(&empty[s]);
                     umma_commit(&acc_full[b]);
+                    CONV_TRACE(4, it);
                 }
             }
         }
@@ -370,6 +384,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
         for (int it = 0; it < total; ++it) {
             const int s = it % kStages;
             mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+            if (t == 0) CONV_TRACE(1, it);
             float4* hi = reinterpret_cast<float4*>(tiles + (size_t)s * kStageFloats + 2 * kATile);
             float4* lo = hi + kBTile / 4;
 #pragma unroll 8
@@ -387,6 +402,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
             fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
+            if (t == 0) CONV_TRACE(2, it);
         }
     } else {
         reg_alloc<kRegsDrain>();
@@ -447,6 +463,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 // the first round's residual is requested before the wait for the tile's last accumulator
                 if (RES && kb == nkb - 1) load_residual(r, rptr, nvalid);
                 mbar_wait(&acc_full[b], (uint32_t)((it / kAccs) & 1));
+                if (threadIdx.x == kFirstDrainWarp * 32) CONV_TRACE(5, it);
                 tc_fence_after();
                 // all 16-column loads of this warp's part of the accumulator go out back to back and are waited for once
                 // (one TMEM round trip per k-block)
@@ -467,6 +484,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[b]);
+                if (threadIdx.x == kFirstDrainWarp * 32) CONV_TRACE(6, it);
             }
             // Epilogue, 16 channels at a time: the 16 residual loads go out together (L2 hits after the bulk prefetch),
             // then alpha / beta / residual / clamp in bn_act_kernel's order of operations (fmul, fadd, fadd, max, min) and
@@ -520,6 +538,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < kCols - 2 * kGroup; ++j) run[j] = run[j + 2 * kGroup];
             }
+            if (threadIdx.x == kFirstDrainWarp * 32) CONV_TRACE(7, it - 1);
         }
     }
     __syncthreads();
@@ -627,6 +646,9 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     a.prefetch_residual = 0;
 #ifdef GPFQ_CONV_EXPERIMENT
     a.experiment = getenv("GPFQ_CONV_EXPERIMENT") ? atoi(getenv("GPFQ_CONV_EXPERIMENT")) : 0;
+#endif
+#ifdef GPFQ_CONV_TRACE
+    a.trace = getenv("GPFQ_CONV_TRACE_PTR") ? (long long*)strtoull(getenv("GPFQ_CONV_TRACE_PTR"), nullptr, 0) : nullptr;
 #endif
     tmRes = tmX;                 // a valid map in any case; only dereferenced when prefetch_residual is set
     if (residual != nullptr && HW % 4 == 0) {
