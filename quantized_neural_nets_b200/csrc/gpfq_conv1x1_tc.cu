@@ -189,6 +189,7 @@ struct ConvArgs {
     float lo, hi;
     int C, N, HW, B;
     int n_tiles, cpi, total_chunks, total_tiles;   // cpi = 32-pixel chunks per image
+    uint32_t m_tiles, m_cpi; // floor(2^32 / n_tiles), floor(2^32 / cpi): divisions by multiplication (fast_div)
     int prefetch_residual;   // tmRes is valid
     int experiment;          // only read under -DGPFQ_CONV_EXPERIMENT (timing experiments that give WRONG results)
     long long* trace;        // only under -DGPFQ_CONV_TRACE: clock64() stamps of CTA 0's roles, [event][k-block]
@@ -279,15 +280,27 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constan
     // last chunk of an image may be partly empty), a tile takes four consecutive ones -- so a tile may straddle images and
     // small planes (28 x 28, 14 x 14, 7 x 7) do not leave most of their last tile empty.  Channel tiles of one pixel tile
     // are adjacent in the schedule, so CTAs that run side by side share the activation through L2.
+    // (the drain warps run these between two tiles, on their critical path: ~25 instructions per hardware division)
+    auto fast_div = [](uint32_t n, uint32_t d, uint32_t m, uint32_t& rem) {
+        uint32_t q = __umulhi(n, m);       // m = floor(2^32 / d) (2^32 - 1 for d = 1): q or q - 1
+        rem = n - q * d;
+        if (rem >= d) {
+            ++q;
+            rem -= d;
+        }
+        return q;
+    };
     auto tile_coords = [&](int i, int& q0, int& n0) {
-        const int t = worker + i * n_workers;
-        n0 = (t % a.n_tiles) * kTM;
-        q0 = (t / a.n_tiles) * (kTN / kPx);
+        uint32_t nt;
+        const uint32_t pt = fast_div((uint32_t)(worker + i * n_workers), (uint32_t)a.n_tiles, a.m_tiles, nt);
+        n0 = (int)nt * kTM;
+        q0 = (int)pt * (kTN / kPx);
     };
     // chunk index -> (image, first pixel); a chunk past the end belongs to image B (loads are zero-filled, nothing is stored)
     auto chunk_coords = [&](int q, int& img, int& p0) {
-        img = q / a.cpi;
-        p0 = (q - img * a.cpi) * kPx;
+        uint32_t c;
+        img = (int)fast_div((uint32_t)q, (uint32_t)a.cpi, a.m_cpi, c);
+        p0 = (int)c * kPx;
     };
     // channels of the tile that starts at channel n0, rounded up to 32: the N of the tile's MMAs (the weight rows beyond
     // a.N arrive as zeros) and twice the number of accumulator columns one drain warp owns
@@ -642,6 +655,8 @@ int conv1x1_tc(const float* x, int64_t x_ld, const float* W, float* out, const f
     const int64_t total = (int64_t)a.n_tiles * ceil_div(chunks, kTN / kPx);
     GPFQ_REQUIRE(chunks < (1ll << 30) && total < (1ll << 30), "conv1x1_tc: too many tiles");
     a.total_chunks = (int)chunks;
+    a.m_tiles = a.n_tiles == 1 ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / (uint32_t)a.n_tiles);
+    a.m_cpi = a.cpi == 1 ? 0xFFFFFFFFu : (uint32_t)((1ull << 32) / (uint32_t)a.cpi);
     a.total_tiles = (int)total;
     a.prefetch_residual = 0;
 #ifdef GPFQ_CONV_EXPERIMENT

@@ -59,3 +59,10 @@ for spec in sys.argv[1:]:
     n = min(len(ep), len(last_drain)) - 1
     print(f"  epilogue: last drain -> tile stored                  {med(ep[3:n] - last_drain[3:n])}")
     print(f"  tile period (drain warp)                             {med(np.diff(ep[3:n]))}")
+    first = t[5][0::nkb]                 # accumulator-complete stamp of each tile's first k-block
+    print(f"  tile stored -> next tile's first accumulator taken   {med(first[4:n + 1] - ep[3:n])}")
+    if nkb > 1:
+        inner = (t[5][1:] - t[6][:-1]).reshape(-1)
+        idx = np.array([i for i in range(lo, hi) if (i + 1) % nkb != 0])
+        print(f"  drained(kb) -> accumulator(kb+1) taken, same tile    {med(inner[idx])}")
+    print(f"  MMA warp: issue(it) done -> ready for it+1           {med(t[3][lo + 1:hi] - t[4][lo:hi - 1])}")
