@@ -15,6 +15,7 @@ Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes
+import gc
 import json
 import os
 import statistics
@@ -230,6 +231,10 @@ def run_cuda_arm(args):
                                    calibration=calibration or args.calibration,
                                    fuse_forward=args.fuse_forward if fuse is None else fuse,
                                    pointwise_gemm=args.pointwise_gemm if fuse is None else fuse)
+        # every step builds two fresh network copies and two torch.fx graphs; collect that garbage HERE, outside the timed
+        # region, so that a full (generation-2) collection of Python's cyclic GC does not land inside it (seen as one step
+        # in three taking +240 ms with the GPU idle)
+        gc.collect()
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
@@ -245,6 +250,9 @@ def run_cuda_arm(args):
         barrier()
         return start.elapsed_time(end), qnn, d2h
 
+    STEP_LOG = []      # every timed step of this rank, in order (diagnostics: which loop a slow step belongs to)
+    ALLOC_LOG = []     # cumulative (cudaMalloc calls, cudaFree calls, allocation retries) of the caching allocator after each
+
     def timed(pool, read_back, sampler=None, forward=None, warmup=None, calibration=None, fuse=None):
         for _ in range(args.warmup if warmup is None else warmup):
             one_step(pool, read_back, forward=forward, calibration=calibration, fuse=fuse)
@@ -256,6 +264,9 @@ def run_cuda_arm(args):
         for _ in range(args.steps):
             ms, qnn, d2h = one_step(pool, read_back, forward=forward, calibration=calibration, fuse=fuse)
             total += ms
+            st = torch.cuda.memory_stats(dev)
+            STEP_LOG.append(round(ms, 1))
+            ALLOC_LOG.append((st.get("num_device_alloc", 0), st.get("num_device_free", 0), st.get("num_alloc_retries", 0)))
         launches = _lib.launch_count() - before
         clocks = sampler.stop() if sampler else None
         t = torch.tensor([total], dtype=torch.float64, device=dev)
@@ -275,7 +286,18 @@ def run_cuda_arm(args):
             dist.destroy_process_group()
         return None
     total_ms, launches, clocks, qnn, _ = timed(dev_pool, False, ClockSampler(local) if rank == 0 else None)
+    value_steps = list(STEP_LOG)
     e2e_ms, _, _, qnn, d2h = timed(host_pool, True)
+    e2e_steps = STEP_LOG[len(value_steps):]
+    # the box's pinned host -> device rate (one batch): the e2e step copies `layers` batches, one per layer, prefetched one
+    # layer ahead; the first layers' prefix passes are shorter than a copy, so e2e - value grows as this rate drops
+    a_ev, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_ev.record()
+    for hb in host_pool[:4]:
+        hb.to(dev, non_blocking=True)
+    b_ev.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * img_bytes / (a_ev.elapsed_time(b_ev) * 1e-3) / 1e9
     other_ms = None
     if world > 1:   # the other multi-GPU forward mode, for the record (same K, one warm-up)
         other = "replicated" if args.forward == "sharded" else "sharded"
@@ -322,7 +344,9 @@ def run_cuda_arm(args):
             "units_per_step": units, "layers": n_layers,
             "e2e": {"value": units / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": n_layers * img_bytes, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps, "steps_ms": e2e_steps, "pinned_h2d_gbs": round(h2d_gbs, 1)},
+            "steps_ms": value_steps,
+            "allocator_after_each_step": ALLOC_LOG[:len(value_steps) + len(e2e_steps)],
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": None,      # filled below: the kernel of this library with the largest share of the step

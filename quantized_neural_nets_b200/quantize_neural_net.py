@@ -220,6 +220,8 @@ class QuantizeNeuralNet:
                 self._fused = {}
         # host -> device copy of the NEXT layer's batch runs on a copy stream while this layer computes
         self._copy_stream = None
+        self._stage_bufs = [None, None]  # persistent device buffers for host batches (see _fetch)
+        self._stage_next = 0
         self._prefetched = None      # (device images, ready event, sharded?) of the next layer
         self._layers_left = 0
         self.verbose = verbose
@@ -480,11 +482,32 @@ class QuantizeNeuralNet:
                 raise ValueError(f"shard_forward needs the batch ({B}) to be a multiple of the world size ({world})")
             shard_range = (rank * (B // world), (rank + 1) * (B // world))
             raw_input_data = raw_input_data[shard_range[0]:shard_range[1]]
+        main = torch.cuda.current_stream(self.device)
+        if raw_input_data.is_cuda:
+            images = raw_input_data.to(self.device)      # already resident (a no-op on the same device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            return images, ready, sharded, shard_range, B
+        # Host batches go through TWO persistent device buffers used alternately (layer i reads one while layer i + 1's
+        # batch lands in the other) instead of a fresh 150 MB allocation per layer: allocations made on the copy stream and
+        # handed to the main stream are recycled late by the caching allocator, which kept calling cudaMalloc -- a
+        # synchronising call -- in the middle of steps (seen as e2e steps of 1250 ... 1430 ms tracking the number of
+        # cudaMalloc calls inside them).
+        j = self._stage_next
+        self._stage_next ^= 1
+        buf = self._stage_bufs[j]
+        if buf is None or buf.shape != raw_input_data.shape or buf.dtype != raw_input_data.dtype:
+            buf = torch.empty(raw_input_data.shape, dtype=raw_input_data.dtype, device=self.device)
+            self._stage_bufs[j] = buf
+        # the buffer's previous batch (two layers back) was consumed by work already enqueued on the main stream
+        free = torch.cuda.Event()
+        free.record(main)
+        stream.wait_event(free)
         with torch.cuda.stream(stream):
-            images = raw_input_data.to(self.device, non_blocking=True)
+            buf.copy_(raw_input_data, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(stream)
-        return images, ready, sharded, shard_range, B
+        return buf, ready, sharded, shard_range, B
 
     def _next_images(self):
         """Device images of the layer about to be captured; the copy of the FOLLOWING layer's batch (the loader is
@@ -497,7 +520,6 @@ class QuantizeNeuralNet:
             images, ready, sharded, shard_range, B = self._prefetched
             self._prefetched = None
             main.wait_event(ready)
-            images.record_stream(main)
         if self._layers_left > 0:
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=self.device)
