@@ -137,6 +137,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_min_mhz": min(sm) if sm else None, "sm_mhz_samples": sm[:64],
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
