@@ -261,11 +261,13 @@ def test_pointwise_convs_as_gemm_patches_and_restores():
     assert not any('forward' in m.__dict__ for m in model.modules())
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    """The JSON line bench.py printed on the B200 for the final r01 tree (profiles/) carries every key of the bench
-    contract: metric / value / e2e / gpu_launches / clocks / roofline / cpu_baseline."""
+@pytest.mark.parametrize("name", ["r01_bench_n1_final4.json", "r02b_bench_n1_final.json"])
+def test_committed_bench_line_has_the_contract_keys(name):
+    """The JSON lines bench.py printed on the B200 for the final trees of both rounds (profiles/) carry every key of the
+    bench contract: metric / value / e2e / gpu_launches / clocks / roofline / cpu_baseline."""
     import json
-    j = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_n1_final4.json")))
+    text = open(os.path.join(ROOT, "profiles", name)).read()
+    j = json.loads(next(line for line in text.splitlines() if line.startswith("{")))
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert key in j, key
