@@ -146,7 +146,10 @@ class FusedConvBNAct(nn.Module):
     def _weight_planes(self, device, Ck):
         """TF32 hi / lo planes of the weight (gpfq_conv1x1_split_weight_f32), made once per weight VALUE: a layer runs in
         up to 106 prefix passes of a step with the same weight (the analog network's never changes, a quantized layer's
-        changes once), so the split is not repeated in front of every convolution launch."""
+        changes once), so the split is not repeated in front of every convolution launch.  The tag is (data pointer,
+        version counter, shape, device): assigning ``weight.data`` or any tracked in-place operation refreshes the planes;
+        an in-place write THROUGH ``weight.data`` (which bumps no version counter) does not -- set ``_planes = None`` after
+        one (QuantizeNeuralNet.quantize_network() does so for all its modules at the start of every run)."""
         w = self.conv.weight
         tag = (w.data_ptr(), w._version, tuple(w.shape), device)
         if self._planes is None or self._planes[1] != tag:

@@ -270,6 +270,12 @@ class QuantizeNeuralNet:
             print(f'Total number of layers to quantize {len(layers_to_quantize)}')
         deltas = self._layer_deltas(layers_to_quantize)
         self.layer_deltas = deltas             # {layer index: alphabet step}; read by export.export_packed
+        # cached TF32 planes of the convolution weights are keyed by (data pointer, version, shape); an in-place write
+        # through ``weight.data`` between two calls changes none of them, so every run starts from fresh planes
+        for gm in self._fused.values():
+            for mod in gm.modules():
+                if hasattr(mod, '_planes'):
+                    mod._planes = None
         if self.pointwise_gemm:                # 1x1 convolutions of the calibration passes as batched SGEMMs
             from .forward_fusion import pointwise_convs_as_gemm
             with pointwise_convs_as_gemm(self.analog_network, self.quantized_network):
