@@ -108,15 +108,16 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=500):
         self.index = index
+        self.interval_ms = interval_ms
         self.rows = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "500", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.interval_ms), "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -286,7 +287,7 @@ def run_cuda_arm(args):
         if world > 1:
             dist.destroy_process_group()
         return None
-    total_ms, launches, clocks, qnn, _ = timed(dev_pool, False, ClockSampler(local) if rank == 0 else None)
+    total_ms, launches, clocks, qnn, _ = timed(dev_pool, False, ClockSampler(local, 500 if world < 4 else 200) if rank == 0 else None)
     value_steps = list(STEP_LOG)
     e2e_ms, _, _, qnn, d2h = timed(host_pool, True)
     e2e_steps = STEP_LOG[len(value_steps):]
